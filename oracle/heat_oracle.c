@@ -1,0 +1,341 @@
+/*
+ * heat_oracle.c — CPU ORACLE (TEST INFRASTRUCTURE ONLY).  See heat_oracle.h for scope, the
+ * reference lines each routine restates, and the "parity unpinned" statement.
+ *
+ * Build: gcc -O2 -fopenmp -ffp-contract=off -mfma  (contraction is OFF so the element
+ * arithmetic is reproduced bit-for-bit by the CUDA path compiled with -fmad=false; the only
+ * fused operations are the explicit fma() calls in oracle_spmv).
+ */
+#include "heat_oracle.h"
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+int oracle_num_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * P1 element rows.  K_ab = vol * grad(phi_a).grad(phi_b), written as (G_a.G_b) * s with
+ * G = det * grad(phi) (cross products of edges) and s = 1/(6|det|) (tets) or 1/(2|det|) (tris).
+ * No reference counterpart (the reference assembles a graph Laplacian, ExodusIO.hpp:591-608);
+ * this is the north-star P1 operator on the reference's sparsity pattern.
+ * ------------------------------------------------------------------------------------------- */
+static void tet_G(double p[4][3], double G[4][3], double *s) {
+    double ax = p[1][0] - p[0][0], ay = p[1][1] - p[0][1], az = p[1][2] - p[0][2];
+    double bx = p[2][0] - p[0][0], by = p[2][1] - p[0][1], bz = p[2][2] - p[0][2];
+    double cx = p[3][0] - p[0][0], cy = p[3][1] - p[0][1], cz = p[3][2] - p[0][2];
+    /* G1 = b x c, G2 = c x a, G3 = a x b */
+    G[1][0] = by * cz - bz * cy; G[1][1] = bz * cx - bx * cz; G[1][2] = bx * cy - by * cx;
+    G[2][0] = cy * az - cz * ay; G[2][1] = cz * ax - cx * az; G[2][2] = cx * ay - cy * ax;
+    G[3][0] = ay * bz - az * by; G[3][1] = az * bx - ax * bz; G[3][2] = ax * by - ay * bx;
+    for (int d = 0; d < 3; ++d) G[0][d] = -((G[1][d] + G[2][d]) + G[3][d]);
+    double det = (ax * G[1][0] + ay * G[1][1]) + az * G[1][2];
+    *s = 1.0 / (6.0 * fabs(det));
+}
+
+static void tri_G(double p[4][3], double G[4][3], double *s) {
+    double ax = p[1][0] - p[0][0], ay = p[1][1] - p[0][1];
+    double bx = p[2][0] - p[0][0], by = p[2][1] - p[0][1];
+    G[1][0] = by;  G[1][1] = -bx; G[1][2] = 0.0;
+    G[2][0] = -ay; G[2][1] = ax;  G[2][2] = 0.0;
+    G[0][0] = -(G[1][0] + G[2][0]); G[0][1] = -(G[1][1] + G[2][1]); G[0][2] = 0.0;
+    G[3][0] = G[3][1] = G[3][2] = 0.0;
+    double det = ax * by - ay * bx;
+    *s = 1.0 / (2.0 * fabs(det));
+}
+
+static int cmp_i32(const void *a, const void *b) {
+    int32_t x = *(const int32_t *)a, y = *(const int32_t *)b;
+    return (x > y) - (x < y);
+}
+
+/* sorted unique neighbour nodes of g (excluding g) over its incident elements */
+static int collect_neighbours(int64_t g, const int64_t *n2e_ptr, const int64_t *n2e, int npe,
+                              const int32_t *conn, int32_t *buf) {
+    int m = 0;
+    for (int64_t q = n2e_ptr[g]; q < n2e_ptr[g + 1]; ++q) {
+        const int32_t *e = conn + n2e[q] * npe;
+        for (int k = 0; k < npe; ++k)
+            if (e[k] != g) buf[m++] = e[k];
+    }
+    qsort(buf, (size_t)m, sizeof(int32_t), cmp_i32);
+    int u = 0;
+    for (int i = 0; i < m; ++i)
+        if (u == 0 || buf[u - 1] != buf[i]) buf[u++] = buf[i];
+    return u;
+}
+
+int oracle_assemble(int64_t N, const double *x, const double *y, const double *z, int64_t ne,
+                    int npe, const int32_t *conn, const double *node_bc, int mode,
+                    oracle_system *out) {
+    memset(out, 0, sizeof(*out));
+    if (mode == ORACLE_P1_FEM && npe != 4 && npe != 3) return 1;
+    if (npe < 2 || npe > 27) return 2;
+
+    /* -- elimination: reduced id = rank among DOF nodes in ascending original id (:216-252) -- */
+    int64_t *red = (int64_t *)malloc(sizeof(int64_t) * (size_t)N);
+    int64_t n = 0;
+    for (int64_t g = 0; g < N; ++g) red[g] = isnan(node_bc[g]) ? n++ : -1;
+    int64_t *red2orig = (int64_t *)malloc(sizeof(int64_t) * (size_t)(n > 0 ? n : 1));
+    for (int64_t g = 0; g < N; ++g)
+        if (red[g] >= 0) red2orig[red[g]] = g;
+
+    /* -- node -> incident elements (ascending element id) by counting sort -- */
+    int64_t *n2e_ptr = (int64_t *)calloc((size_t)N + 1, sizeof(int64_t));
+    for (int64_t e = 0; e < ne; ++e)
+        for (int k = 0; k < npe; ++k) {
+            int32_t v = conn[e * npe + k];
+            if (v < 0 || v >= N) { free(red); free(red2orig); free(n2e_ptr); return 3; }
+            n2e_ptr[v + 1]++;
+        }
+    int64_t max_inc = 0;
+    for (int64_t g = 0; g < N; ++g) {
+        if (n2e_ptr[g + 1] > max_inc) max_inc = n2e_ptr[g + 1];
+        n2e_ptr[g + 1] += n2e_ptr[g];
+    }
+    int64_t *n2e = (int64_t *)malloc(sizeof(int64_t) * (size_t)(ne * npe > 0 ? ne * npe : 1));
+    {
+        int64_t *fill = (int64_t *)malloc(sizeof(int64_t) * (size_t)(N > 0 ? N : 1));
+        memcpy(fill, n2e_ptr, sizeof(int64_t) * (size_t)N);
+        for (int64_t e = 0; e < ne; ++e)
+            for (int k = 0; k < npe; ++k) n2e[fill[conn[e * npe + k]]++] = e;
+        free(fill);
+    }
+    const int bufcap = (int)(max_inc * (npe - 1)) + 1;
+
+    /* -- pass 1: row lengths (DOF neighbours + diagonal), :380-386 + FIXED D3 -- */
+    int64_t *row_ptr = (int64_t *)calloc((size_t)n + 1, sizeof(int64_t));
+#pragma omp parallel
+    {
+        int32_t *buf = (int32_t *)malloc(sizeof(int32_t) * (size_t)bufcap);
+#pragma omp for schedule(static)
+        for (int64_t i = 0; i < n; ++i) {
+            int64_t g = red2orig[i];
+            int u = collect_neighbours(g, n2e_ptr, n2e, npe, conn, buf);
+            int len = 1;
+            for (int t = 0; t < u; ++t)
+                if (red[buf[t]] >= 0) len++;
+            row_ptr[i + 1] = len;
+        }
+        free(buf);
+    }
+    int32_t max_row = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        if (row_ptr[i + 1] > max_row) max_row = (int32_t)row_ptr[i + 1];
+        row_ptr[i + 1] += row_ptr[i];
+    }
+    int64_t nnz = row_ptr[n];
+    int32_t *col = (int32_t *)malloc(sizeof(int32_t) * (size_t)(nnz > 0 ? nnz : 1));
+    double *val = (double *)malloc(sizeof(double) * (size_t)(nnz > 0 ? nnz : 1));
+    double *b = (double *)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
+
+    /* -- pass 2: columns, values (:591-608) and right-hand side (:671-687) -- */
+#pragma omp parallel
+    {
+        int32_t *buf = (int32_t *)malloc(sizeof(int32_t) * (size_t)bufcap);
+#pragma omp for schedule(static)
+        for (int64_t i = 0; i < n; ++i) {
+            int64_t g = red2orig[i];
+            int u = collect_neighbours(g, n2e_ptr, n2e, npe, conn, buf);
+            int32_t *c = col + row_ptr[i];
+            double *v = val + row_ptr[i];
+            int len = 0, placed = 0;
+            double bsum = 0.0;
+            for (int t = 0; t < u; ++t) {
+                int64_t r = red[buf[t]];
+                if (r >= 0) {
+                    if (!placed && r > i) { c[len++] = (int32_t)i; placed = 1; }
+                    c[len++] = (int32_t)r;
+                } else if (mode == ORACLE_GRAPH_LAPLACIAN) {
+                    bsum += node_bc[buf[t]];          /* B[i] = sum of Dirichlet nbr values */
+                }
+            }
+            if (!placed) c[len++] = (int32_t)i;
+            int dpos = 0;
+            for (int t = 0; t < len; ++t)
+                if (c[t] == i) dpos = t;
+            if (mode == ORACLE_GRAPH_LAPLACIAN) {
+                for (int t = 0; t < len; ++t) v[t] = -1.0;
+                v[dpos] = (double)u;                   /* full degree, DOF + Dirichlet (:606) */
+            } else {
+                for (int t = 0; t < len; ++t) v[t] = 0.0;
+                for (int64_t q = n2e_ptr[g]; q < n2e_ptr[g + 1]; ++q) {
+                    const int32_t *e = conn + n2e[q] * npe;
+                    double p[4][3], G[4][3], s;
+                    int a = -1;
+                    for (int k = 0; k < npe; ++k) {
+                        p[k][0] = x[e[k]]; p[k][1] = y[e[k]]; p[k][2] = z ? z[e[k]] : 0.0;
+                        if (e[k] == g && a < 0) a = k;
+                    }
+                    if (npe == 4) tet_G(p, G, &s); else tri_G(p, G, &s);
+                    for (int k = 0; k < npe; ++k) {
+                        double kab = ((G[a][0] * G[k][0] + G[a][1] * G[k][1]) + G[a][2] * G[k][2]) * s;
+                        int64_t j = e[k];
+                        if (j == g) {
+                            v[dpos] += kab;
+                        } else if (red[j] >= 0) {
+                            int32_t r = (int32_t)red[j];
+                            int lo = 0, hi = len - 1;
+                            while (lo < hi) { int mid = (lo + hi) >> 1; if (c[mid] < r) lo = mid + 1; else hi = mid; }
+                            v[lo] += kab;
+                        } else {
+                            double t2 = kab * node_bc[j];
+                            bsum = bsum - t2;
+                        }
+                    }
+                }
+            }
+            b[i] = bsum;
+        }
+        free(buf);
+    }
+    free(n2e); free(n2e_ptr); free(red);
+    out->num_nodes = N; out->n = n; out->nnz = nnz; out->row_ptr = row_ptr; out->col = col;
+    out->val = val; out->b = b; out->red2orig = red2orig; out->max_row = max_row;
+    return 0;
+}
+
+void oracle_system_free(oracle_system *s) {
+    free(s->row_ptr); free(s->col); free(s->val); free(s->b); free(s->red2orig);
+    memset(s, 0, sizeof(*s));
+}
+
+void oracle_cube_mesh(int nx, int ny, int nz, double *x, double *y, double *z, int32_t *conn,
+                      double *node_bc) {
+    static const int perms[6][3] = {{0, 1, 2}, {0, 2, 1}, {1, 0, 2}, {1, 2, 0}, {2, 0, 1}, {2, 1, 0}};
+    const int64_t sx = 1, sy = nx, sz = (int64_t)nx * ny;
+    const int64_t stride[3] = {sx, sy, sz};
+#pragma omp parallel for schedule(static)
+    for (int k = 0; k < nz; ++k)
+        for (int j = 0; j < ny; ++j)
+            for (int i = 0; i < nx; ++i) {
+                int64_t g = i + (int64_t)nx * (j + (int64_t)ny * k);
+                x[g] = -5.0 + 10.0 * (double)i / (double)(nx - 1);
+                y[g] = -5.0 + 10.0 * (double)j / (double)(ny - 1);
+                z[g] = -5.0 + 10.0 * (double)k / (double)(nz - 1);
+                node_bc[g] = (i == 0) ? 1000.0 : (i == nx - 1) ? 100.0 : NAN;
+            }
+#pragma omp parallel for schedule(static)
+    for (int ck = 0; ck < nz - 1; ++ck)
+        for (int cj = 0; cj < ny - 1; ++cj)
+            for (int ci = 0; ci < nx - 1; ++ci) {
+                int64_t cell = ci + (int64_t)(nx - 1) * (cj + (int64_t)(ny - 1) * ck);
+                int64_t v0 = ci + (int64_t)nx * (cj + (int64_t)ny * ck);
+                for (int p = 0; p < 6; ++p) {
+                    int32_t *e = conn + (cell * 6 + p) * 4;
+                    int64_t v = v0;
+                    e[0] = (int32_t)v;
+                    for (int s = 0; s < 3; ++s) { v += stride[perms[p][s]]; e[s + 1] = (int32_t)v; }
+                }
+            }
+}
+
+void oracle_spmv(int64_t n, const int64_t *row_ptr, const int32_t *col, const double *val,
+                 const double *x, double *y) {
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) {
+        double acc = 0.0;
+        for (int64_t q = row_ptr[i]; q < row_ptr[i + 1]; ++q) acc = fma(val[q], x[col[q]], acc);
+        y[i] = acc;
+    }
+}
+
+static double dot(int64_t n, const double *a, const double *b) {
+    double s = 0.0;
+#pragma omp parallel for reduction(+ : s) schedule(static)
+    for (int64_t i = 0; i < n; ++i) s += a[i] * b[i];
+    return s;
+}
+
+/* Ifpack2 Chebyshev apply, zero start: z = p_k(D^-1 A) D^-1 r */
+static void cheb_apply(int64_t n, const int64_t *rp, const int32_t *col, const double *val,
+                       const double *dinv, const double *r, double *z, double *w, double *t,
+                       int degree, double lmax, double ratio) {
+    double alpha = lmax / ratio, beta = 1.1 * lmax;
+    double delta = 2.0 / (beta - alpha), theta = 0.5 * (beta + alpha);
+    double s1 = theta * delta, rho = 1.0 / s1;
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) { w[i] = dinv[i] * r[i] / theta; z[i] = w[i]; }
+    for (int d = 1; d < degree; ++d) {
+        double rho_new = 1.0 / (2.0 * s1 - rho);
+        double c1 = rho_new * rho, c2 = 2.0 * rho_new * delta;
+        oracle_spmv(n, rp, col, val, z, t);
+#pragma omp parallel for schedule(static)
+        for (int64_t i = 0; i < n; ++i) {
+            w[i] = c1 * w[i] + c2 * (dinv[i] * (r[i] - t[i]));
+            z[i] += w[i];
+        }
+        rho = rho_new;
+    }
+}
+
+int oracle_pcg(int64_t n, const int64_t *rp, const int32_t *col, const double *val,
+               const double *b, double *x, int prec, int cheb_degree, double lmax, double ratio,
+               int max_iters, double tol, double *achieved_tol, double *res_hist) {
+    double *r = (double *)malloc(sizeof(double) * (size_t)n), *z = (double *)malloc(sizeof(double) * (size_t)n);
+    double *p = (double *)malloc(sizeof(double) * (size_t)n), *Ap = (double *)malloc(sizeof(double) * (size_t)n);
+    double *dinv = (double *)malloc(sizeof(double) * (size_t)n);
+    double *w = NULL, *t = NULL;
+    if (prec == ORACLE_PREC_CHEBYSHEV) {
+        w = (double *)malloc(sizeof(double) * (size_t)n); t = (double *)malloc(sizeof(double) * (size_t)n);
+    }
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) {
+        double d = 1.0;
+        for (int64_t q = rp[i]; q < rp[i + 1]; ++q)
+            if (col[q] == i) d = val[q];
+        dinv[i] = (prec == ORACLE_PREC_NONE) ? 1.0 : 1.0 / d;
+    }
+    oracle_spmv(n, rp, col, val, x, Ap);
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) r[i] = b[i] - Ap[i];
+    if (prec == ORACLE_PREC_CHEBYSHEV) cheb_apply(n, rp, col, val, dinv, r, z, w, t, cheb_degree, lmax, ratio);
+    else {
+#pragma omp parallel for schedule(static)
+        for (int64_t i = 0; i < n; ++i) z[i] = dinv[i] * r[i];
+    }
+    memcpy(p, z, sizeof(double) * (size_t)n);
+    double rz = dot(n, r, z), rr = dot(n, r, r), rr0 = rr;
+    int it = 0, status = 0;
+    if (res_hist) res_hist[0] = 1.0;
+    while (1) {
+        double rel = (rr0 > 0.0) ? sqrt(rr / rr0) : 0.0;
+        if (rel <= tol || it >= max_iters) break;
+        oracle_spmv(n, rp, col, val, p, Ap);
+        double pAp = dot(n, p, Ap);
+        if (!(pAp > 0.0)) { status = -1; break; }
+        double alpha = rz / pAp;
+#pragma omp parallel for schedule(static)
+        for (int64_t i = 0; i < n; ++i) { x[i] += alpha * p[i]; r[i] -= alpha * Ap[i]; }
+        if (prec == ORACLE_PREC_CHEBYSHEV) cheb_apply(n, rp, col, val, dinv, r, z, w, t, cheb_degree, lmax, ratio);
+        else {
+#pragma omp parallel for schedule(static)
+            for (int64_t i = 0; i < n; ++i) z[i] = dinv[i] * r[i];
+        }
+        double rz_new = dot(n, r, z);
+        rr = dot(n, r, r);
+        double beta = rz_new / rz;
+        rz = rz_new;
+#pragma omp parallel for schedule(static)
+        for (int64_t i = 0; i < n; ++i) p[i] = z[i] + beta * p[i];
+        ++it;
+        if (res_hist) res_hist[it] = sqrt(rr / rr0);
+    }
+    if (achieved_tol) *achieved_tol = (rr0 > 0.0) ? sqrt(rr / rr0) : 0.0;
+    free(r); free(z); free(p); free(Ap); free(dinv); free(w); free(t);
+    return status < 0 ? -1 : it;
+}
+
+void oracle_scatter_field(int64_t N, const double *node_bc, int64_t n, const int64_t *red2orig,
+                          const double *x, double *field) {
+    for (int64_t g = 0; g < N; ++g) field[g] = isnan(node_bc[g]) ? 0.0 : node_bc[g];
+    for (int64_t i = 0; i < n; ++i) field[red2orig[i]] = x[i];
+}

@@ -1,0 +1,168 @@
+"""Pins the CPU oracle (oracle/heat_oracle.c) — CPU only.
+
+The reference ships no golden vectors and cannot be built here ("parity unpinned" against the
+binary), so the pins are: the hand-checkable 3x3 system, golden numbers produced by the
+independent numpy/scipy restatement + a sparse direct solve (tests/golden/make_golden.py),
+the analytic P1 solution, structural properties, and METIS known answers."""
+import numpy as np
+import pytest
+import scipy.sparse.linalg as spl
+
+from conftest import mesh_path
+
+MESH_NAMES = ["rectangle-tris-boundary", "bolted_bracket", "tet-cube-heat", "mitchell_tri"]
+
+
+def test_hand_checked_3x3(oracle):
+    # A=[[5,0,-1],[0,4,-1],[-1,-1,5]], B=[500,450,300]
+    m = oracle.read_exodus(mesh_path("rectangle-tris-boundary"))
+    s = oracle.assemble(m, oracle.GRAPH_LAPLACIAN)
+    assert s.n == 3 and s.nnz == 7
+    np.testing.assert_array_equal(s.csr().toarray(), [[5, 0, -1], [0, 4, -1], [-1, -1, 5]])
+    np.testing.assert_array_equal(s.b, [500, 450, 300])
+    x, it, ach, _ = oracle.pcg(s, tol=1e-12)
+    np.testing.assert_allclose(x, [122.527472527472, 140.659340659340, 112.637362637362], rtol=1e-12)
+    assert it <= 3
+
+
+@pytest.mark.parametrize("name", MESH_NAMES)
+@pytest.mark.parametrize("mode_name", ["graph", "p1"])
+def test_oracle_matches_golden(oracle, golden, name, mode_name):
+    mode = oracle.GRAPH_LAPLACIAN if mode_name == "graph" else oracle.P1_FEM
+    g = golden[name][mode_name]
+    m = oracle.read_exodus(mesh_path(name))
+    s = oracle.assemble(m, mode)
+    A = s.csr()
+    assert (s.n, s.nnz) == (g["n"], g["nnz"])
+    assert A.diagonal().sum() == pytest.approx(g["trace"], rel=1e-13)
+    assert s.b.sum() == pytest.approx(g["sum_b"], rel=1e-12)
+    assert abs(A - A.T).sum() <= 1e-10 * abs(A).sum()
+    x = spl.spsolve(A.tocsc(), s.b)
+    for k, v in (("x_min", x.min()), ("x_max", x.max()), ("x_mean", x.mean()), ("x_norm2", np.linalg.norm(x))):
+        assert v == pytest.approx(g[k], rel=1e-9), k
+    np.testing.assert_allclose(x[:3], g["x_head"], rtol=1e-9)
+
+
+@pytest.mark.parametrize("name", MESH_NAMES)
+@pytest.mark.parametrize("mode", [0, 1])
+def test_c_oracle_equals_numpy_restatement(oracle, name, mode):
+    m = oracle.read_exodus(mesh_path(name))
+    s = oracle.assemble(m, mode)
+    A, b, r2o = oracle.assemble_np(m, mode)
+    Ac = s.csr()
+    np.testing.assert_array_equal(Ac.indptr, A.indptr)        # pattern bit-exact
+    np.testing.assert_array_equal(Ac.indices, A.indices)
+    np.testing.assert_array_equal(s.red2orig, r2o)
+    scale = np.abs(A.data).max()
+    if mode == 0:
+        np.testing.assert_array_equal(Ac.data, A.data)         # integer-valued
+        np.testing.assert_array_equal(s.b, b)
+    else:
+        assert np.abs(Ac.data - A.data).max() <= 1e-12 * scale
+        assert np.abs(s.b - b).max() <= 1e-12 * max(1.0, np.abs(b).max())
+
+
+def test_structural_properties_graph(oracle):
+    # symmetric; A.1 = number of Dirichlet neighbours; diag = full degree
+    m = oracle.read_exodus(mesh_path("tet-cube-heat"))
+    s = oracle.assemble(m, oracle.GRAPH_LAPLACIAN)
+    A = s.csr()
+    assert abs(A - A.T).sum() == 0
+    rowsum = np.asarray(A.sum(1)).ravel()
+    bc = s.node_bc
+    ndir = np.zeros(s.n)
+    orig2red = np.full(m.num_nodes, -1)
+    orig2red[s.red2orig] = np.arange(s.n)
+    edges = set()
+    for a in range(4):
+        for b_ in range(4):
+            if a != b_:
+                edges.update(zip(m.conn[:, a].tolist(), m.conn[:, b_].tolist()))
+    for u, v in edges:
+        if orig2red[u] >= 0 and not np.isnan(bc[v]):
+            ndir[orig2red[u]] += 1
+    np.testing.assert_array_equal(rowsum, ndir)
+    assert (A.diagonal() >= 3).all()
+
+
+def test_p1_reproduces_linear_field(oracle):
+    # exact solution T = 550 - 90 x on tet-cube-heat.exo
+    m = oracle.read_exodus(mesh_path("tet-cube-heat"))
+    s = oracle.assemble(m, oracle.P1_FEM)
+    x, it, ach, hist = oracle.pcg(s, tol=1e-12, max_iters=2000)
+    f = oracle.scatter_field(s, x)
+    assert np.abs(f - (550.0 - 90.0 * m.x)).max() < 1e-7
+    assert ach <= 1e-12
+
+
+def test_pcg_iteration_counts(oracle):
+    # BASELINE.md §2 (survey-derived): Jacobi-PCG, x0 = 0
+    expect = {("tet-cube-heat", 0): (105, 136), ("tet-cube-heat", 1): (140, 180), ("bolted_bracket", 0): (123, 137)}
+    for (name, mode), (i8, i10) in expect.items():
+        s = oracle.assemble(oracle.read_exodus(mesh_path(name)), mode)
+        assert abs(oracle.pcg(s, tol=1e-8)[1] - i8) <= 1
+        assert abs(oracle.pcg(s, tol=1e-10)[1] - i10) <= 1
+
+
+def test_bug_compat_d1(oracle, golden):
+    # the reference's off-by-one (ExodusIO.hpp:220) for 1 rank
+    m = oracle.read_exodus(mesh_path("tet-cube-heat"))
+    A, b, _ = oracle.assemble_np(m, oracle.GRAPH_LAPLACIAN, bug_compat_d1=True)
+    g = golden["tet-cube-heat"]["graph_bug_compat_d1"]
+    assert (A.shape[0], A.nnz, A.diagonal().sum()) == (19248, 274791, 260686)
+    assert abs(A - A.T).sum() == 22
+    assert g["n"] == 19248
+
+
+def test_cube_mesh_properties(oracle):
+    # SURVEY.md Appendix E
+    nx = ny = nz = 6
+    m = oracle.cube_mesh(nx, ny, nz)
+    assert m.conn.shape == (6 * 5 ** 3, 4)
+    P = np.stack([m.x, m.y, m.z], 1)[m.conn]
+    vol = np.abs(np.linalg.det(P[:, 1:] - P[:, :1])) / 6
+    assert vol.sum() == pytest.approx(1000.0, rel=1e-12)
+    s = oracle.assemble(m, oracle.GRAPH_LAPLACIAN)
+    a, b_, c = nx - 2, ny, nz
+    edges = ((a - 1) * b_ * c + a * (b_ - 1) * c + a * b_ * (c - 1) + (a - 1) * (b_ - 1) * c
+             + a * (b_ - 1) * (c - 1) + (a - 1) * b_ * (c - 1) + (a - 1) * (b_ - 1) * (c - 1))
+    assert s.n == a * b_ * c and s.nnz == s.n + 2 * edges
+    lens = np.diff(s.row_ptr)
+    assert lens.max() == 15
+    # P1 on the Kuhn cube: exactly linear T = 1000 - 900 i/(nx-1)
+    sp1 = oracle.assemble(m, oracle.P1_FEM)
+    x, *_ = oracle.pcg(sp1, tol=1e-13, max_iters=500)
+    f = oracle.scatter_field(sp1, x)
+    i = np.arange(nx * ny * nz) % nx
+    assert np.abs(f - (1000.0 - 900.0 * i / (nx - 1))).max() < 1e-8
+
+
+def test_chebyshev_pcg_converges(oracle):
+    s = oracle.assemble(oracle.read_exodus(mesh_path("bolted_bracket")), 0)
+    xj, itj, *_ = oracle.pcg(s, tol=1e-10)
+    xc, itc, *_ = oracle.pcg(s, tol=1e-10, prec=oracle.PREC_CHEBYSHEV, cheb_degree=3, cheb_lambda_max=2.0)
+    assert itc < itj
+    assert np.abs(xc - xj).max() <= 1e-7 * np.abs(xj).max()
+
+
+def test_spmv_matches_scipy(oracle):
+    s = oracle.assemble(oracle.read_exodus(mesh_path("bolted_bracket")), 1)
+    rng = np.random.default_rng(0)
+    x = rng.uniform(-1, 1, s.n)
+    np.testing.assert_allclose(oracle.spmv(s, x), s.csr() @ x, rtol=0, atol=1e-12)
+
+
+def test_metis_known_answers(oracle, golden):
+    # SURVEY.md §8c(v) with the bundled METIS and the reference's arguments (ExodusIO.hpp:1615)
+    m = oracle.read_exodus(mesh_path("rectangle-tris"))
+    obj, epart, npart = oracle.metis_part_mesh_dual(m.conn, m.num_nodes, 2, 2)
+    assert obj == 2
+    assert epart.tolist() == [0, 1, 1, 1, 0, 0, 0, 1]
+    assert npart.tolist() == [0, 0, 0, 1, 1, 1, 1, 1, 0]
+    for key, rec in golden["metis_part_mesh_dual"].items():
+        name, nparts = key.split(":")
+        mm = oracle.read_exodus(mesh_path(name))
+        ncommon = 2 if mm.conn.shape[1] == 3 else 3
+        obj, epart, npart = oracle.metis_part_mesh_dual(mm.conn, mm.num_nodes, ncommon, int(nparts))
+        assert obj == rec["objval"]
+        assert np.bincount(epart, minlength=int(nparts)).tolist() == rec["epart_hist"]
