@@ -1,0 +1,405 @@
+// cg.cu — fused vector kernels of the preconditioned CG iteration (sm_100a, HBM-bound).
+//
+// Replaces what Belos + Tpetra::MultiVector do per iteration on the reference path
+// (BelosMueLuSolver.cpp:114-133 -> MultiVector::update/dot/norm2 + Teuchos::reduceAll) with a
+// few streaming kernels: 128-bit loads/stores, warp-shuffle + last-block deterministic
+// reductions, scalars kept on the device (no host round trip inside an iteration).
+//
+// Classical PCG (HEAT_SOLVER_CG), iteration k (records H[k] = {gamma_k, -, rr_k, alpha_k}):
+//   spmv+dot :  Ap = A p ; S[PAP] = p.Ap                                   (spmv.cu)
+//   update_xr:  alpha = gamma_k / p.Ap ; x += alpha p ; r -= alpha Ap ; z = D^-1 r
+//               H[k+1].rz = r.z ; H[k+1].rr = r.r ; iters = k+1
+//   update_p :  beta = gamma_{k+1}/gamma_k ; p = D^-1 r + beta p
+// Single-reduction PCG (HEAT_SOLVER_CG_SINGLE_REDUCE, Chronopoulos-Gear):
+//   fused_update: beta, alpha from H[k], H[k-1] ; p = u + beta p ; s = w + beta s ;
+//                 x += alpha p ; r -= alpha s ; u = D^-1 r ; H[k+1].{rz,rr}
+//   spmv+dot    : w = A u ; H[k+1].delta = w.u     -> ONE all-reduce of {rz, delta, rr}
+#include "device_utils.cuh"
+#include "kernels.cuh"
+
+namespace heat {
+
+__device__ __forceinline__ bool cg_done(const CgGate &g) {
+    if (g.H == nullptr) return false;
+    if (g.I[I_STATUS] != 0) return true;
+    const double rr = g.H[g.it].rr, rr0 = g.H[0].rr;
+    return !(rr > g.S[S_TOL2] * rr0);
+}
+
+int vec_grid(int64_t n, int sm_count) {
+    int64_t blocks = (n / 2 + kBlock - 1) / kBlock;
+    return grid_for(blocks, sm_count, 8);
+}
+
+// -------------------------------------------------------------------------------------------------
+// r = b - Ax ; z = D^-1 r ; q = z (p, or u of the single-reduce variant) ; H[0] = {r.z, 0, r.r}
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) cg_init_kernel(int64_t n, const double *__restrict__ b,
+                                                         const double *__restrict__ ax,
+                                                         const double *__restrict__ dinv,
+                                                         double *__restrict__ r, double *__restrict__ q,
+                                                         CgRec *H, double *partials, int *counter) {
+    double acc[2] = {0.0, 0.0};
+    const int64_t n2 = n >> 1, stride = (int64_t)gridDim.x * kBlock;
+    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n2; i += stride) {
+        double2 bv = ld_stream_f64x2(b + 2 * i), av = ld_stream_f64x2(ax + 2 * i), dv = ld_stream_f64x2(dinv + 2 * i);
+        double2 rv = make_double2(bv.x - av.x, bv.y - av.y);
+        double2 zv = make_double2(dv.x * rv.x, dv.y * rv.y);
+        *reinterpret_cast<double2 *>(r + 2 * i) = rv;
+        *reinterpret_cast<double2 *>(q + 2 * i) = zv;
+        acc[0] += rv.x * zv.x + rv.y * zv.y;
+        acc[1] += rv.x * rv.x + rv.y * rv.y;
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        const int64_t i = n - 1;
+        double rv = b[i] - ax[i], zv = dinv[i] * rv;
+        r[i] = rv; q[i] = zv;
+        acc[0] += rv * zv; acc[1] += rv * rv;
+    }
+    double *const out[2] = {&H[0].rz, &H[0].rr};
+    grid_sum<2>(acc, partials, 0, gridDim.x, counter, out);
+}
+
+int launch_cg_init(int64_t n, const double *b, const double *ax, const double *dinv, double *r,
+                   double *q, CgRec *H, double *partials, int *counter, int grid, cudaStream_t st) {
+    cg_init_kernel<<<grid, kBlock, 0, st>>>(n, b, ax, dinv, r, q, H, partials, counter);
+    HEAT_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+// classical: x += alpha p ; r -= alpha Ap ; z = D^-1 r ; reduce r.z, r.r into H[it+1]
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) cg_update_xr_kernel(int64_t n, double *__restrict__ x,
+                                                              double *__restrict__ r,
+                                                              const double *__restrict__ p,
+                                                              const double *__restrict__ ap,
+                                                              const double *__restrict__ dinv, CgGate g,
+                                                              CgRec *H, double *S, int *I,
+                                                              double *partials, int *counter) {
+    if (cg_done(g)) return;
+    const double pap = S[S_PAP0];
+    if (!(pap > 0.0)) {                                   // Belos: "p.Ap <= 0" is a breakdown
+        if (blockIdx.x == 0 && threadIdx.x == 0) I[I_STATUS] = 2;
+        return;
+    }
+    const double alpha = H[g.it].rz / pap;
+    double acc[2] = {0.0, 0.0};
+    const int64_t n2 = n >> 1, stride = (int64_t)gridDim.x * kBlock;
+    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n2; i += stride) {
+        double2 pv = ld_stream_f64x2(p + 2 * i), av = ld_stream_f64x2(ap + 2 * i), dv = ld_stream_f64x2(dinv + 2 * i);
+        double2 xv = *reinterpret_cast<const double2 *>(x + 2 * i);
+        double2 rv = *reinterpret_cast<const double2 *>(r + 2 * i);
+        xv.x = fma(alpha, pv.x, xv.x); xv.y = fma(alpha, pv.y, xv.y);
+        rv.x = fma(-alpha, av.x, rv.x); rv.y = fma(-alpha, av.y, rv.y);
+        *reinterpret_cast<double2 *>(x + 2 * i) = xv;
+        *reinterpret_cast<double2 *>(r + 2 * i) = rv;
+        acc[0] += (dv.x * rv.x) * rv.x + (dv.y * rv.y) * rv.y;
+        acc[1] += rv.x * rv.x + rv.y * rv.y;
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        const int64_t i = n - 1;
+        double xv = fma(alpha, p[i], x[i]), rv = fma(-alpha, ap[i], r[i]);
+        x[i] = xv; r[i] = rv;
+        acc[0] += (dinv[i] * rv) * rv; acc[1] += rv * rv;
+    }
+    double *const out[2] = {&H[g.it + 1].rz, &H[g.it + 1].rr};
+    if (grid_sum<2>(acc, partials, 0, gridDim.x, counter, out)) {
+        H[g.it].alpha = alpha;
+        I[I_ITERS] = g.it + 1;
+    }
+}
+
+int launch_cg_update_xr(int64_t n, double *x, double *r, const double *p, const double *ap,
+                        const double *dinv, CgGate gate, CgRec *H, double *S, int *I,
+                        double *partials, int *counter, int grid, cudaStream_t st) {
+    cg_update_xr_kernel<<<grid, kBlock, 0, st>>>(n, x, r, p, ap, dinv, gate, H, S, I, partials, counter);
+    HEAT_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// classical: p = D^-1 r + beta p, beta = gamma_{it+1} / gamma_it
+__global__ void __launch_bounds__(kBlock) cg_update_p_kernel(int64_t n, double *__restrict__ p,
+                                                             const double *__restrict__ r,
+                                                             const double *__restrict__ dinv, CgGate g) {
+    if (cg_done(g)) return;
+    CgGate nxt = g; nxt.it = g.it + 1;
+    if (cg_done(nxt)) return;                              // converged: p is never used again
+    const double beta = g.H[g.it + 1].rz / g.H[g.it].rz;
+    const int64_t n2 = n >> 1, stride = (int64_t)gridDim.x * kBlock;
+    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n2; i += stride) {
+        double2 rv = ld_stream_f64x2(r + 2 * i), dv = ld_stream_f64x2(dinv + 2 * i);
+        double2 pv = *reinterpret_cast<const double2 *>(p + 2 * i);
+        pv.x = fma(beta, pv.x, dv.x * rv.x); pv.y = fma(beta, pv.y, dv.y * rv.y);
+        *reinterpret_cast<double2 *>(p + 2 * i) = pv;
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        const int64_t i = n - 1;
+        p[i] = fma(beta, p[i], dinv[i] * r[i]);
+    }
+}
+
+int launch_cg_update_p(int64_t n, double *p, const double *r, const double *dinv, CgGate gate,
+                       int grid, cudaStream_t st) {
+    cg_update_p_kernel<<<grid, kBlock, 0, st>>>(n, p, r, dinv, gate);
+    HEAT_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+// single-reduce (Chronopoulos-Gear): all vector work of an iteration in one pass
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) cg_fused_update_kernel(int64_t n, double *__restrict__ x,
+                                                                 double *__restrict__ r,
+                                                                 double *__restrict__ p,
+                                                                 double *__restrict__ s,
+                                                                 double *__restrict__ u,
+                                                                 const double *__restrict__ w,
+                                                                 const double *__restrict__ dinv,
+                                                                 CgGate g, CgRec *H, int *I,
+                                                                 double *partials, int *counter) {
+    if (cg_done(g)) return;
+    const double gamma = H[g.it].rz, delta = H[g.it].delta;
+    double beta = 0.0, denom = delta;
+    if (g.it > 0) {
+        beta = gamma / H[g.it - 1].rz;
+        denom = delta - beta * gamma / H[g.it - 1].alpha;
+    }
+    if (!(denom > 0.0)) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) I[I_STATUS] = 2;
+        return;
+    }
+    const double alpha = gamma / denom;
+    double acc[2] = {0.0, 0.0};
+    const int64_t n2 = n >> 1, stride = (int64_t)gridDim.x * kBlock;
+    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n2; i += stride) {
+        double2 wv = ld_stream_f64x2(w + 2 * i), dv = ld_stream_f64x2(dinv + 2 * i);
+        double2 uv = *reinterpret_cast<const double2 *>(u + 2 * i);
+        double2 pv = *reinterpret_cast<const double2 *>(p + 2 * i);
+        double2 sv = *reinterpret_cast<const double2 *>(s + 2 * i);
+        double2 xv = *reinterpret_cast<const double2 *>(x + 2 * i);
+        double2 rv = *reinterpret_cast<const double2 *>(r + 2 * i);
+        pv.x = fma(beta, pv.x, uv.x); pv.y = fma(beta, pv.y, uv.y);
+        sv.x = fma(beta, sv.x, wv.x); sv.y = fma(beta, sv.y, wv.y);
+        xv.x = fma(alpha, pv.x, xv.x); xv.y = fma(alpha, pv.y, xv.y);
+        rv.x = fma(-alpha, sv.x, rv.x); rv.y = fma(-alpha, sv.y, rv.y);
+        uv.x = dv.x * rv.x; uv.y = dv.y * rv.y;
+        *reinterpret_cast<double2 *>(p + 2 * i) = pv;
+        *reinterpret_cast<double2 *>(s + 2 * i) = sv;
+        *reinterpret_cast<double2 *>(x + 2 * i) = xv;
+        *reinterpret_cast<double2 *>(r + 2 * i) = rv;
+        *reinterpret_cast<double2 *>(u + 2 * i) = uv;
+        acc[0] += rv.x * uv.x + rv.y * uv.y;
+        acc[1] += rv.x * rv.x + rv.y * rv.y;
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        const int64_t i = n - 1;
+        double pv = fma(beta, p[i], u[i]), sv = fma(beta, s[i], w[i]);
+        double xv = fma(alpha, pv, x[i]), rv = fma(-alpha, sv, r[i]), uv = dinv[i] * rv;
+        p[i] = pv; s[i] = sv; x[i] = xv; r[i] = rv; u[i] = uv;
+        acc[0] += rv * uv; acc[1] += rv * rv;
+    }
+    double *const out[2] = {&H[g.it + 1].rz, &H[g.it + 1].rr};
+    if (grid_sum<2>(acc, partials, 0, gridDim.x, counter, out)) {
+        H[g.it].alpha = alpha;
+        I[I_ITERS] = g.it + 1;
+    }
+}
+
+int launch_cg_fused_update(int64_t n, double *x, double *r, double *p, double *s, double *u,
+                           const double *w, const double *dinv, CgGate gate, CgRec *H, int *I,
+                           double *partials, int *counter, int grid, cudaStream_t st) {
+    cg_fused_update_kernel<<<grid, kBlock, 0, st>>>(n, x, r, p, s, u, w, dinv, gate, H, I, partials, counter);
+    HEAT_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+// generic pieces (Chebyshev-preconditioned CG, residual checks)
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) axpby_kernel(int64_t n, double a, const double *__restrict__ x,
+                                                       double b, double *__restrict__ y) {
+    const int64_t stride = (int64_t)gridDim.x * kBlock;
+    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += stride)
+        y[i] = (b == 0.0) ? a * x[i] : fma(a, x[i], b * y[i]);
+}
+int launch_axpby(int64_t n, double a, const double *x, double b, double *y, int grid, cudaStream_t st) {
+    axpby_kernel<<<grid, kBlock, 0, st>>>(n, a, x, b, y);
+    HEAT_CUDA(cudaGetLastError());
+    return 0;
+}
+
+__global__ void __launch_bounds__(kBlock) dot2_kernel(int64_t n, const double *__restrict__ a,
+                                                      const double *__restrict__ b,
+                                                      const double *__restrict__ c,
+                                                      const double *__restrict__ d, double *out_ab,
+                                                      double *out_cd, double *partials, int *counter) {
+    double acc[2] = {0.0, 0.0};
+    const int64_t stride = (int64_t)gridDim.x * kBlock;
+    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += stride) {
+        acc[0] += a[i] * b[i];
+        acc[1] += c[i] * d[i];
+    }
+    double *const out[2] = {out_ab, out_cd};
+    grid_sum<2>(acc, partials, 0, gridDim.x, counter, out);
+}
+int launch_dot2(int64_t n, const double *a, const double *b, const double *c, const double *d,
+                double *out_ab, double *out_cd, double *partials, int *counter, int grid, cudaStream_t st) {
+    dot2_kernel<<<grid, kBlock, 0, st>>>(n, a, b, c, d, out_ab, out_cd, partials, counter);
+    HEAT_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// Ifpack2 Chebyshev, zero start: W = D^-1 r / theta ; Z = W
+__global__ void __launch_bounds__(kBlock) cheb_first_kernel(int64_t n, const double *__restrict__ dinv,
+                                                            const double *__restrict__ r, double inv_theta,
+                                                            double *__restrict__ w, double *__restrict__ z,
+                                                            CgGate g) {
+    if (cg_done(g)) return;
+    const int64_t stride = (int64_t)gridDim.x * kBlock;
+    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += stride) {
+        double v = dinv[i] * r[i] * inv_theta;
+        w[i] = v; z[i] = v;
+    }
+}
+int launch_cheb_first(int64_t n, const double *dinv, const double *r, double inv_theta, double *w,
+                      double *z, CgGate gate, int grid, cudaStream_t st) {
+    cheb_first_kernel<<<grid, kBlock, 0, st>>>(n, dinv, r, inv_theta, w, z, gate);
+    HEAT_CUDA(cudaGetLastError());
+    return 0;
+}
+// W = c1 W + c2 D^-1 (r - A Z) ; Z += W
+__global__ void __launch_bounds__(kBlock) cheb_step_kernel(int64_t n, const double *__restrict__ dinv,
+                                                           const double *__restrict__ r,
+                                                           const double *__restrict__ az, double c1, double c2,
+                                                           double *__restrict__ w, double *__restrict__ z,
+                                                           CgGate g) {
+    if (cg_done(g)) return;
+    const int64_t stride = (int64_t)gridDim.x * kBlock;
+    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += stride) {
+        double v = c1 * w[i] + c2 * (dinv[i] * (r[i] - az[i]));
+        w[i] = v; z[i] += v;
+    }
+}
+int launch_cheb_step(int64_t n, const double *dinv, const double *r, const double *az, double c1,
+                     double c2, double *w, double *z, CgGate gate, int grid, cudaStream_t st) {
+    cheb_step_kernel<<<grid, kBlock, 0, st>>>(n, dinv, r, az, c1, c2, w, z, gate);
+    HEAT_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// x += alpha p ; r -= alpha Ap (no reduction; z comes from a separate preconditioner apply)
+__global__ void __launch_bounds__(kBlock) cg_xr_plain_kernel(int64_t n, double *__restrict__ x,
+                                                             double *__restrict__ r,
+                                                             const double *__restrict__ p,
+                                                             const double *__restrict__ ap, CgGate g,
+                                                             double *S, int *I) {
+    if (cg_done(g)) return;
+    const double pap = S[S_PAP0];
+    if (!(pap > 0.0)) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) I[I_STATUS] = 2;
+        return;
+    }
+    const double alpha = g.H[g.it].rz / pap;
+    const int64_t stride = (int64_t)gridDim.x * kBlock;
+    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += stride) {
+        x[i] = fma(alpha, p[i], x[i]);
+        r[i] = fma(-alpha, ap[i], r[i]);
+    }
+}
+int launch_cg_xr_plain(int64_t n, double *x, double *r, const double *p, const double *ap,
+                       CgGate gate, double *S, int *I, int grid, cudaStream_t st) {
+    cg_xr_plain_kernel<<<grid, kBlock, 0, st>>>(n, x, r, p, ap, gate, S, I);
+    HEAT_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// H[it+1] = {r.z, -, r.r} ; iters = it+1   (gated: a frozen solve must not write records)
+__global__ void __launch_bounds__(kBlock) cg_dots_kernel(int64_t n, const double *__restrict__ r,
+                                                         const double *__restrict__ z, CgGate g, CgRec *H,
+                                                         int *I, double *partials, int *counter) {
+    if (cg_done(g)) return;
+    double acc[2] = {0.0, 0.0};
+    const int64_t stride = (int64_t)gridDim.x * kBlock;
+    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += stride) {
+        const double rv = r[i];
+        acc[0] += rv * z[i];
+        acc[1] += rv * rv;
+    }
+    double *const out[2] = {&H[g.it + 1].rz, &H[g.it + 1].rr};
+    if (grid_sum<2>(acc, partials, 0, gridDim.x, counter, out)) I[I_ITERS] = g.it + 1;
+}
+int launch_cg_dots(int64_t n, const double *r, const double *z, CgGate gate, CgRec *H, int *I,
+                   double *partials, int *counter, int grid, cudaStream_t st) {
+    cg_dots_kernel<<<grid, kBlock, 0, st>>>(n, r, z, gate, H, I, partials, counter);
+    HEAT_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// p = z + beta p
+__global__ void __launch_bounds__(kBlock) cg_p_plain_kernel(int64_t n, double *__restrict__ p,
+                                                            const double *__restrict__ z, CgGate g) {
+    if (cg_done(g)) return;
+    CgGate nxt = g; nxt.it = g.it + 1;
+    if (cg_done(nxt)) return;
+    const double beta = g.H[g.it + 1].rz / g.H[g.it].rz;
+    const int64_t stride = (int64_t)gridDim.x * kBlock;
+    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += stride) p[i] = fma(beta, p[i], z[i]);
+}
+int launch_cg_p_plain(int64_t n, double *p, const double *z, CgGate gate, int grid, cudaStream_t st) {
+    cg_p_plain_kernel<<<grid, kBlock, 0, st>>>(n, p, z, gate);
+    HEAT_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+__global__ void fill_kernel(int64_t n, double *x, double v) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) x[i] = v;
+}
+int launch_fill(int64_t n, double *x, double v, cudaStream_t st) {
+    if (n <= 0) return 0;
+    int grid = (int)((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096);
+    fill_kernel<<<grid, 256, 0, st>>>(n, x, v);
+    HEAT_CUDA(cudaGetLastError());
+    return 0;
+}
+
+__device__ __forceinline__ uint64_t splitmix64(uint64_t z) {
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+// x[i] = U(-1,1) keyed on the global reduced id: GPU-count invariant input
+__global__ void fill_hash_kernel(int64_t n, double *x, const int64_t *gids, int64_t gid0, uint64_t seed) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        uint64_t g = (uint64_t)(gids ? gids[i] : gid0 + i);
+        uint64_t h = splitmix64(g ^ (0x9E3779B97F4A7C15ull * seed));
+        x[i] = (double)(h >> 11) * (1.0 / 9007199254740992.0) * 2.0 - 1.0;
+    }
+}
+int launch_fill_hash(int64_t n, double *x, const int64_t *gids, int64_t gid0, uint64_t seed, cudaStream_t st) {
+    if (n <= 0) return 0;
+    int grid = (int)((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096);
+    fill_hash_kernel<<<grid, 256, 0, st>>>(n, x, gids, gid0, seed);
+    HEAT_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// halo pack: out[i] = x[idx[i]]
+__global__ void gather_kernel(int64_t n, const double *__restrict__ x, const int32_t *__restrict__ idx,
+                              double *__restrict__ out) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = x[idx[i]];
+}
+int launch_gather(int64_t n, const double *x, const int32_t *idx, double *out, cudaStream_t st) {
+    if (n <= 0) return 0;
+    int grid = (int)((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184);
+    gather_kernel<<<grid, 256, 0, st>>>(n, x, idx, out);
+    HEAT_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace heat

@@ -1,0 +1,175 @@
+// common.cuh — shared declarations of libheat_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <map>
+
+#include "../../include/heat_b200.h"
+
+namespace heat {
+
+void set_error(const char *fmt, ...);
+
+#define HEAT_CUDA(call)                                                                          \
+    do {                                                                                         \
+        cudaError_t e__ = (call);                                                                \
+        if (e__ != cudaSuccess) {                                                                \
+            heat::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            return 100;                                                                          \
+        }                                                                                        \
+    } while (0)
+
+#define HEAT_TRY(call)                                                                           \
+    do {                                                                                         \
+        int rc__ = (call);                                                                       \
+        if (rc__ != 0) return rc__;                                                              \
+    } while (0)
+
+#define HEAT_FAIL(code, ...)                                                                     \
+    do {                                                                                         \
+        heat::set_error(__VA_ARGS__);                                                            \
+        return (code);                                                                           \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// device buffer (cudaMalloc owned)
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    DevBuf &operator=(DevBuf &&o) noexcept {
+        if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+        return *this;
+    }
+    ~DevBuf() { release(); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr; n = 0;
+    }
+    int alloc(size_t count) {
+        release();
+        if (count == 0) count = 1;
+        cudaError_t e = cudaMalloc((void **)&p, count * sizeof(T));
+        if (e != cudaSuccess) {
+            p = nullptr;
+            set_error("cudaMalloc(%zu bytes) failed: %s", count * sizeof(T), cudaGetErrorString(e));
+            return 101;
+        }
+        n = count;
+        return 0;
+    }
+};
+
+constexpr int kSellRowsPerLane = 2;                      // R
+constexpr int kSellChunk = 32 * kSellRowsPerLane;        // C: rows per SELL slice (one warp)
+constexpr int kMaxPartials = 4096;                       // per-launch block partials capacity
+
+// scalar slots of the CG state (device doubles)
+enum {
+    S_RZ0 = 0, S_RZ1 = 1,        // gamma = r.z, ping-pong by iteration parity
+    S_PAP0 = 2, S_PAP1 = 3,      // delta = p.Ap (classical) / w.u (single-reduce), ping-pong
+    S_ALPHA0 = 4, S_ALPHA1 = 5,  // alpha ping-pong (single-reduce variant)
+    S_RR = 6,                    // ||r||^2 (current)
+    S_RR0 = 7,                   // ||r0||^2
+    S_TOL2 = 8,                  // tol^2
+    S_TMP0 = 9, S_TMP1 = 10, S_TMP2 = 11,
+    S_COUNT = 16
+};
+enum { I_ITERS = 0, I_STATUS = 1, I_COUNTER = 2, I_COUNTER2 = 3, I_COUNT = 8 };
+
+}  // namespace heat
+
+struct heat_vector {
+    heat_ctx *ctx = nullptr;
+    int64_t n_owned = 0, n_ghost = 0;
+    heat::DevBuf<double> d;     // [n_owned + n_ghost]
+};
+
+struct HaloPlan {
+    int n_neighbors = 0;
+    std::vector<int32_t> nbr_rank;
+    std::vector<int64_t> send_ptr;   // [n_neighbors+1]
+    std::vector<int32_t> send_idx;   // local owned row ids, concatenated by neighbour
+    std::vector<int64_t> recv_ptr;   // [n_neighbors+1] offsets into the ghost segment
+    heat::DevBuf<int32_t> d_send_idx;
+    heat::DevBuf<double> d_send_buf;
+};
+
+struct heat_matrix {
+    heat_ctx *ctx = nullptr;
+    int op_mode = 0;
+    int64_t n_global = 0, nnz_global = 0;
+    int64_t n_owned = 0, n_ghost = 0, nnz = 0;
+    int32_t max_row_len = 0;
+    // local CSR (kept for export / parity; columns are LOCAL ids: owned first, then ghosts)
+    heat::DevBuf<int64_t> row_ptr;
+    heat::DevBuf<int32_t> col;
+    heat::DevBuf<double> val;
+    // SELL-C (C = kSellChunk, R rows per lane), the SpMV format
+    int64_t n_slices = 0, sell_padded = 0;
+    heat::DevBuf<int64_t> slice_ptr;     // [n_slices+1] entry offsets
+    heat::DevBuf<int32_t> sell_col;
+    heat::DevBuf<double> sell_val;
+    heat::DevBuf<int32_t> slices_interior, slices_boundary;   // slice id lists (multi-GPU overlap)
+    int64_t n_int_slices = 0, n_bnd_slices = 0;
+    heat::DevBuf<double> dinv;           // 1/diag (owned)
+    heat::DevBuf<double> diag;
+    // maps
+    std::vector<int64_t> owned_gids, ghost_gids, red2orig_owned;
+    std::vector<int32_t> ghost_owner;
+    bool owned_contiguous = true;        // owned gids = gid0 .. gid0+n_owned-1
+    int64_t gid0 = 0;
+    heat::DevBuf<int64_t> d_owned_gids;  // only when !owned_contiguous
+    HaloPlan halo;
+    // solver workspace (lazily allocated)
+    heat::DevBuf<double> w_r, w_p, w_ap, w_s, w_u, w_t, w_w;
+    heat::DevBuf<double> partials;       // [2 * kMaxPartials * 4]
+    heat::DevBuf<double> scal;           // [S_COUNT]
+    heat::DevBuf<int> iscal;             // [I_COUNT]
+    double assemble_ms = 0.0;
+};
+
+struct ExoFile;   // exodus.hpp
+
+struct HostMesh {
+    bool valid = false;
+    bool is_cube = false;
+    bool cube_explicit = false;
+    int nx = 0, ny = 0, nz = 0;
+    int64_t num_nodes = 0, num_elem = 0;
+    int num_dim = 3, npe = 0;
+    std::vector<double> x, y, z;
+    std::vector<int32_t> conn;                       // 0-based [num_elem][npe]
+    std::map<int64_t, std::vector<int64_t>> nodesets; // id -> 0-based nodes (nodeSetMap, ExodusIO.hpp:2088)
+    std::string elem_type;
+};
+
+struct heat_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    cudaStream_t comm_stream = nullptr;
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_halo = nullptr, ev_pack = nullptr;
+    int rank = 0, nranks = 1;
+    void *nccl_comm = nullptr;           // ncclComm_t
+    HostMesh mesh;
+    ExoFile *read_file = nullptr;        // readFID  (ExodusIO.hpp:2082)
+    ExoFile *write_file = nullptr;       // writeFID (ExodusIO.hpp:2083)
+    std::string write_path;
+    bool printed_time_zero = false;      // printedTimeZero (ExodusIO.hpp:2084)
+    // state cached by assemble for writeSolution (ExodusIO.hpp:2086-2098)
+    std::vector<double> node_bc;         // NaN for DOF nodes, else lowest nodeset id
+    std::vector<double> node_bc_hi;      // highest nodeset id (reference output rule, :1983-1989)
+    int64_t n_global = 0;
+    std::vector<int64_t> owned_gids;     // reduced global ids of this rank's rows (globalIDMap keys, :2092-2098)
+};

@@ -1,0 +1,61 @@
+// kernels.cuh — launch interfaces of the sm_100a kernels (definitions in *.cu).
+#pragma once
+#include "common.cuh"
+
+namespace heat {
+
+// One record per CG iteration k: gamma_k = r_k.z_k, delta_k (single-reduce: w_k.u_k),
+// rr_k = ||r_k||^2, alpha_k.  Records are zero-initialised; an unwritten record (rr == 0) reads
+// as "converged", which freezes every later launch once the stopping test fires.
+struct CgRec { double rz, delta, rr, alpha; };
+
+struct CgGate {               // stopping test evaluated by every block of every CG kernel
+    const CgRec *H;           // iteration records
+    const double *S;          // scalars (S_TOL2)
+    const int *I;             // I_STATUS
+    int it;                   // iteration this launch belongs to
+};
+
+struct DotOut {               // where a fused dot product is reduced to
+    double *partials; int part_offset; int total_blocks; int *counter; double *out;
+};
+
+// ---- sell.cu ----
+int sell_from_csr(heat_matrix *A, cudaStream_t st);
+// ---- spmv.cu ----
+// y = A x over `n_list` slices (slice_list == nullptr: slices 0..n_list-1).  gate.H == nullptr
+// disables the CG stopping test; dot.out == nullptr disables the fused sum_i y_i * x_i.
+int launch_spmv(const heat_matrix *A, const double *x, double *y, const int32_t *slice_list,
+                int64_t n_list, CgGate gate, DotOut dot, int grid, cudaStream_t st);
+int spmv_grid(int64_t n_list, int sm_count);
+// ---- cg.cu ----
+int launch_cg_init(int64_t n, const double *b, const double *ax, const double *dinv, double *r,
+                   double *p_or_u, CgRec *H, double *partials, int *counter, int grid, cudaStream_t st);
+int launch_cg_update_xr(int64_t n, double *x, double *r, const double *p, const double *ap,
+                        const double *dinv, CgGate gate, CgRec *H, double *S, int *I,
+                        double *partials, int *counter, int grid, cudaStream_t st);
+int launch_cg_update_p(int64_t n, double *p, const double *r, const double *dinv, CgGate gate,
+                       int grid, cudaStream_t st);
+int launch_cg_fused_update(int64_t n, double *x, double *r, double *p, double *s, double *u,
+                           const double *w, const double *dinv, CgGate gate, CgRec *H, int *I,
+                           double *partials, int *counter, int grid, cudaStream_t st);
+// generic pieces for the Chebyshev path / residual
+int launch_axpby(int64_t n, double a, const double *x, double b, double *y, int grid, cudaStream_t st);
+int launch_dot2(int64_t n, const double *a, const double *b, const double *c, const double *d,
+                double *out_ab, double *out_cd, double *partials, int *counter, int grid, cudaStream_t st);
+int launch_cheb_first(int64_t n, const double *dinv, const double *r, double inv_theta, double *w,
+                      double *z, CgGate gate, int grid, cudaStream_t st);
+int launch_cheb_step(int64_t n, const double *dinv, const double *r, const double *az, double c1,
+                     double c2, double *w, double *z, CgGate gate, int grid, cudaStream_t st);
+int launch_cg_xr_plain(int64_t n, double *x, double *r, const double *p, const double *ap,
+                       CgGate gate, double *S, int *I, int grid, cudaStream_t st);
+int launch_cg_p_plain(int64_t n, double *p, const double *z, CgGate gate, int grid, cudaStream_t st);
+int launch_cg_dots(int64_t n, const double *r, const double *z, CgGate gate, CgRec *H, int *I,
+                   double *partials, int *counter, int grid, cudaStream_t st);
+int launch_fill(int64_t n, double *x, double v, cudaStream_t st);
+int launch_fill_hash(int64_t n, double *x, const int64_t *gids, int64_t gid0, uint64_t seed, cudaStream_t st);
+int launch_gather(int64_t n, const double *x, const int32_t *idx, double *out, cudaStream_t st);
+int launch_extract_diag(const heat_matrix *A, cudaStream_t st);
+int vec_grid(int64_t n, int sm_count);
+
+}  // namespace heat

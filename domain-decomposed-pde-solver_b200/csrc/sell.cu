@@ -1,0 +1,130 @@
+// sell.cu — local CSR -> SELL-C (C = 64, 2 rows per lane) conversion, diagonal extraction and the
+// interior / boundary slice split used to overlap the halo exchange with the interior SpMV.
+// (Role of Tpetra::CrsMatrix::fillComplete's local-matrix + Import set-up, ExodusIO.hpp:609.)
+#include <cub/cub.cuh>
+
+#include "device_utils.cuh"
+#include "kernels.cuh"
+
+namespace heat {
+
+// one thread per slice: width = longest row of the slice
+__global__ void sell_width_kernel(const int64_t *__restrict__ row_ptr, int64_t n_rows, int64_t n_slices,
+                                  int64_t *__restrict__ slice_entries) {
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_slices) return;
+    const int64_t r0 = s * kSellChunk;
+    const int64_t r1 = (r0 + kSellChunk < n_rows) ? r0 + kSellChunk : n_rows;
+    int64_t w = 0;
+    for (int64_t r = r0; r < r1; ++r) {
+        int64_t len = row_ptr[r + 1] - row_ptr[r];
+        w = len > w ? len : w;
+    }
+    slice_entries[s] = w * kSellChunk;
+}
+
+// one warp per slice: lane owns rows 2*lane, 2*lane+1; padding = (value 0, column = own row)
+__global__ void __launch_bounds__(kBlock)
+sell_fill_kernel(const int64_t *__restrict__ row_ptr, const int32_t *__restrict__ col,
+                 const double *__restrict__ val, int64_t n_rows, int64_t n_owned_cols, int64_t n_slices,
+                 const int64_t *__restrict__ slice_ptr, int32_t *__restrict__ scol,
+                 double *__restrict__ sval, int32_t *__restrict__ slice_is_boundary) {
+    const int lane = threadIdx.x & 31;
+    const int64_t s = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    if (s >= n_slices) return;
+    const int64_t base = slice_ptr[s];
+    const int w = (int)((slice_ptr[s + 1] - base) >> 6);
+    const int64_t row0 = s * kSellChunk + 2 * lane, row1 = row0 + 1;
+    int64_t b0 = 0, l0 = 0, b1 = 0, l1 = 0;
+    if (row0 < n_rows) { b0 = row_ptr[row0]; l0 = row_ptr[row0 + 1] - b0; }
+    if (row1 < n_rows) { b1 = row_ptr[row1]; l1 = row_ptr[row1 + 1] - b1; }
+    const int32_t pad0 = row0 < n_rows ? (int32_t)row0 : 0, pad1 = row1 < n_rows ? (int32_t)row1 : 0;
+    int ghost = 0;
+    for (int k = 0; k < w; ++k) {
+        int32_t c0 = pad0, c1 = pad1;
+        double v0 = 0.0, v1 = 0.0;
+        if (k < l0) { c0 = col[b0 + k]; v0 = val[b0 + k]; }
+        if (k < l1) { c1 = col[b1 + k]; v1 = val[b1 + k]; }
+        ghost |= (c0 >= n_owned_cols) | (c1 >= n_owned_cols);
+        const int64_t o = base + (int64_t)k * kSellChunk + 2 * lane;
+        *reinterpret_cast<int2 *>(scol + o) = make_int2(c0, c1);
+        *reinterpret_cast<double2 *>(sval + o) = make_double2(v0, v1);
+    }
+    ghost = __any_sync(0xffffffffu, ghost);
+    if (lane == 0 && slice_is_boundary) slice_is_boundary[s] = ghost;
+}
+
+__global__ void extract_diag_kernel(const int64_t *__restrict__ row_ptr, const int32_t *__restrict__ col,
+                                    const double *__restrict__ val, int64_t n_rows, double *__restrict__ diag,
+                                    double *__restrict__ dinv) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rows) return;
+    double d = 0.0;
+    for (int64_t q = row_ptr[r]; q < row_ptr[r + 1]; ++q)
+        if (col[q] == r) d = val[q];
+    diag[r] = d;
+    dinv[r] = 1.0 / d;
+}
+
+int launch_extract_diag(const heat_matrix *A, cudaStream_t st) {
+    if (A->n_owned == 0) return 0;
+    const int64_t n = A->n_owned;
+    extract_diag_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(A->row_ptr.p, A->col.p, A->val.p, n,
+                                                                    A->diag.p, A->dinv.p);
+    HEAT_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int sell_from_csr(heat_matrix *A, cudaStream_t st) {
+    const int64_t n = A->n_owned;
+    A->n_slices = (n + kSellChunk - 1) / kSellChunk;
+    const int64_t ns = A->n_slices;
+    HEAT_TRY(A->slice_ptr.alloc((size_t)ns + 1));
+    HEAT_TRY(A->diag.alloc((size_t)n));
+    HEAT_TRY(A->dinv.alloc((size_t)n));
+    HEAT_CUDA(cudaMemsetAsync(A->slice_ptr.p, 0, sizeof(int64_t) * (size_t)(ns + 1), st));
+    if (ns > 0) {
+        DevBuf<int64_t> entries;
+        HEAT_TRY(entries.alloc((size_t)ns));
+        sell_width_kernel<<<(unsigned)((ns + 255) / 256), 256, 0, st>>>(A->row_ptr.p, n, ns, entries.p);
+        HEAT_CUDA(cudaGetLastError());
+        size_t tmp_bytes = 0;
+        HEAT_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, entries.p, A->slice_ptr.p + 1, ns, st));
+        DevBuf<char> tmp;
+        HEAT_TRY(tmp.alloc(tmp_bytes));
+        HEAT_CUDA(cub::DeviceScan::InclusiveSum(tmp.p, tmp_bytes, entries.p, A->slice_ptr.p + 1, ns, st));
+        HEAT_CUDA(cudaMemcpyAsync(&A->sell_padded, A->slice_ptr.p + ns, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        HEAT_CUDA(cudaStreamSynchronize(st));
+        HEAT_TRY(A->sell_col.alloc((size_t)A->sell_padded));
+        HEAT_TRY(A->sell_val.alloc((size_t)A->sell_padded));
+        DevBuf<int32_t> flags;
+        const bool need_split = A->n_ghost > 0;
+        if (need_split) HEAT_TRY(flags.alloc((size_t)ns));
+        sell_fill_kernel<<<(unsigned)((ns + kWarpsPerBlock - 1) / kWarpsPerBlock), kBlock, 0, st>>>(
+            A->row_ptr.p, A->col.p, A->val.p, n, A->n_owned, ns, A->slice_ptr.p, A->sell_col.p, A->sell_val.p,
+            need_split ? flags.p : nullptr);
+        HEAT_CUDA(cudaGetLastError());
+        A->n_int_slices = ns;
+        A->n_bnd_slices = 0;
+        if (need_split) {
+            std::vector<int32_t> h((size_t)ns);
+            HEAT_CUDA(cudaMemcpyAsync(h.data(), flags.p, sizeof(int32_t) * (size_t)ns, cudaMemcpyDeviceToHost, st));
+            HEAT_CUDA(cudaStreamSynchronize(st));
+            std::vector<int32_t> li, lb;
+            for (int64_t s = 0; s < ns; ++s) (h[(size_t)s] ? lb : li).push_back((int32_t)s);
+            A->n_int_slices = (int64_t)li.size();
+            A->n_bnd_slices = (int64_t)lb.size();
+            HEAT_TRY(A->slices_interior.alloc(li.size()));
+            HEAT_TRY(A->slices_boundary.alloc(lb.size()));
+            if (!li.empty())
+                HEAT_CUDA(cudaMemcpyAsync(A->slices_interior.p, li.data(), sizeof(int32_t) * li.size(), cudaMemcpyHostToDevice, st));
+            if (!lb.empty())
+                HEAT_CUDA(cudaMemcpyAsync(A->slices_boundary.p, lb.data(), sizeof(int32_t) * lb.size(), cudaMemcpyHostToDevice, st));
+            HEAT_CUDA(cudaStreamSynchronize(st));
+        }
+    }
+    HEAT_TRY(launch_extract_diag(A, st));
+    return 0;
+}
+
+}  // namespace heat

@@ -1,0 +1,238 @@
+// solve.cu — host drivers of SpMV and preconditioned CG (role of belosSolver,
+// BelosMueLuSolver.cpp:87-139, with Belos "CG" + Ifpack2 Jacobi/Chebyshev per the north-star).
+//
+// No host round trip inside an iteration: scalars live on the device, every kernel evaluates
+// the Belos stopping test (||r||/||r0|| <= tol, checked BEFORE an iteration) itself and becomes a
+// no-op once it fires, so the host only polls every `check_every` iterations.  Multi-GPU: the halo
+// exchange of the SpMV input overlaps the interior slices; dot products are all-reduced as one
+// (single-reduce solver) or two (classical) tiny NCCL calls per iteration.
+#include "comm.cuh"
+#include "device_utils.cuh"
+#include "kernels.cuh"
+#include "solve.cuh"
+
+namespace heat {
+
+static int g_sm_count = 0;
+int sm_count(int device) {
+    if (g_sm_count == 0) {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return 148;
+        g_sm_count = prop.multiProcessorCount;
+    }
+    return g_sm_count;
+}
+
+// y = A x with the halo exchange of x overlapped with the interior slices
+int spmv_halo(heat_ctx *ctx, heat_matrix *A, double *x, double *y, CgGate gate, double *dot_out) {
+    const int sms = sm_count(ctx->device);
+    const bool split = ctx->nranks > 1 && A->halo.n_neighbors > 0;
+    DotOut d{A->partials.p, 0, 0, A->iscal.p + I_COUNTER, dot_out};
+    if (!split) {
+        const int g = spmv_grid(A->n_slices, sms);
+        d.total_blocks = g;
+        return launch_spmv(A, x, y, nullptr, A->n_slices, gate, d, g, ctx->stream);
+    }
+    const int g1 = spmv_grid(A->n_int_slices, sms), g2 = spmv_grid(A->n_bnd_slices, sms) > 2048 ? 2048 : spmv_grid(A->n_bnd_slices, sms);
+    const int g1c = g1 > 2048 ? 2048 : g1;
+    HEAT_TRY(halo_begin(ctx, A, x));
+    d.part_offset = 0; d.total_blocks = g1c + g2;
+    HEAT_TRY(launch_spmv(A, x, y, A->slices_interior.p, A->n_int_slices, gate, d, g1c, ctx->stream));
+    HEAT_TRY(halo_end(ctx, A));
+    d.part_offset = g1c;
+    HEAT_TRY(launch_spmv(A, x, y, A->slices_boundary.p, A->n_bnd_slices, gate, d, g2, ctx->stream));
+    return 0;
+}
+
+int ensure_workspace(heat_matrix *A, bool single_reduce, bool cheb) {
+    const size_t nv = (size_t)(A->n_owned + A->n_ghost);
+    if (!A->w_r.p) HEAT_TRY(A->w_r.alloc((size_t)A->n_owned));
+    if (!A->w_p.p) HEAT_TRY(A->w_p.alloc(nv));
+    if (!A->w_ap.p) HEAT_TRY(A->w_ap.alloc((size_t)A->n_owned));
+    if (single_reduce) {
+        if (!A->w_s.p) HEAT_TRY(A->w_s.alloc((size_t)A->n_owned));
+        if (!A->w_u.p) HEAT_TRY(A->w_u.alloc(nv));
+    }
+    if (cheb) {
+        if (!A->w_u.p) HEAT_TRY(A->w_u.alloc(nv));                  // z (SpMV input: needs ghosts)
+        if (!A->w_w.p) HEAT_TRY(A->w_w.alloc((size_t)A->n_owned));
+        if (!A->w_t.p) HEAT_TRY(A->w_t.alloc((size_t)A->n_owned));
+    }
+    if (!A->partials.p) HEAT_TRY(A->partials.alloc((size_t)kMaxPartials * 2));
+    if (!A->scal.p) HEAT_TRY(A->scal.alloc(S_COUNT));
+    if (!A->iscal.p) {
+        HEAT_TRY(A->iscal.alloc(I_COUNT));
+        HEAT_CUDA(cudaMemset(A->iscal.p, 0, sizeof(int) * I_COUNT));
+    }
+    return 0;
+}
+
+struct ChebCoef { double inv_theta, delta, s1; };
+
+// z = p_k(D^-1 A) D^-1 r, Ifpack2 recurrences, zero starting solution
+static int cheb_apply(heat_ctx *ctx, heat_matrix *A, const heat_solve_opts &o, double lmax, const double *r,
+                      double *z, CgGate gate, int grid) {
+    const double ratio = o.cheb_ratio > 0 ? o.cheb_ratio : 30.0;
+    const double alpha = lmax / ratio, beta = 1.1 * lmax;
+    const double delta = 2.0 / (beta - alpha), theta = 0.5 * (beta + alpha), s1 = theta * delta;
+    double rho = 1.0 / s1;
+    HEAT_TRY(launch_cheb_first(A->n_owned, A->dinv.p, r, 1.0 / theta, A->w_w.p, z, gate, grid, ctx->stream));
+    for (int d = 1; d < o.cheb_degree; ++d) {
+        const double rho_new = 1.0 / (2.0 * s1 - rho);
+        HEAT_TRY(spmv_halo(ctx, A, z, A->w_t.p, gate, nullptr));
+        HEAT_TRY(launch_cheb_step(A->n_owned, A->dinv.p, r, A->w_t.p, rho_new * rho, 2.0 * rho_new * delta, A->w_w.p, z,
+                                  gate, grid, ctx->stream));
+        rho = rho_new;
+    }
+    return 0;
+}
+
+// lambda_max(D^-1 A) by 10 power iterations from a fixed pseudo-random start (Ifpack2 default is a
+// random start; a counter-based start keeps the solve reproducible and GPU-count invariant)
+static int estimate_lambda_max(heat_ctx *ctx, heat_matrix *A, double *lmax_out) {
+    const int grid = vec_grid(A->n_owned, sm_count(ctx->device));
+    double *x = A->w_u.p;
+    HEAT_TRY(launch_fill_hash(A->n_owned, x, A->owned_contiguous ? nullptr : A->d_owned_gids.p, A->gid0, 777, ctx->stream));
+    double lam = 1.0;
+    CgGate nogate{nullptr, nullptr, nullptr, 0};
+    for (int itp = 0; itp < 10; ++itp) {
+        double *y = A->w_t.p;
+        HEAT_TRY(spmv_halo(ctx, A, x, y, nogate, nullptr));
+        // y2 = D^-1 A x : cheb_first with r := y, theta := 1 writes it to w_w (and to the scratch w_r)
+        HEAT_TRY(launch_cheb_first(A->n_owned, A->dinv.p, y, 1.0, A->w_w.p, A->w_r.p, nogate, grid, ctx->stream));
+        y = A->w_w.p;
+        double *S = A->scal.p;
+        HEAT_TRY(launch_dot2(A->n_owned, x, y, y, y, S + S_TMP0, S + S_TMP1, A->partials.p, A->iscal.p + I_COUNTER2, grid, ctx->stream));
+        HEAT_TRY(launch_dot2(A->n_owned, x, x, x, x, S + S_TMP2, S + S_TMP2 + 1, A->partials.p, A->iscal.p + I_COUNTER2, grid, ctx->stream));
+        HEAT_TRY(comm_allreduce_sum(ctx, S + S_TMP0, 3));
+        double h[3];
+        HEAT_CUDA(cudaMemcpyAsync(h, S + S_TMP0, sizeof(double) * 3, cudaMemcpyDeviceToHost, ctx->stream));
+        HEAT_CUDA(cudaStreamSynchronize(ctx->stream));
+        lam = h[0] / h[2];                                           // Rayleigh quotient x.D^-1Ax / x.x
+        const double ny = sqrt(h[1]);
+        if (!(ny > 0.0)) break;
+        HEAT_TRY(launch_axpby(A->n_owned, 1.0 / ny, y, 0.0, x, grid, ctx->stream));
+    }
+    *lmax_out = lam;
+    return 0;
+}
+
+int solve_device(heat_ctx *ctx, heat_matrix *A, double *x, const double *b, const heat_solve_opts &o,
+                 heat_solve_info *info) {
+    HEAT_CUDA(cudaSetDevice(ctx->device));
+    const bool single = o.solver == HEAT_SOLVER_CG_SINGLE_REDUCE;
+    const bool cheb = o.prec == HEAT_PREC_CHEBYSHEV;
+    if (o.solver != HEAT_SOLVER_CG && !single) HEAT_FAIL(2, "heat_solve: unknown solver %d", o.solver);
+    if (o.prec != HEAT_PREC_NONE && o.prec != HEAT_PREC_JACOBI && !cheb) HEAT_FAIL(2, "heat_solve: unknown preconditioner %d", o.prec);
+    if (cheb && single) HEAT_FAIL(2, "heat_solve: Chebyshev is implemented for HEAT_SOLVER_CG only");
+    if (o.max_iters < 0 || !(o.tol >= 0.0)) HEAT_FAIL(2, "heat_solve: bad max_iters/tol");
+    HEAT_TRY(ensure_workspace(A, single, cheb));
+    const int64_t n = A->n_owned;
+    const int sms = sm_count(ctx->device);
+    const int vgrid = vec_grid(n, sms);
+    cudaStream_t st = ctx->stream;
+
+    // unit "preconditioner" for HEAT_PREC_NONE: a vector of ones in place of D^-1
+    DevBuf<double> ones;
+    const double *dinv = A->dinv.p;
+    if (o.prec == HEAT_PREC_NONE) {
+        HEAT_TRY(ones.alloc((size_t)n));
+        HEAT_TRY(launch_fill(n, ones.p, 1.0, st));
+        dinv = ones.p;
+    }
+
+    DevBuf<CgRec> Hbuf;
+    const size_t nrec = (size_t)o.max_iters + 2;
+    HEAT_TRY(Hbuf.alloc(nrec));
+    CgRec *H = Hbuf.p;
+    HEAT_CUDA(cudaMemsetAsync(H, 0, sizeof(CgRec) * nrec, st));
+    HEAT_CUDA(cudaMemsetAsync(A->iscal.p, 0, sizeof(int) * I_COUNT, st));
+    double hS[S_COUNT] = {0};
+    hS[S_TOL2] = o.tol * o.tol;
+    HEAT_CUDA(cudaMemcpyAsync(A->scal.p, hS, sizeof(hS), cudaMemcpyHostToDevice, st));
+    double *S = A->scal.p;
+    int *I = A->iscal.p;
+    double *r = A->w_r.p, *p = A->w_p.p, *ap = A->w_ap.p;
+    CgGate nogate{nullptr, nullptr, nullptr, 0};
+
+    double lmax = o.cheb_lambda_max;
+    if (cheb && !(lmax > 0.0)) HEAT_TRY(estimate_lambda_max(ctx, A, &lmax));
+
+    HEAT_CUDA(cudaEventRecord(ctx->ev_a, st));
+    // ---- r0 = b - A x0 ; z0 ; p0 (or u0, w0) ; H[0] ----
+    HEAT_TRY(spmv_halo(ctx, A, x, ap, nogate, nullptr));
+    if (single) {
+        double *u = A->w_u.p, *s = A->w_s.p, *w = ap;
+        HEAT_TRY(launch_cg_init(n, b, ap, dinv, r, u, H, A->partials.p, I + I_COUNTER2, vgrid, st));
+        HEAT_TRY(launch_fill(n, p, 0.0, st));
+        HEAT_TRY(launch_fill(n, s, 0.0, st));
+        HEAT_TRY(spmv_halo(ctx, A, u, w, nogate, &H[0].delta));
+        HEAT_TRY(comm_allreduce_sum(ctx, &H[0].rz, 3));
+    } else if (!cheb) {
+        HEAT_TRY(launch_cg_init(n, b, ap, dinv, r, p, H, A->partials.p, I + I_COUNTER2, vgrid, st));
+        HEAT_TRY(comm_allreduce_sum(ctx, &H[0].rz, 3));
+    } else {
+        double *z = A->w_u.p;
+        HEAT_TRY(launch_cg_init(n, b, ap, A->dinv.p, r, z, H, A->partials.p, I + I_COUNTER2, vgrid, st));   // r (z overwritten below)
+        HEAT_TRY(cheb_apply(ctx, A, o, lmax, r, z, nogate, vgrid));
+        HEAT_TRY(launch_dot2(n, r, z, r, r, &H[0].rz, &H[0].rr, A->partials.p, I + I_COUNTER2, vgrid, st));
+        HEAT_TRY(comm_allreduce_sum(ctx, &H[0].rz, 3));
+        HEAT_TRY(launch_axpby(n, 1.0, z, 0.0, p, vgrid, st));
+    }
+
+    // ---- iterations, polled every check_every ----
+    const int check = o.check_every > 0 ? o.check_every : 32;
+    int launched = 0, h_iters = 0, h_status = 0;
+    while (launched < o.max_iters) {
+        const int batch = (o.max_iters - launched) < check ? (o.max_iters - launched) : check;
+        for (int q = 0; q < batch; ++q) {
+            const int it = launched + q;
+            CgGate gate{H, S, I, it};
+            if (single) {
+                double *u = A->w_u.p, *s = A->w_s.p, *w = ap;
+                HEAT_TRY(launch_cg_fused_update(n, x, r, p, s, u, w, dinv, gate, H, I, A->partials.p, I + I_COUNTER2, vgrid, st));
+                HEAT_TRY(spmv_halo(ctx, A, u, w, gate, &H[it + 1].delta));
+                HEAT_TRY(comm_allreduce_sum(ctx, &H[it + 1].rz, 3));
+            } else if (!cheb) {
+                HEAT_TRY(spmv_halo(ctx, A, p, ap, gate, S + S_PAP0));
+                HEAT_TRY(comm_allreduce_sum(ctx, S + S_PAP0, 1));
+                HEAT_TRY(launch_cg_update_xr(n, x, r, p, ap, dinv, gate, H, S, I, A->partials.p, I + I_COUNTER2, vgrid, st));
+                HEAT_TRY(comm_allreduce_sum(ctx, &H[it + 1].rz, 3));
+                HEAT_TRY(launch_cg_update_p(n, p, r, dinv, gate, vgrid, st));
+            } else {
+                double *z = A->w_u.p;
+                HEAT_TRY(spmv_halo(ctx, A, p, ap, gate, S + S_PAP0));
+                HEAT_TRY(comm_allreduce_sum(ctx, S + S_PAP0, 1));
+                HEAT_TRY(launch_cg_xr_plain(n, x, r, p, ap, gate, S, I, vgrid, st));
+                HEAT_TRY(cheb_apply(ctx, A, o, lmax, r, z, gate, vgrid));
+                HEAT_TRY(launch_cg_dots(n, r, z, gate, H, I, A->partials.p, I + I_COUNTER2, vgrid, st));
+                HEAT_TRY(comm_allreduce_sum(ctx, &H[it + 1].rz, 3));
+                HEAT_TRY(launch_cg_p_plain(n, p, z, gate, vgrid, st));
+            }
+        }
+        launched += batch;
+        int hI[2];
+        HEAT_CUDA(cudaMemcpyAsync(hI, I, sizeof(int) * 2, cudaMemcpyDeviceToHost, st));
+        HEAT_CUDA(cudaStreamSynchronize(st));
+        h_iters = hI[I_ITERS]; h_status = hI[I_STATUS];
+        if (h_iters < launched) break;              // the stopping test fired (or breakdown): frozen
+    }
+    HEAT_CUDA(cudaEventRecord(ctx->ev_b, st));
+    CgRec h0, hk;
+    HEAT_CUDA(cudaMemcpyAsync(&h0, H, sizeof(CgRec), cudaMemcpyDeviceToHost, st));
+    HEAT_CUDA(cudaMemcpyAsync(&hk, H + h_iters, sizeof(CgRec), cudaMemcpyDeviceToHost, st));
+    HEAT_CUDA(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    HEAT_CUDA(cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b));
+    if (info) {
+        info->iters = h_iters;
+        info->r0_norm = sqrt(h0.rr);
+        info->achieved_tol = h0.rr > 0.0 ? sqrt(hk.rr / h0.rr) : 0.0;
+        info->converged = (hk.rr <= o.tol * o.tol * h0.rr) ? 1 : 0;
+        info->solve_ms = ms;
+    }
+    if (h_status == 2) HEAT_FAIL(50, "heat_solve: CG breakdown (p.Ap <= 0) at iteration %d — matrix not SPD?", h_iters);
+    return 0;
+}
+
+}  // namespace heat

@@ -1,0 +1,12 @@
+// solve.cuh — host drivers (definitions in solve.cu).
+#pragma once
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace heat {
+int sm_count(int device);
+int spmv_halo(heat_ctx *ctx, heat_matrix *A, double *x, double *y, CgGate gate, double *dot_out);
+int ensure_workspace(heat_matrix *A, bool single_reduce, bool cheb);
+int solve_device(heat_ctx *ctx, heat_matrix *A, double *x, const double *b, const heat_solve_opts &o,
+                 heat_solve_info *info);
+}  // namespace heat

@@ -1,0 +1,408 @@
+"""heat_b200 — ctypes face of libheat_b200.so (include/heat_b200.h).
+
+Host-side mirror of the reference's only first-party interface, `ExodusIO::IO`
+(/root/reference/ExodusIO.hpp:83-2225) plus `belosSolver` (BelosMueLuSolver.cpp:87-139):
+`IO.open / create / assemble / decompose / writeSolution` keep the reference's names, argument
+order and call-order contract; failures raise `HeatError` (the reference returns `false` and
+prints to stderr).  All compute runs in the CUDA library — there is NO CPU fallback: importing
+works anywhere (so the CPU test suite can check the ABI), but every compute call raises without
+a CUDA device or without the built library.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libheat_b200.so")
+
+OP_GRAPH_LAPLACIAN, OP_P1_FEM = 0, 1
+SOLVER_CG, SOLVER_CG_SINGLE_REDUCE = 0, 1
+PREC_NONE, PREC_JACOBI, PREC_CHEBYSHEV = 0, 1, 2
+PART_CONTIGUOUS, PART_METIS_KWAY, PART_SLAB = 0, 1, 2
+COMM_ID_BYTES = 128
+
+
+class HeatError(RuntimeError):
+    pass
+
+
+class SolveOpts(C.Structure):
+    _fields_ = [("solver", C.c_int), ("prec", C.c_int), ("max_iters", C.c_int), ("tol", C.c_double),
+                ("cheb_degree", C.c_int), ("cheb_lambda_max", C.c_double), ("cheb_ratio", C.c_double),
+                ("check_every", C.c_int)]
+
+
+class SolveInfo(C.Structure):
+    _fields_ = [("iters", C.c_int), ("converged", C.c_int), ("achieved_tol", C.c_double),
+                ("r0_norm", C.c_double), ("solve_ms", C.c_double)]
+
+
+class MatrixInfo(C.Structure):
+    _fields_ = [("num_nodes", C.c_int64), ("num_elem", C.c_int64), ("n_global", C.c_int64), ("nnz_global", C.c_int64),
+                ("n_owned", C.c_int64), ("n_ghost", C.c_int64), ("nnz_local", C.c_int64),
+                ("max_row_len", C.c_int32), ("npe", C.c_int32), ("num_dim", C.c_int32), ("num_node_sets", C.c_int32),
+                ("rank", C.c_int32), ("nranks", C.c_int32), ("n_neighbors", C.c_int32), ("sell_chunk", C.c_int32),
+                ("sell_padded_nnz", C.c_int64), ("n_boundary_slices", C.c_int64), ("n_slices", C.c_int64),
+                ("assemble_ms", C.c_double)]
+
+
+class PlanSizes(C.Structure):
+    _fields_ = [("n_owned", C.c_int64), ("n_ghost", C.c_int64), ("n_neighbors", C.c_int32), ("n_send", C.c_int64)]
+
+
+# every symbol include/heat_b200.h declares (tests check the .so exports all of them)
+ABI_SYMBOLS = [
+    "heat_last_error", "heat_version", "heat_device_count", "heat_ctx_create", "heat_ctx_set_stream", "heat_open",
+    "heat_create", "heat_close", "heat_mesh_set", "heat_mesh_cube", "heat_comm_unique_id", "heat_comm_init",
+    "heat_comm_rank", "heat_assemble", "heat_solve_opts_default", "heat_solve", "heat_solve_host", "heat_spmv",
+    "heat_cg_iterations", "heat_decompose", "heat_write_solution", "heat_nodal_field", "heat_decompose_partition",
+    "heat_matrix_get_info", "heat_matrix_export_csr", "heat_matrix_export_maps", "heat_matrix_export_plan",
+    "heat_matrix_export_red2orig", "heat_matrix_free", "heat_vector_create", "heat_vector_size",
+    "heat_vector_device_ptr", "heat_vector_set", "heat_vector_get", "heat_vector_fill", "heat_vector_fill_hash",
+    "heat_vector_free", "heat_plan_build", "heat_partition_rows",
+]
+
+_lib = None
+
+
+def lib():
+    """Load libheat_b200.so.  Raises HeatError (loudly) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise HeatError(f"{LIB_PATH} not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "(there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp, i64p, i32p, dp = C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_double)
+    L.heat_last_error.restype = C.c_char_p
+    L.heat_ctx_create.argtypes = [C.c_int, C.POINTER(vp)]
+    L.heat_ctx_set_stream.argtypes = [vp, vp]
+    L.heat_open.argtypes = [vp, C.c_char_p, C.c_int]
+    L.heat_create.argtypes = [vp, C.c_char_p]
+    L.heat_close.argtypes = [vp]
+    L.heat_mesh_set.argtypes = [vp, C.c_int64, C.c_int, dp, dp, dp, C.c_int64, C.c_int, i32p, C.c_int, i64p, i64p, i64p]
+    L.heat_mesh_cube.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.heat_comm_unique_id.argtypes = [C.c_char_p]
+    L.heat_comm_init.argtypes = [vp, C.c_int, C.c_int, C.c_char_p]
+    L.heat_comm_rank.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.heat_assemble.argtypes = [vp, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    L.heat_solve_opts_default.argtypes = [C.POINTER(SolveOpts)]
+    L.heat_solve_opts_default.restype = None
+    L.heat_solve.argtypes = [vp, vp, vp, vp, C.POINTER(SolveOpts), C.POINTER(SolveInfo)]
+    L.heat_solve_host.argtypes = [vp, vp, vp, vp, C.POINTER(SolveOpts), C.POINTER(SolveInfo)]
+    L.heat_spmv.argtypes = [vp, vp, vp, vp]
+    L.heat_cg_iterations.argtypes = [vp, vp, vp, vp, C.POINTER(SolveOpts), C.c_int, C.POINTER(SolveInfo)]
+    L.heat_decompose.argtypes = [vp, C.c_int]
+    L.heat_write_solution.argtypes = [vp, vp, C.c_int]
+    L.heat_nodal_field.argtypes = [vp, vp, dp, C.c_int64]
+    L.heat_decompose_partition.argtypes = [vp, C.c_int, i64p, i64p, i64p]
+    L.heat_matrix_get_info.argtypes = [vp, C.POINTER(MatrixInfo)]
+    L.heat_matrix_export_csr.argtypes = [vp, i64p, i32p, dp]
+    L.heat_matrix_export_maps.argtypes = [vp, i64p, i64p, i32p]
+    L.heat_matrix_export_plan.argtypes = [vp, i32p, i64p, i32p, i64p]
+    L.heat_matrix_export_red2orig.argtypes = [vp, i64p]
+    L.heat_matrix_free.argtypes = [vp]
+    L.heat_vector_create.argtypes = [vp, vp, C.POINTER(vp)]
+    L.heat_vector_size.argtypes = [vp]
+    L.heat_vector_size.restype = C.c_int64
+    L.heat_vector_device_ptr.argtypes = [vp]
+    L.heat_vector_device_ptr.restype = vp
+    L.heat_vector_set.argtypes = [vp, vp, vp, C.c_int64]
+    L.heat_vector_get.argtypes = [vp, vp, vp, C.c_int64]
+    L.heat_vector_fill.argtypes = [vp, vp, C.c_double]
+    L.heat_vector_fill_hash.argtypes = [vp, vp, vp, C.c_uint64]
+    L.heat_vector_free.argtypes = [vp]
+    L.heat_plan_build.argtypes = [C.c_int64, i64p, i32p, i32p, C.c_int, C.c_int, C.POINTER(PlanSizes), i64p, i64p, i32p,
+                                  i32p, i64p, i64p, i64p]
+    L.heat_partition_rows.argtypes = [C.c_int64, i64p, i32p, C.c_int, C.c_int, i32p]
+    _lib = L
+    return L
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise HeatError(f"[heat_b200 rc={rc}] {lib().heat_last_error().decode(errors='replace')}")
+
+
+def _ptr(a: np.ndarray, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def device_count() -> int:
+    return int(lib().heat_device_count())
+
+
+def _as_pointer(obj):
+    """host numpy array, torch tensor (any device) or raw int address -> void*"""
+    if obj is None:
+        return None
+    if isinstance(obj, np.ndarray):
+        return C.c_void_p(obj.ctypes.data)
+    if hasattr(obj, "data_ptr"):
+        return C.c_void_p(obj.data_ptr())
+    return C.c_void_p(int(obj))
+
+
+class Vector:
+    """Teuchos::RCP<Tpetra::MultiVector<>> (one column) living on the GPU."""
+
+    def __init__(self, io: "IO", handle):
+        self.io, self.h = io, handle
+
+    def __len__(self):
+        return int(lib().heat_vector_size(self.h))
+
+    @property
+    def device_ptr(self) -> int:
+        return int(lib().heat_vector_device_ptr(self.h))
+
+    def numpy(self) -> np.ndarray:
+        out = np.empty(len(self), dtype=np.float64)
+        _check(lib().heat_vector_get(self.io.h, self.h, _as_pointer(out), len(self)))
+        return out
+
+    def set(self, src):
+        if isinstance(src, np.ndarray):
+            src = np.ascontiguousarray(src, dtype=np.float64)
+            n = src.size
+        else:
+            n = src.numel()
+        _check(lib().heat_vector_set(self.io.h, self.h, _as_pointer(src), n))
+        return self
+
+    def fill(self, value: float):
+        _check(lib().heat_vector_fill(self.io.h, self.h, float(value)))
+        return self
+
+    def free(self):
+        if self.h:
+            lib().heat_vector_free(self.h)
+            self.h = None
+
+
+class Matrix:
+    """Teuchos::RCP<Tpetra::CrsMatrix<>>: this rank's rows, device resident (CSR + SELL-C)."""
+
+    def __init__(self, io: "IO", handle):
+        self.io, self.h = io, handle
+
+    @property
+    def info(self) -> MatrixInfo:
+        mi = MatrixInfo()
+        _check(lib().heat_matrix_get_info(self.h, C.byref(mi)))
+        return mi
+
+    def csr(self):
+        """(row_ptr int64, col int32 LOCAL ids, val) host copies."""
+        mi = self.info
+        rp = np.empty(mi.n_owned + 1, dtype=np.int64)
+        col = np.empty(max(mi.nnz_local, 1), dtype=np.int32)
+        val = np.empty(max(mi.nnz_local, 1), dtype=np.float64)
+        _check(lib().heat_matrix_export_csr(self.h, _ptr(rp, C.c_int64), _ptr(col, C.c_int32), _ptr(val, C.c_double)))
+        return rp, col[: mi.nnz_local], val[: mi.nnz_local]
+
+    def maps(self):
+        mi = self.info
+        owned = np.empty(max(mi.n_owned, 1), dtype=np.int64)
+        ghost = np.empty(max(mi.n_ghost, 1), dtype=np.int64)
+        owner = np.empty(max(mi.n_ghost, 1), dtype=np.int32)
+        _check(lib().heat_matrix_export_maps(self.h, _ptr(owned, C.c_int64), _ptr(ghost, C.c_int64), _ptr(owner, C.c_int32)))
+        return owned[: mi.n_owned], ghost[: mi.n_ghost], owner[: mi.n_ghost]
+
+    def plan(self):
+        mi = self.info
+        k = mi.n_neighbors
+        nbr = np.empty(max(k, 1), dtype=np.int32)
+        sp = np.zeros(k + 1, dtype=np.int64)
+        rp = np.zeros(k + 1, dtype=np.int64)
+        _check(lib().heat_matrix_export_plan(self.h, _ptr(nbr, C.c_int32), _ptr(sp, C.c_int64), None, _ptr(rp, C.c_int64)))
+        sidx = np.empty(max(int(sp[-1]), 1), dtype=np.int32)
+        _check(lib().heat_matrix_export_plan(self.h, None, None, _ptr(sidx, C.c_int32), None))
+        return nbr[:k], sp, sidx[: int(sp[-1])], rp
+
+    def red2orig(self) -> np.ndarray:
+        out = np.empty(max(self.info.n_owned, 1), dtype=np.int64)
+        _check(lib().heat_matrix_export_red2orig(self.h, _ptr(out, C.c_int64)))
+        return out[: self.info.n_owned]
+
+    def new_vector(self) -> Vector:
+        h = C.c_void_p()
+        _check(lib().heat_vector_create(self.io.h, self.h, C.byref(h)))
+        return Vector(self.io, h)
+
+    def hash_vector(self, seed: int = 12345) -> Vector:
+        v = self.new_vector()
+        _check(lib().heat_vector_fill_hash(self.io.h, self.h, v.h, seed))
+        return v
+
+    def free(self):
+        if self.h:
+            lib().heat_matrix_free(self.h)
+            self.h = None
+
+
+@dataclass
+class SolveResult:
+    iters: int
+    converged: bool
+    achieved_tol: float
+    r0_norm: float
+    solve_ms: float
+
+
+class IO:
+    """Mirror of `ExodusIO::IO` (ExodusIO.hpp:83).  One IO per process == per GPU == per rank.
+    Call order contract of the reference: open -> assemble -> (rank 0) create -> decompose ->
+    repeated writeSolution."""
+
+    def __init__(self, device: int = 0, stream=None):
+        h = C.c_void_p()
+        _check(lib().heat_ctx_create(device, C.byref(h)))
+        self.h = h
+        if stream is not None:
+            self.set_stream(stream)
+
+    # -- plumbing -------------------------------------------------------------------------------
+    def set_stream(self, stream):
+        """cudaStream_t as an int, or a torch.cuda.Stream."""
+        s = getattr(stream, "cuda_stream", stream)
+        _check(lib().heat_ctx_set_stream(self.h, C.c_void_p(int(s))))
+
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = C.create_string_buffer(COMM_ID_BYTES)
+        _check(lib().heat_comm_unique_id(buf))
+        return buf.raw
+
+    def comm_init(self, rank: int, nranks: int, unique_id: bytes):
+        _check(lib().heat_comm_init(self.h, rank, nranks, unique_id))
+
+    # -- ExodusIO::IO -----------------------------------------------------------------------------
+    def open(self, fname: str, read_only: bool = False) -> bool:          # ExodusIO.hpp:88
+        _check(lib().heat_open(self.h, fname.encode(), int(read_only)))
+        return True
+
+    def create(self, fname: str) -> bool:                                  # ExodusIO.hpp:103
+        _check(lib().heat_create(self.h, fname.encode()))
+        return True
+
+    def mesh_set(self, x, y, z, conn, nodesets: dict, num_dim: int = 3):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.ascontiguousarray(y, dtype=np.float64)
+        zz = None if z is None else np.ascontiguousarray(z, dtype=np.float64)
+        conn = np.ascontiguousarray(conn, dtype=np.int32)
+        ids = np.array(sorted(nodesets), dtype=np.int64)
+        ptr = np.zeros(len(ids) + 1, dtype=np.int64)
+        nodes = []
+        for k, sid in enumerate(ids):
+            arr = np.asarray(nodesets[int(sid)], dtype=np.int64)
+            nodes.append(arr)
+            ptr[k + 1] = ptr[k] + arr.size
+        flat = np.concatenate(nodes).astype(np.int64) if nodes else np.zeros(0, dtype=np.int64)
+        flat = np.ascontiguousarray(flat) if flat.size else np.zeros(1, dtype=np.int64)
+        ids_ = ids if ids.size else np.zeros(1, dtype=np.int64)
+        _check(lib().heat_mesh_set(self.h, x.size, num_dim, _ptr(x, C.c_double), _ptr(y, C.c_double),
+                                   _ptr(zz, C.c_double) if zz is not None else None, conn.shape[0], conn.shape[1],
+                                   _ptr(conn, C.c_int32), len(ids), _ptr(ids_, C.c_int64), _ptr(ptr, C.c_int64),
+                                   _ptr(flat, C.c_int64)))
+
+    def mesh_cube(self, nx: int, ny: int, nz: int, explicit_mesh: bool = False):
+        _check(lib().heat_mesh_cube(self.h, nx, ny, nz, int(explicit_mesh)))
+
+    def assemble(self, op_mode: int = OP_GRAPH_LAPLACIAN, partitioner: int = PART_METIS_KWAY):   # ExodusIO.hpp:128
+        """-> (A, X, B) like `assemble(&A, &X, &B)`; X is zero (the reference randomises it unseeded)."""
+        a, x, b = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        _check(lib().heat_assemble(self.h, op_mode, partitioner, C.byref(a), C.byref(x), C.byref(b)))
+        return Matrix(self, a), Vector(self, x), Vector(self, b)
+
+    def decompose(self, partitions: int) -> bool:                          # ExodusIO.hpp:1496
+        _check(lib().heat_decompose(self.h, partitions))
+        return True
+
+    def decompose_partition(self, partitions: int, num_elem: int, num_nodes: int):
+        epart = np.zeros(num_elem, dtype=np.int64)
+        npart = np.zeros(num_nodes, dtype=np.int64)
+        obj = C.c_int64(0)
+        _check(lib().heat_decompose_partition(self.h, partitions, C.byref(obj), _ptr(epart, C.c_int64), _ptr(npart, C.c_int64)))
+        return int(obj.value), epart, npart
+
+    def writeSolution(self, vec: Vector, timestep: int) -> bool:           # ExodusIO.hpp:1972
+        _check(lib().heat_write_solution(self.h, vec.h, timestep))
+        return True
+
+    def nodal_field(self, vec: Vector, num_nodes: int) -> np.ndarray:
+        out = np.empty(num_nodes, dtype=np.float64)
+        _check(lib().heat_nodal_field(self.h, vec.h, _ptr(out, C.c_double), num_nodes))
+        return out
+
+    # -- belosSolver --------------------------------------------------------------------------------
+    @staticmethod
+    def solve_opts(**kw) -> SolveOpts:
+        o = SolveOpts()
+        lib().heat_solve_opts_default(C.byref(o))
+        for k, v in kw.items():
+            if not hasattr(o, k):
+                raise TypeError(f"unknown solve option {k}")
+            setattr(o, k, v)
+        return o
+
+    def solve(self, A: Matrix, X: Vector, B: Vector, **kw) -> SolveResult:   # BelosMueLuSolver.cpp:87
+        o, info = self.solve_opts(**kw), SolveInfo()
+        _check(lib().heat_solve(self.h, A.h, X.h, B.h, C.byref(o), C.byref(info)))
+        return SolveResult(info.iters, bool(info.converged), info.achieved_tol, info.r0_norm, info.solve_ms)
+
+    def solve_host(self, A: Matrix, b_host, x_host, **kw) -> SolveResult:
+        """b_host / x_host: numpy arrays or pinned torch CPU tensors (x_host: x0 in, solution out)."""
+        o, info = self.solve_opts(**kw), SolveInfo()
+        _check(lib().heat_solve_host(self.h, A.h, _as_pointer(b_host), _as_pointer(x_host), C.byref(o), C.byref(info)))
+        return SolveResult(info.iters, bool(info.converged), info.achieved_tol, info.r0_norm, info.solve_ms)
+
+    def cg_iterations(self, A: Matrix, X: Vector, B: Vector, iters: int, **kw) -> SolveResult:
+        o, info = self.solve_opts(**kw), SolveInfo()
+        _check(lib().heat_cg_iterations(self.h, A.h, X.h, B.h, C.byref(o), iters, C.byref(info)))
+        return SolveResult(info.iters, bool(info.converged), info.achieved_tol, info.r0_norm, info.solve_ms)
+
+    def spmv(self, A: Matrix, x: Vector, y: Vector):
+        _check(lib().heat_spmv(self.h, A.h, x.h, y.h))
+
+    def close(self):
+        if self.h:
+            lib().heat_close(self.h)
+            self.h = None
+
+
+# -- pure-host helpers (no GPU needed) ---------------------------------------------------------------
+def partition_rows(row_ptr, col, partitioner: int, nranks: int) -> np.ndarray:
+    row_ptr = np.ascontiguousarray(row_ptr, dtype=np.int64)
+    col = np.ascontiguousarray(col, dtype=np.int32)
+    n = row_ptr.size - 1
+    part = np.zeros(max(n, 1), dtype=np.int32)
+    _check(lib().heat_partition_rows(n, _ptr(row_ptr, C.c_int64), _ptr(col, C.c_int32), partitioner, nranks, _ptr(part, C.c_int32)))
+    return part[:n]
+
+
+def plan_build(row_ptr, col, part, nranks: int, rank: int) -> dict:
+    """Owned/ghost/send maps of `rank` (Tpetra conventions) from a global pattern + row partition."""
+    row_ptr = np.ascontiguousarray(row_ptr, dtype=np.int64)
+    col = np.ascontiguousarray(col, dtype=np.int32)
+    part = np.ascontiguousarray(part, dtype=np.int32)
+    n = row_ptr.size - 1
+    sz = PlanSizes()
+    args = (n, _ptr(row_ptr, C.c_int64), _ptr(col, C.c_int32), _ptr(part, C.c_int32), nranks, rank)
+    _check(lib().heat_plan_build(*args, C.byref(sz), None, None, None, None, None, None, None))
+    owned = np.empty(max(sz.n_owned, 1), dtype=np.int64)
+    ghost = np.empty(max(sz.n_ghost, 1), dtype=np.int64)
+    owner = np.empty(max(sz.n_ghost, 1), dtype=np.int32)
+    nbr = np.empty(max(sz.n_neighbors, 1), dtype=np.int32)
+    sp = np.zeros(sz.n_neighbors + 1, dtype=np.int64)
+    rp = np.zeros(sz.n_neighbors + 1, dtype=np.int64)
+    sg = np.empty(max(sz.n_send, 1), dtype=np.int64)
+    _check(lib().heat_plan_build(*args, C.byref(sz), _ptr(owned, C.c_int64), _ptr(ghost, C.c_int64), _ptr(owner, C.c_int32),
+                                 _ptr(nbr, C.c_int32), _ptr(sp, C.c_int64), _ptr(sg, C.c_int64), _ptr(rp, C.c_int64)))
+    return dict(owned=owned[: sz.n_owned], ghost=ghost[: sz.n_ghost], ghost_owner=owner[: sz.n_ghost],
+                nbr=nbr[: sz.n_neighbors], send_ptr=sp, send_gids=sg[: sz.n_send], recv_ptr=rp)

@@ -1,0 +1,152 @@
+// ExodusIO_b200.hpp — C++ mirror of the reference's `ExodusIO::IO` (ExodusIO.hpp:83-2225) and
+// `belosSolver` (BelosMueLuSolver.cpp:87) over the C ABI of include/heat_b200.h.
+//
+// Same method names, argument order, bool returns and call-order contract as the reference:
+//     IO io; io.open(in, true); io.assemble(&A, &X, &B); io.create(out); io.decompose(parts);
+//     belosSolver(A, X, B, iterations, tolerance, io, verbose);   // calls io.writeSolution
+// Tpetra cannot exist here, so Teuchos::RCP<Tpetra::CrsMatrix<>> / MultiVector<> are replaced by
+// ref-counted handles heat::Matrix / heat::Vector (std::shared_ptr, same ownership semantics).
+// One IO per process == per GPU (the reference: one IO per MPI rank).
+#pragma once
+#include <algorithm>
+#include <cstdio>
+#include <iostream>
+#include <memory>
+#include <string>
+
+#include "heat_b200.h"
+
+namespace heat {
+
+struct MatrixHandle {
+    heat_matrix *h = nullptr;
+    ~MatrixHandle() { heat_matrix_free(h); }
+};
+struct VectorHandle {
+    heat_vector *h = nullptr;
+    ~VectorHandle() { heat_vector_free(h); }
+};
+using Matrix = std::shared_ptr<MatrixHandle>;   // role of Teuchos::RCP<Tpetra::CrsMatrix<>>
+using Vector = std::shared_ptr<VectorHandle>;   // role of Teuchos::RCP<Tpetra::MultiVector<>>
+
+struct Options {                 // knobs the reference hard-codes (ExodusIO.hpp:644-646, BelosMueLuSolver.cpp:93-106)
+    int device = 0;
+    int op_mode = HEAT_OP_GRAPH_LAPLACIAN;
+    int partitioner = HEAT_PART_METIS_KWAY;
+    int solver = HEAT_SOLVER_CG;
+    int prec = HEAT_PREC_JACOBI;
+    int cheb_degree = 3;
+    double cheb_lambda_max = 0.0;
+    int write_every = 0;         // 0: write the final field only; k: every k iterations (the reference: 1)
+};
+
+}  // namespace heat
+
+namespace ExodusIO {
+
+class IO {
+   public:
+    explicit IO(const heat::Options &opt = heat::Options()) : opt_(opt) {
+        if (heat_ctx_create(opt.device, &ctx_)) std::cerr << "heat_ctx_create: " << heat_last_error() << std::endl;
+    }
+    IO(const IO &) = delete;
+    IO &operator=(const IO &) = delete;
+    ~IO() { heat_close(ctx_); }                                   // ExodusIO.hpp:2072-2079
+
+    // Opens the read-in Exodus file (ExodusIO.hpp:88-100)
+    bool open(std::string fname, bool read_only = false) {
+        if (!ctx_ || heat_open(ctx_, fname.c_str(), read_only ? 1 : 0)) { perror_("ex_open"); return false; }
+        return true;
+    }
+    // Opens the written-out Exodus file (ExodusIO.hpp:103-114)
+    bool create(std::string fname) {
+        if (!ctx_ || heat_create(ctx_, fname.c_str())) { perror_("ex_create"); return false; }
+        return true;
+    }
+    // ExodusIO.hpp:128 — A, X, B for the steady-state heat problem of the opened mesh
+    bool assemble(heat::Matrix *A, heat::Vector *X, heat::Vector *B, bool verbose = false) {
+        if (!ctx_) return false;
+        auto a = std::make_shared<heat::MatrixHandle>();
+        auto x = std::make_shared<heat::VectorHandle>();
+        auto b = std::make_shared<heat::VectorHandle>();
+        if (heat_assemble(ctx_, opt_.op_mode, opt_.partitioner, &a->h, &x->h, &b->h)) { perror_("assemble"); return false; }
+        if (verbose) {
+            heat_matrix_info mi;
+            heat_matrix_get_info(a->h, &mi);
+            std::cout << "# of Nodes: " << mi.num_nodes << "\n# of Elements: " << mi.num_elem << "\n# of Node Sets: "
+                      << mi.num_node_sets << "\nDOF rows: " << mi.n_global << " (rank " << mi.rank << " owns " << mi.n_owned
+                      << ", ghosts " << mi.n_ghost << ")\nnnz: " << mi.nnz_global << "\nassemble ms: " << mi.assemble_ms
+                      << std::endl;
+        }
+        *A = a; *X = x; *B = b;
+        return true;
+    }
+    // ExodusIO.hpp:1496 — partition with METIS and write the mesh with one element block per partition
+    bool decompose(int partitions, bool verbose = false) {
+        if (!ctx_ || heat_decompose(ctx_, partitions)) { perror_("decompose"); return false; }
+        if (verbose) std::cout << "Decomposed into " << partitions << " partitions." << std::endl;
+        return true;
+    }
+    // ExodusIO.hpp:1972 — nodal variable "Steady-State Heat Solution" at step timestep+1
+    bool writeSolution(heat::Vector vec, const int timestep, bool verbose = false) {
+        if (!ctx_ || !vec || heat_write_solution(ctx_, vec->h, timestep)) { perror_("writeSolution"); return false; }
+        if (verbose) std::cout << "Wrote nodal values for timestep " << timestep << "!" << std::endl;
+        return true;
+    }
+
+    heat_ctx *ctx() { return ctx_; }
+    const heat::Options &options() const { return opt_; }
+
+   private:
+    void perror_(const char *what) { std::cerr << what << ": " << heat_last_error() << std::endl; }
+    heat_ctx *ctx_ = nullptr;
+    heat::Options opt_;
+};
+
+}  // namespace ExodusIO
+
+// Solves A x = b (BelosMueLuSolver.cpp:87-139).  The reference runs Belos GMRES(1)+ILUT restarted in a
+// loop and writes the field after every iteration; here the Krylov loop is device-resident PCG and
+// the field is written every `write_every` iterations (and at the end).
+inline void belosSolver(const heat::Matrix A, const heat::Vector X, const heat::Vector B, size_t numIterations,
+                        double tolerance, ExodusIO::IO &io, bool verbose) {
+    const heat::Options &opt = io.options();
+    heat_solve_opts o;
+    heat_solve_opts_default(&o);
+    o.solver = opt.solver; o.prec = opt.prec; o.tol = tolerance;
+    o.cheb_degree = opt.cheb_degree; o.cheb_lambda_max = opt.cheb_lambda_max;
+    int rank = 0, nranks = 1;
+    heat_comm_rank(io.ctx(), &rank, &nranks);
+    size_t iterations = 0;
+    heat_solve_info info{};
+    const size_t chunk = opt.write_every > 0 ? (size_t)opt.write_every : numIterations;
+    int frame = 0;
+    bool converged = false;
+    if (opt.write_every > 0 && chunk < numIterations) {
+        // trajectory mode: restart CG every `chunk` iterations from the current X (loses the Krylov
+        // space at each restart, like the reference's reset()/setProblem() loop at :131-132)
+        while (iterations < numIterations) {
+            o.max_iters = (int)std::min(chunk, numIterations - iterations);
+            const double r0_first = info.r0_norm;
+            if (heat_solve(io.ctx(), A->h, X->h, B->h, &o, &info)) { std::cerr << heat_last_error() << std::endl; return; }
+            (void)r0_first;
+            iterations += (size_t)info.iters;
+            io.writeSolution(X, frame++, verbose);
+            if (info.converged || info.iters == 0) { converged = info.converged != 0; break; }
+        }
+    } else {
+        o.max_iters = (int)numIterations;
+        if (heat_solve(io.ctx(), A->h, X->h, B->h, &o, &info)) { std::cerr << heat_last_error() << std::endl; return; }
+        iterations = (size_t)info.iters;
+        converged = info.converged != 0;
+        io.writeSolution(X, 0, verbose);
+    }
+    if (rank == 0) {
+        if (converged)
+            std::cout << "The Belos solve took " << iterations << " iteration(s) to reach a relative residual tolerance of "
+                      << info.achieved_tol << "." << std::endl;
+        else
+            std::cout << "The Belos solve took " << iterations << " iteration(s), but did not converge. Achieved tolerance = "
+                      << info.achieved_tol << "." << std::endl;
+    }
+}

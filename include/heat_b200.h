@@ -1,0 +1,181 @@
+/*
+ * heat_b200.h — C ABI of the B200-native steady-state heat path.
+ *
+ * This is the drop-in boundary for ONE path of LouisJenkinsCS/Domain-Decomposed-PDE-Solver:
+ *     mesh (Exodus-II) -> Dirichlet elimination -> CSR assembly -> fp64 SpMV -> PCG -> nodal field
+ * Every entry point names the reference interface it replaces (file:line in /root/reference).
+ * The reference exposes a header-only C++ class (ExodusIO::IO) with Tpetra types in its
+ * signatures; the C++ mirror of that class over this ABI is include/ExodusIO_b200.hpp.
+ *
+ * Conventions: all functions return 0 on success, non-zero on failure (the reference returns
+ * bool + perror/cerr; heat_last_error() holds the message).  Plain pointers and sizes only.
+ * Pointers named *_host are host memory, *_dev device memory of the context's GPU, and plain
+ * `void*` data pointers accept either (resolved with cudaPointerGetAttributes).  One heat_ctx
+ * per process == per GPU == per "MPI rank" of the reference; calls on a ctx are not
+ * thread-safe (neither is ExodusIO::IO).  There is NO CPU fallback: without a CUDA device every
+ * compute entry point fails loudly.
+ */
+#ifndef HEAT_B200_H
+#define HEAT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HEAT_B200_VERSION 100
+
+typedef struct heat_ctx    heat_ctx;     /* ExodusIO::IO state, ExodusIO.hpp:2081-2098          */
+typedef struct heat_matrix heat_matrix;  /* Teuchos::RCP<Tpetra::CrsMatrix<>>   (local rows)     */
+typedef struct heat_vector heat_vector;  /* Teuchos::RCP<Tpetra::MultiVector<>> (1 column)       */
+
+/* operator assembled on the reference's sparsity pattern */
+enum { HEAT_OP_GRAPH_LAPLACIAN = 0,      /* reference-exact, ExodusIO.hpp:116-127, :591-608      */
+       HEAT_OP_P1_FEM = 1 };             /* north-star P1 stiffness, same pattern                */
+/* Krylov solver (reference: Belos "GMRES", BelosMueLuSolver.cpp:106; north-star: CG)            */
+enum { HEAT_SOLVER_CG = 0,               /* classical Belos-style PCG, 2 reductions / iteration  */
+       HEAT_SOLVER_CG_SINGLE_REDUCE = 1  /* Chronopoulos-Gear PCG, 1 reduction / iteration       */ };
+/* preconditioner (reference: Ifpack2 "ILUT", BelosMueLuSolver.cpp:93; north-star: below)        */
+enum { HEAT_PREC_NONE = 0, HEAT_PREC_JACOBI = 1, HEAT_PREC_CHEBYSHEV = 2 };
+/* partitioner used by heat_assemble when nranks > 1                                             */
+enum { HEAT_PART_CONTIGUOUS = 0,         /* Tpetra uniform contiguous map, ExodusIO.hpp:252      */
+       HEAT_PART_METIS_KWAY = 1,         /* METIS k-way on the matrix row graph (role of Zoltan2
+                                            "parmetis", ExodusIO.hpp:644-656)                    */
+       HEAT_PART_SLAB = 2 };             /* synthetic cubes: slabs along the slowest index       */
+
+const char *heat_last_error(void);
+int  heat_version(void);
+int  heat_device_count(void);            /* CUDA devices visible; 0 => every compute call fails  */
+
+/* ---- lifecycle: IO() / open / create / ~IO  (ExodusIO.hpp:85, :88-100, :103-114, :2072-2079) */
+int  heat_ctx_create(int device, heat_ctx **out);
+int  heat_ctx_set_stream(heat_ctx *ctx, void *cuda_stream);   /* cudaStream_t; default: own stream */
+int  heat_open(heat_ctx *ctx, const char *path, int read_only);
+int  heat_create(heat_ctx *ctx, const char *path);
+int  heat_close(heat_ctx *ctx);                               /* closes files, frees everything   */
+
+/* ---- meshes that do not come from a file ---------------------------------------------------- */
+/* Explicit mesh from host memory (what open()+the reads at ExodusIO.hpp:143-192,:342-359 yield):
+ * conn is 0-based [num_elem][npe]; nodeset s has id ns_ids[s] and nodes
+ * ns_nodes[ns_ptr[s] .. ns_ptr[s+1]) (0-based).  z may be NULL for 2-D meshes.                   */
+int  heat_mesh_set(heat_ctx *ctx, int64_t num_nodes, int num_dim, const double *x_host,
+                   const double *y_host, const double *z_host, int64_t num_elem, int npe,
+                   const int32_t *conn_host, int num_node_sets, const int64_t *ns_ids,
+                   const int64_t *ns_ptr, const int64_t *ns_nodes_host);
+/* Synthetic structured Kuhn tet cube (BASELINE.json configs[2..4]):
+ * nx*ny*nz nodes on [-5,5]^3, nodeset 1000 on i==0, 100 on i==nx-1.  `explicit_mesh` != 0
+ * materialises coordinates + connectivity on the device and runs the general assembly kernels;
+ * 0 uses the analytic-connectivity kernels (needed for 512^3 and for per-GPU slabs).            */
+int  heat_mesh_cube(heat_ctx *ctx, int nx, int ny, int nz, int explicit_mesh);
+
+/* ---- multi-GPU plumbing (replaces MPI_COMM_WORLD; one process per GPU) ---------------------- */
+#define HEAT_COMM_ID_BYTES 128
+int  heat_comm_unique_id(char id_out[HEAT_COMM_ID_BYTES]);    /* rank 0 makes it; broadcast it    */
+int  heat_comm_init(heat_ctx *ctx, int rank, int nranks, const char id[HEAT_COMM_ID_BYTES]);
+int  heat_comm_rank(const heat_ctx *ctx, int *rank, int *nranks);
+
+/* ---- assemble  (IO::assemble, ExodusIO.hpp:128-723) ------------------------------------------ *
+ * Builds this rank's rows of A (reduced system, Dirichlet nodes eliminated and moved to B),
+ * X (zero; the reference's unseeded random X is not reproducible) and B, all on
+ * the device.  Collective over the ranks of heat_comm_init.                                      */
+int  heat_assemble(heat_ctx *ctx, int op_mode, int partitioner, heat_matrix **A, heat_vector **X,
+                   heat_vector **B);
+
+/* ---- solve  (belosSolver, BelosMueLuSolver.cpp:87-139) --------------------------------------- *
+ * Stops when ||r||_2/||r0||_2 <= tol (status test before each iteration, as Belos) or after
+ * max_iters iterations.  Returns 0 also when max_iters was hit; *converged tells which.          */
+typedef struct {
+    int    solver;            /* HEAT_SOLVER_*                                                    */
+    int    prec;              /* HEAT_PREC_*                                                      */
+    int    max_iters;         /* reference default 300 (BelosMueLuSolver.cpp:149)                 */
+    double tol;               /* reference default 1e-14 (:151); north-star 1e-10                 */
+    int    cheb_degree;       /* Ifpack2 "chebyshev: degree" (default 1)                          */
+    double cheb_lambda_max;   /* "chebyshev: max eigenvalue"; <=0 => 10 power iterations          */
+    double cheb_ratio;        /* "chebyshev: ratio eigenvalue" (default 30)                       */
+    int    check_every;       /* host convergence poll period in iterations (0 => 32)             */
+} heat_solve_opts;
+typedef struct {
+    int    iters;
+    int    converged;
+    double achieved_tol;      /* ||r||/||r0|| (Belos achievedTol(), BelosMueLuSolver.cpp:121)     */
+    double r0_norm;
+    double solve_ms;          /* device time of the iteration loop (CUDA events)                  */
+} heat_solve_info;
+void heat_solve_opts_default(heat_solve_opts *o);
+int  heat_solve(heat_ctx *ctx, heat_matrix *A, heat_vector *X, const heat_vector *B,
+                const heat_solve_opts *opts, heat_solve_info *info);
+/* Same, through host buffers (the end-to-end path): b_host[n_owned] is copied in, x_host holds
+ * x0 on entry and the solution on exit.                                                          */
+int  heat_solve_host(heat_ctx *ctx, heat_matrix *A, const double *b_host, double *x_host,
+                     const heat_solve_opts *opts, heat_solve_info *info);
+
+/* y = A x  (Tpetra::CrsMatrix::apply; explicit use at ExodusMatrixTest.cpp:101) incl. halo.      */
+int  heat_spmv(heat_ctx *ctx, heat_matrix *A, heat_vector *x, heat_vector *y);
+/* fixed number of CG iterations with no convergence exit (bench hook; same kernels as solve)    */
+int  heat_cg_iterations(heat_ctx *ctx, heat_matrix *A, heat_vector *X, const heat_vector *B,
+                        const heat_solve_opts *opts, int iters, heat_solve_info *info);
+
+/* ---- output  (IO::decompose ExodusIO.hpp:1496-1969, IO::writeSolution :1972-2070) ------------ */
+int  heat_decompose(heat_ctx *ctx, int partitions);           /* rank 0 only, after heat_create   */
+int  heat_write_solution(heat_ctx *ctx, const heat_vector *X, int timestep);   /* collective      */
+/* dense nodal field writeSolution would store (DOF nodes from X, nodeset nodes = their id)       */
+int  heat_nodal_field(heat_ctx *ctx, const heat_vector *X, double *field_host, int64_t num_nodes);
+/* METIS_PartMeshDual with the reference's arguments (ExodusIO.hpp:1615); arrays are int64        */
+int  heat_decompose_partition(heat_ctx *ctx, int partitions, int64_t *objval, int64_t *epart_host,
+                              int64_t *npart_host);
+
+/* ---- inspection / parity hooks (host copies) ------------------------------------------------- */
+typedef struct {
+    int64_t num_nodes, num_elem, n_global, nnz_global;
+    int64_t n_owned, n_ghost, nnz_local;
+    int32_t max_row_len, npe, num_dim, num_node_sets;
+    int32_t rank, nranks, n_neighbors, sell_chunk;
+    int64_t sell_padded_nnz, n_boundary_slices, n_slices;
+    double  assemble_ms;      /* device time of pattern+values+SELL (CUDA events)                 */
+} heat_matrix_info;
+int  heat_matrix_get_info(const heat_matrix *A, heat_matrix_info *info);
+/* local CSR: row_ptr[n_owned+1] (int64), col[nnz_local] LOCAL column ids (int32), val.           */
+int  heat_matrix_export_csr(const heat_matrix *A, int64_t *row_ptr_host, int32_t *col_host,
+                            double *val_host);
+/* maps: owned_gids[n_owned], ghost_gids[n_ghost], ghost_owner[n_ghost] (reduced global ids)      */
+int  heat_matrix_export_maps(const heat_matrix *A, int64_t *owned_gids_host, int64_t *ghost_gids_host,
+                             int32_t *ghost_owner_host);
+/* send plan: for neighbour slot s (0..n_neighbors): rank nbr_rank[s], local rows
+ * send_idx[send_ptr[s]..send_ptr[s+1]) are sent, recv_ptr[s]..recv_ptr[s+1] ghosts received.     */
+int  heat_matrix_export_plan(const heat_matrix *A, int32_t *nbr_rank_host, int64_t *send_ptr_host,
+                             int32_t *send_idx_host, int64_t *recv_ptr_host);
+/* reduced global id -> 0-based original node (globalIDMap, ExodusIO.hpp:572-576) of owned rows   */
+int  heat_matrix_export_red2orig(const heat_matrix *A, int64_t *red2orig_host);
+int  heat_matrix_free(heat_matrix *A);
+
+int  heat_vector_create(heat_ctx *ctx, const heat_matrix *A, heat_vector **out);
+int64_t heat_vector_size(const heat_vector *v);               /* owned entries                    */
+void *heat_vector_device_ptr(heat_vector *v);                 /* fp64, owned entries then ghosts  */
+int  heat_vector_set(heat_ctx *ctx, heat_vector *v, const void *src, int64_t count);
+int  heat_vector_get(heat_ctx *ctx, const heat_vector *v, void *dst, int64_t count);
+int  heat_vector_fill(heat_ctx *ctx, heat_vector *v, double value);
+/* x[i] = U(-1,1) from a counter-based generator keyed on the GLOBAL reduced id:
+ * identical values for any GPU count.                                                            */
+int  heat_vector_fill_hash(heat_ctx *ctx, const heat_matrix *A, heat_vector *v, uint64_t seed);
+int  heat_vector_free(heat_vector *v);
+
+/* ---- host-side partition / ghost-map plan (pure CPU; also used internally by heat_assemble) -- *
+ * From a global CSR pattern (reduced ids, diagonal included or not) and part[row] in [0,nranks):
+ * Tpetra conventions — owned rows ascending; ghost columns grouped by owner rank ascending,
+ * ascending gid inside an owner; send list p->q = q's ghosts owned by p in q's ghost order.
+ * Call with NULL outputs to get the sizes.                                                       */
+typedef struct { int64_t n_owned, n_ghost; int32_t n_neighbors; int64_t n_send; } heat_plan_sizes;
+int  heat_plan_build(int64_t n_global, const int64_t *row_ptr, const int32_t *col, const int32_t *part,
+                     int nranks, int rank, heat_plan_sizes *sizes, int64_t *owned_gids,
+                     int64_t *ghost_gids, int32_t *ghost_owner, int32_t *nbr_rank, int64_t *send_ptr,
+                     int64_t *send_gids, int64_t *recv_ptr);
+/* partition a global row graph exactly as heat_assemble does                                     */
+int  heat_partition_rows(int64_t n_global, const int64_t *row_ptr, const int32_t *col, int partitioner,
+                         int nranks, int32_t *part_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HEAT_B200_H */

@@ -1,0 +1,281 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI
+(include/heat_b200.h via ctypes), against the CPU oracle on the same inputs.
+
+Bars (BASELINE.json north_star): sparsity pattern / maps bit-exact; matrix entries within 1e-12
+relative (we get bit-exact: the element arithmetic is contraction-free on both sides); solution
+within 1e-8 relative at relative residual <= 1e-10; iteration counts within +-2.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import mesh_path
+
+pytestmark = pytest.mark.gpu
+
+EXO = ["rectangle-tris-boundary", "bolted_bracket", "tet-cube-heat", "mitchell_tri"]
+SOL_RTOL = 1e-8      # north_star: solution within 1e-8 relative
+RES_TOL = 1e-10      # ... at relative residual <= 1e-10
+ITER_SLACK = 2       # ... iteration counts within +-2
+
+
+@pytest.fixture(scope="module")
+def hb():
+    import heat_b200
+    if heat_b200.device_count() < 1:
+        pytest.fail("no CUDA device visible: the product has no CPU fallback")
+    return heat_b200
+
+
+@pytest.fixture()
+def io(hb):
+    h = hb.IO(0)
+    yield h
+    h.close()
+
+
+def _assemble_exo(hb, io, oracle, name, mode):
+    io.open(mesh_path(name), True)
+    A, X, B = io.assemble(mode, hb.PART_METIS_KWAY)
+    ref = oracle.assemble(oracle.read_exodus(mesh_path(name)), mode)
+    return A, X, B, ref
+
+
+@pytest.mark.parametrize("name", EXO)
+@pytest.mark.parametrize("mode", [0, 1])
+def test_assemble_matches_oracle_bit_exact(hb, io, oracle, name, mode):
+    A, X, B, ref = _assemble_exo(hb, io, oracle, name, mode)
+    rp, col, val = A.csr()
+    mi = A.info
+    assert (mi.n_global, mi.nnz_global, mi.n_owned, mi.n_ghost) == (ref.n, ref.nnz, ref.n, 0)
+    np.testing.assert_array_equal(rp, ref.row_ptr)          # sparsity pattern bit-exact
+    np.testing.assert_array_equal(col, ref.col)
+    np.testing.assert_array_equal(A.red2orig(), ref.red2orig)
+    np.testing.assert_array_equal(val, ref.val)              # entries: bar 1e-12 relative, measured bit-exact
+    np.testing.assert_array_equal(B.numpy(), ref.b)
+    assert np.all(X.numpy() == 0.0)
+
+
+@pytest.mark.parametrize("name", EXO)
+def test_assemble_matches_golden(hb, io, oracle, golden, name):
+    for mode, key in ((0, "graph"), (1, "p1")):
+        A, X, B, _ = _assemble_exo(hb, io, oracle, name, mode)
+        g = golden[name][key]
+        rp, col, val = A.csr()
+        diag = val[col == np.repeat(np.arange(len(rp) - 1), np.diff(rp))]
+        assert (A.info.n_global, A.info.nnz_global) == (g["n"], g["nnz"])
+        assert diag.sum() == pytest.approx(g["trace"], rel=1e-13)
+        assert B.numpy().sum() == pytest.approx(g["sum_b"], rel=1e-12)
+
+
+@pytest.mark.parametrize("name", ["bolted_bracket", "tet-cube-heat"])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_spmv_bit_exact(hb, io, oracle, name, mode):
+    A, X, B, ref = _assemble_exo(hb, io, oracle, name, mode)
+    x = A.hash_vector(12345)
+    y = A.new_vector()
+    io.spmv(A, x, y)
+    xh = x.numpy()
+    assert np.abs(xh).max() <= 1.0 and abs(xh.mean()) < 0.05
+    np.testing.assert_array_equal(y.numpy(), oracle.spmv(ref, xh))
+
+
+@pytest.mark.parametrize("name", ["rectangle-tris-boundary", "bolted_bracket", "tet-cube-heat", "mitchell_tri"])
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("solver", [0, 1])
+def test_solve_matches_oracle(hb, io, oracle, golden, name, mode, solver):
+    A, X, B, ref = _assemble_exo(hb, io, oracle, name, mode)
+    res = io.solve(A, X, B, solver=solver, prec=hb.PREC_JACOBI, max_iters=2000, tol=RES_TOL, check_every=16)
+    x_ref, it_ref, ach_ref, _ = oracle.pcg(ref, tol=RES_TOL, max_iters=2000)
+    x = X.numpy()
+    assert res.converged and res.achieved_tol <= RES_TOL
+    assert abs(res.iters - it_ref) <= ITER_SLACK, (res.iters, it_ref)
+    assert np.abs(x - x_ref).max() <= SOL_RTOL * np.abs(x_ref).max()
+    # true residual, not the recurrence
+    r = ref.b - ref.csr() @ x
+    assert np.linalg.norm(r) <= 10 * RES_TOL * np.linalg.norm(ref.b)
+    g = golden[name]["graph" if mode == 0 else "p1"]
+    assert x.mean() == pytest.approx(g["x_mean"], rel=1e-7)
+    assert x.min() == pytest.approx(g["x_min"], rel=1e-6) and x.max() == pytest.approx(g["x_max"], rel=1e-6)
+
+
+def test_p1_analytic_linear_field(hb, io, oracle):
+    # T = 550 - 90 x on tet-cube-heat.exo
+    io.open(mesh_path("tet-cube-heat"), True)
+    A, X, B = io.assemble(hb.OP_P1_FEM)
+    res = io.solve(A, X, B, max_iters=3000, tol=1e-12)
+    m = oracle.read_exodus(mesh_path("tet-cube-heat"))
+    f = io.nodal_field(X, m.num_nodes)
+    assert res.converged
+    assert np.abs(f - (550.0 - 90.0 * m.x)).max() < 1e-7
+    assert set(np.unique(f[m.nodesets[100]])) == {100.0} and set(np.unique(f[m.nodesets[1000]])) == {1000.0}
+
+
+def test_iteration_counts_baseline_table(hb, io, oracle):
+    # BASELINE.md §2
+    expect = {("tet-cube-heat", 0): (105, 136), ("tet-cube-heat", 1): (140, 180), ("bolted_bracket", 0): (123, 137)}
+    for (name, mode), (i8, i10) in expect.items():
+        A, X, B, _ = _assemble_exo(hb, io, oracle, name, mode)
+        assert abs(io.solve(A, X, B, max_iters=1000, tol=1e-8).iters - i8) <= ITER_SLACK
+        X.fill(0.0)
+        assert abs(io.solve(A, X, B, max_iters=1000, tol=1e-10).iters - i10) <= ITER_SLACK
+
+
+def test_max_iters_and_status(hb, io, oracle):
+    A, X, B, ref = _assemble_exo(hb, io, oracle, "bolted_bracket", 0)
+    res = io.solve(A, X, B, max_iters=7, tol=1e-14, check_every=3)
+    x_ref, it_ref, ach_ref, hist = oracle.pcg(ref, tol=1e-14, max_iters=7)
+    assert (res.iters, res.converged) == (7, False) and it_ref == 7
+    assert res.achieved_tol == pytest.approx(ach_ref, rel=1e-9)
+    assert np.abs(X.numpy() - x_ref).max() <= 1e-12 * np.abs(x_ref).max()
+    # zero iterations: x untouched, achieved_tol = 1
+    X.fill(0.0)
+    res0 = io.solve(A, X, B, max_iters=0, tol=1e-10)
+    assert res0.iters == 0 and not res0.converged and res0.achieved_tol == pytest.approx(1.0)
+
+
+def test_solve_host_end_to_end(hb, io, oracle):
+    A, X, B, ref = _assemble_exo(hb, io, oracle, "tet-cube-heat", 1)
+    xh = np.zeros(ref.n)
+    res = io.solve_host(A, ref.b.copy(), xh, max_iters=1000, tol=RES_TOL)
+    x_ref = oracle.pcg(ref, tol=RES_TOL, max_iters=1000)[0]
+    assert res.converged and np.abs(xh - x_ref).max() <= SOL_RTOL * np.abs(x_ref).max()
+
+
+def test_chebyshev_matches_oracle(hb, io, oracle):
+    A, X, B, ref = _assemble_exo(hb, io, oracle, "bolted_bracket", 0)
+    res = io.solve(A, X, B, prec=hb.PREC_CHEBYSHEV, cheb_degree=3, cheb_lambda_max=2.0, max_iters=500, tol=RES_TOL)
+    x_ref, it_ref, *_ = oracle.pcg(ref, tol=RES_TOL, prec=oracle.PREC_CHEBYSHEV, cheb_degree=3, cheb_lambda_max=2.0)
+    assert res.converged and abs(res.iters - it_ref) <= ITER_SLACK
+    assert np.abs(X.numpy() - x_ref).max() <= SOL_RTOL * np.abs(x_ref).max()
+    # estimated lambda_max (power iterations) still converges to the same solution
+    X.fill(0.0)
+    res2 = io.solve(A, X, B, prec=hb.PREC_CHEBYSHEV, cheb_degree=2, cheb_lambda_max=0.0, max_iters=500, tol=RES_TOL)
+    assert res2.converged and np.abs(X.numpy() - x_ref).max() <= 1e-7 * np.abs(x_ref).max()
+
+
+def test_no_preconditioner(hb, io, oracle):
+    A, X, B, ref = _assemble_exo(hb, io, oracle, "bolted_bracket", 1)
+    res = io.solve(A, X, B, prec=hb.PREC_NONE, max_iters=3000, tol=RES_TOL)
+    x_ref, it_ref, *_ = oracle.pcg(ref, tol=RES_TOL, prec=oracle.PREC_NONE, max_iters=3000)
+    assert res.converged and abs(res.iters - it_ref) <= max(ITER_SLACK, it_ref // 50)
+    assert np.abs(X.numpy() - x_ref).max() <= 1e-7 * np.abs(x_ref).max()
+
+
+# ---- synthetic Kuhn cubes (BASELINE.json configs[2..4]) -------------------------------------------
+@pytest.mark.parametrize("dims", [(5, 5, 5), (9, 9, 9), (17, 17, 17), (7, 5, 6), (3, 2, 2), (33, 9, 5)])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_cube_analytic_and_explicit_match_oracle(hb, oracle, dims, mode):
+    nx, ny, nz = dims
+    ref = oracle.assemble(oracle.cube_mesh(nx, ny, nz), mode)
+    for explicit in (False, True):
+        io = hb.IO(0)
+        io.mesh_cube(nx, ny, nz, explicit)
+        A, X, B = io.assemble(mode)
+        rp, col, val = A.csr()
+        np.testing.assert_array_equal(rp, ref.row_ptr)
+        np.testing.assert_array_equal(col, ref.col)
+        np.testing.assert_array_equal(val, ref.val)
+        np.testing.assert_array_equal(B.numpy(), ref.b)
+        np.testing.assert_array_equal(A.red2orig(), ref.red2orig)
+        assert A.info.nnz_global == ref.nnz
+        io.close()
+
+
+@pytest.mark.parametrize("mode,solver", [(0, 0), (1, 0), (1, 1)])
+def test_cube_solve_matches_oracle(hb, oracle, mode, solver):
+    n = 17
+    ref = oracle.assemble(oracle.cube_mesh(n, n, n), mode)
+    io = hb.IO(0)
+    io.mesh_cube(n, n, n)
+    A, X, B = io.assemble(mode)
+    res = io.solve(A, X, B, solver=solver, max_iters=1000, tol=RES_TOL)
+    x_ref, it_ref, *_ = oracle.pcg(ref, tol=RES_TOL)
+    assert res.converged and abs(res.iters - it_ref) <= ITER_SLACK
+    assert np.abs(X.numpy() - x_ref).max() <= SOL_RTOL * np.abs(x_ref).max()
+    if mode == 1:   # discrete P1 solution is exactly linear
+        f = io.nodal_field(X, n ** 3)
+        i = np.arange(n ** 3) % n
+        assert np.abs(f - (1000.0 - 900.0 * i / (n - 1))).max() < 1e-6
+    io.close()
+
+
+def test_full_size_256_properties(hb):
+    """BASELINE.json configs[2] at FULL size (16.6 M DOF) through size-independent properties."""
+    n = 256
+    io = hb.IO(0)
+    io.mesh_cube(n, n, n)
+    A, X, B = io.assemble(hb.OP_P1_FEM)
+    mi = A.info
+    assert (mi.n_global, mi.nnz_global) == (16_646_144, 248_130_550)
+    # (1) the exact discrete solution is linear in i: A x* = b  =>  residual ~ rounding
+    gid = np.arange(mi.n_owned)
+    xstar = 1000.0 - 900.0 * ((gid % (n - 2)) + 1) / (n - 1)
+    xs = A.new_vector().set(xstar)
+    y = A.new_vector()
+    io.spmv(A, xs, y)
+    b = B.numpy()
+    assert np.abs(y.numpy() - b).max() <= 1e-9 * max(1.0, np.abs(b).max())
+    # (2) linearity of the SpMV: A(2u + 3v) = 2Au + 3Av
+    u, v = A.hash_vector(1), A.hash_vector(2)
+    yu, yv, yw = A.new_vector(), A.new_vector(), A.new_vector()
+    io.spmv(A, u, yu); io.spmv(A, v, yv)
+    w = A.new_vector().set(2.0 * u.numpy() + 3.0 * v.numpy())
+    io.spmv(A, w, yw)
+    lhs, rhs = yw.numpy(), 2.0 * yu.numpy() + 3.0 * yv.numpy()
+    assert np.abs(lhs - rhs).max() <= 1e-12 * np.abs(rhs).max()
+    # (3) PCG drives the recurrence AND the true residual down; both solvers agree
+    r1 = io.solve(A, X, B, solver=hb.SOLVER_CG, max_iters=3000, tol=1e-10)
+    assert r1.converged
+    io.spmv(A, X, y)
+    assert np.linalg.norm(y.numpy() - b) <= 1e-9 * np.linalg.norm(b)
+    assert np.abs(X.numpy() - xstar).max() <= 1e-5
+    X2 = A.new_vector()
+    r2 = io.solve(A, X2, B, solver=hb.SOLVER_CG_SINGLE_REDUCE, max_iters=3000, tol=1e-10)
+    assert r2.converged and abs(r2.iters - r1.iters) <= ITER_SLACK
+    io.close()
+
+
+def test_full_size_256_graph_rowsums(hb):
+    n = 256
+    io = hb.IO(0)
+    io.mesh_cube(n, n, n)
+    A, X, B = io.assemble(hb.OP_GRAPH_LAPLACIAN)
+    ones = A.new_vector().fill(1.0)
+    y = A.new_vector()
+    io.spmv(A, ones, y)
+    # A.1 = number of Dirichlet neighbours; B = sum of their values => checksum of checksums
+    rows = y.numpy()
+    assert rows.min() >= 0 and rows.max() <= 5 and np.all(rows == np.round(rows))
+    gid = np.arange(A.info.n_owned)
+    i = (gid % (n - 2)) + 1
+    assert np.all(rows[(i > 1) & (i < n - 2)] == 0)
+    b = B.numpy()
+    assert np.all(b[i == 1] == 1000.0 * rows[i == 1]) and np.all(b[i == n - 2] == 100.0 * rows[i == n - 2])
+    io.close()
+
+
+def test_write_solution_round_trip(hb, io, oracle, tmp_path):
+    from scipy.io import netcdf_file
+    io.open(mesh_path("bolted_bracket"), True)
+    A, X, B = io.assemble(hb.OP_GRAPH_LAPLACIAN)
+    out = str(tmp_path / "solution.exo")
+    io.create(out)
+    io.decompose(4)
+    io.solve(A, X, B, max_iters=5, tol=1e-14)
+    io.writeSolution(X, 0)
+    io.solve(A, X, B, max_iters=500, tol=1e-10)
+    io.writeSolution(X, 1)
+    nc = netcdf_file(out, "r", mmap=False)
+    name = b"".join(nc.variables["name_nod_var"].data[0]).split(b"\x00")[0].decode()
+    assert name == "Steady-State Heat Solution"                       # ExodusIO.hpp:2032
+    vals = np.array(nc.variables["vals_nod_var1"].data)
+    assert vals.shape == (2, 4098)
+    np.testing.assert_array_equal(np.array(nc.variables["time_whole"].data), [0.0, 1.0])
+    ref = oracle.assemble(oracle.read_exodus(mesh_path("bolted_bracket")), 0)
+    f = oracle.scatter_field(ref, X.numpy())
+    np.testing.assert_array_equal(vals[1], f)
+    assert nc.dimensions["num_el_blk"] == 4
+    assert np.array(nc.variables["eb_prop1"].data).tolist() == [0, 1, 2, 3]     # block ids start at 0 (D12)
+    nc.close()
