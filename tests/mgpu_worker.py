@@ -1,0 +1,177 @@
+"""Multi-GPU parity worker: one process per GPU (torchrun), NCCL halo exchange + all-reduce inside
+libheat_b200.  Launched by tests/test_gpu_multi.py; can be run by hand:
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+        --master-port 29511 tests/mgpu_worker.py
+
+Checks per rank, against the CPU oracle of the GLOBAL system: local rows (pattern + values mapped
+back to global ids) bit-exact, owned/ghost/send maps bit-exact vs the host plan builder, SpMV with
+halo bit-exact, PCG (both solvers) solution <= 1e-8 relative and iterations within +-2, nodal-field
+gather on rank 0, writeSolution from several ranks.
+"""
+import json
+import os
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (os.path.join(ROOT, "oracle"), os.path.join(ROOT, "domain-decomposed-pde-solver_b200")):
+    sys.path.insert(0, p)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+import heat_b200 as hb  # noqa: E402
+import oracle as O  # noqa: E402
+
+MESHES = os.path.join(ROOT, "tests", "golden", "meshes")
+
+
+def hash_vector(gids, seed):
+    """numpy twin of fill_hash_kernel (cg.cu): U(-1,1) keyed on the global reduced id."""
+    M = np.uint64(0xFFFFFFFFFFFFFFFF)
+    with np.errstate(over="ignore"):
+        z = gids.astype(np.uint64) ^ (np.uint64(0x9E3779B97F4A7C15) * np.uint64(seed))
+        z = (z + np.uint64(0x9E3779B97F4A7C15)) & M
+        z = ((z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)) & M
+        z = ((z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)) & M
+        z = z ^ (z >> np.uint64(31))
+    return (z >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0) * 2.0 - 1.0
+
+
+def slab_part(ref, nx, ny, nz, P):
+    k = ref.red2orig // (nx * ny)
+    base, rem = divmod(nz, P)
+    bounds = [r * base + min(r, rem) for r in range(P + 1)]
+    return (np.searchsorted(np.array(bounds), k, side="right") - 1).astype(np.int32)
+
+
+def check_system(io, A, X, B, ref, part, rank, world, tag, log):
+    mi = A.info
+    owned, ghost, owner = A.maps()
+    plan = hb.plan_build(ref.row_ptr, ref.col, part, world, rank)
+    np.testing.assert_array_equal(owned, plan["owned"], err_msg=f"{tag}: owned map")
+    np.testing.assert_array_equal(ghost, plan["ghost"], err_msg=f"{tag}: ghost map")
+    np.testing.assert_array_equal(owner, plan["ghost_owner"], err_msg=f"{tag}: ghost owners")
+    nbr, sp, sidx, rp_ = A.plan()
+    np.testing.assert_array_equal(nbr, plan["nbr"], err_msg=f"{tag}: neighbours")
+    np.testing.assert_array_equal(sp, plan["send_ptr"]); np.testing.assert_array_equal(rp_, plan["recv_ptr"])
+    np.testing.assert_array_equal(owned[sidx], plan["send_gids"], err_msg=f"{tag}: send lists")
+    assert (mi.n_global, mi.nnz_global, mi.n_owned, mi.n_ghost) == (ref.n, ref.nnz, len(owned), len(ghost))
+    # local rows == global rows (pattern + values), through the local->global column map
+    rp, col, val = A.csr()
+    l2g = np.concatenate([owned, ghost])
+    for l, g in enumerate(owned):
+        s, e = ref.row_ptr[g], ref.row_ptr[g + 1]
+        assert rp[l + 1] - rp[l] == e - s, f"{tag}: row {g} length"
+    sel = np.concatenate([np.arange(ref.row_ptr[g], ref.row_ptr[g + 1]) for g in owned]) if len(owned) else np.zeros(0, int)
+    np.testing.assert_array_equal(l2g[col], ref.col[sel], err_msg=f"{tag}: columns")
+    np.testing.assert_array_equal(val, ref.val[sel], err_msg=f"{tag}: values")
+    np.testing.assert_array_equal(B.numpy(), ref.b[owned], err_msg=f"{tag}: rhs")
+    np.testing.assert_array_equal(A.red2orig(), ref.red2orig[owned])
+    # SpMV with halo exchange: bit-exact
+    xv, yv = A.hash_vector(4242), A.new_vector()
+    xg = hash_vector(np.arange(ref.n), 4242)
+    np.testing.assert_array_equal(xv.numpy(), xg[owned], err_msg=f"{tag}: hash vector")
+    io.spmv(A, xv, yv)
+    np.testing.assert_array_equal(yv.numpy(), O.spmv(ref, xg)[owned], err_msg=f"{tag}: spmv")
+    # PCG
+    x_ref, it_ref, _, _ = O.pcg(ref, tol=1e-10, max_iters=3000)
+    for solver in (hb.SOLVER_CG, hb.SOLVER_CG_SINGLE_REDUCE):
+        X.fill(0.0)
+        res = io.solve(A, X, B, solver=solver, max_iters=3000, tol=1e-10, check_every=8)
+        assert res.converged and abs(res.iters - it_ref) <= 2, (tag, solver, res, it_ref)
+        err = np.abs(X.numpy() - x_ref[owned]).max() / np.abs(x_ref).max()
+        assert err <= 1e-8, (tag, solver, err)
+        log.append(f"{tag} solver={solver} iters={res.iters} (oracle {it_ref}) err={err:.2e} ghosts={len(ghost)} nbrs={len(nbr)}")
+    # Chebyshev (extra halo exchanges inside the preconditioner)
+    X.fill(0.0)
+    res = io.solve(A, X, B, prec=hb.PREC_CHEBYSHEV, cheb_degree=3, cheb_lambda_max=2.5, max_iters=3000, tol=1e-10)
+    xc, itc, *_ = O.pcg(ref, tol=1e-10, prec=O.PREC_CHEBYSHEV, cheb_degree=3, cheb_lambda_max=2.5, max_iters=3000)
+    assert res.converged and abs(res.iters - itc) <= 2 and np.abs(X.numpy() - xc[owned]).max() <= 1e-8 * np.abs(xc).max(), (tag, res, itc)
+    return x_ref
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    idt = torch.zeros(hb.COMM_ID_BYTES, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        idt.copy_(torch.frombuffer(bytearray(hb.IO.comm_unique_id()), dtype=torch.uint8))
+    dist.broadcast(idt, 0)
+    uid = bytes(idt.cpu().numpy().tobytes())
+    log = []
+
+    # one NCCL communicator per IO; unique ids are single-use, so make a fresh id per IO
+    def fresh_io():
+        t = torch.zeros(hb.COMM_ID_BYTES, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            t.copy_(torch.frombuffer(bytearray(hb.IO.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(t, 0)
+        io = hb.IO(local)
+        io.comm_init(rank, world, bytes(t.cpu().numpy().tobytes()))
+        return io
+
+    # ---- 1. analytic Kuhn cube, slab partition (BASELINE.json configs[3] in the small) ----
+    for (nx, ny, nz) in ((12, 9, 11), (9, 9, 2 * world)):
+        mesh = O.cube_mesh(nx, ny, nz)
+        for mode in (hb.OP_GRAPH_LAPLACIAN, hb.OP_P1_FEM):
+            ref = O.assemble(mesh, mode)
+            part = slab_part(ref, nx, ny, nz, world)
+            for explicit in (False, True):
+                io = fresh_io()
+                io.mesh_cube(nx, ny, nz, explicit)
+                A, X, B = io.assemble(mode, hb.PART_SLAB)
+                x_ref = check_system(io, A, X, B, ref, part, rank, world, f"cube{nx}x{ny}x{nz} mode={mode} explicit={explicit}", log)
+                f = io.nodal_field(X, nx * ny * nz)          # collective: rank 0 gets the gathered field
+                if rank == 0:
+                    fx = O.scatter_field(ref, x_ref)
+                    # last solve was Chebyshev: compare loosely
+                    assert np.abs(f - fx).max() <= 1e-6 * np.abs(fx).max()
+                io.close()
+
+    # ---- 2. unstructured mesh, METIS k-way on the row graph (BASELINE.json configs[1]) ----
+    for name in ("bolted_bracket", "tet-cube-heat"):
+        path = os.path.join(MESHES, name + ".exo")
+        mesh = O.read_exodus(path)
+        for mode in (hb.OP_GRAPH_LAPLACIAN, hb.OP_P1_FEM):
+            ref = O.assemble(mesh, mode)
+            for partitioner in (hb.PART_METIS_KWAY, hb.PART_CONTIGUOUS):
+                part = hb.partition_rows(ref.row_ptr, ref.col, partitioner, world)
+                io = fresh_io()
+                io.open(path, True)
+                A, X, B = io.assemble(mode, partitioner)
+                check_system(io, A, X, B, ref, part, rank, world, f"{name} mode={mode} part={partitioner}", log)
+                if partitioner == hb.PART_METIS_KWAY and mode == hb.OP_GRAPH_LAPLACIAN:
+                    # writeSolution from all ranks (ExodusIO.hpp:1972): rank 0 owns the file
+                    out = os.path.join(tempfile.gettempdir(), f"mgpu_{name}_{world}.exo")
+                    if rank == 0:
+                        io.create(out)
+                        io.decompose(max(2, world))
+                    X.fill(0.0)
+                    io.solve(A, X, B, max_iters=3000, tol=1e-10)
+                    io.writeSolution(X, 0)
+                    if rank == 0:
+                        from scipy.io import netcdf_file
+                        nc = netcdf_file(out, "r", mmap=False)
+                        vals = np.array(nc.variables["vals_nod_var1"].data)[0]
+                        x_ref = O.pcg(ref, tol=1e-10, max_iters=3000)[0]
+                        fx = O.scatter_field(ref, x_ref)
+                        assert np.abs(vals - fx).max() <= 1e-8 * np.abs(fx).max()
+                        assert nc.dimensions["num_el_blk"] == max(2, world)
+                        nc.close()
+                io.close()
+
+    dist.barrier()
+    if rank == 0:
+        print("\n".join(log))
+        print(json.dumps({"mgpu_ok": True, "world": world, "checks": len(log)}))
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,114 @@
+"""world_size-2 (gloo, CPU) test of the N>1 HOST logic: the owned/ghost/send plan the C ABI builds
+(heat_plan_build) drives a halo exchange + distributed Jacobi-PCG written in numpy over
+torch.distributed.  No product compute runs here (there is no CPU fallback) — the point is that
+the plan is symmetric (every send has its matching recv, in the receiver's ghost order), that the
+local numbering convention (owned first, ghosts grouped by owner) reproduces the global operator,
+and that one all-reduce of {r.z, w.u, r.r} per iteration (the single-reduce recurrence the CUDA
+path uses) converges to the serial oracle's solution in the same number of iterations (+-2)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT, mesh_path
+
+
+def _worker(rank, world, port, name, partitioner, q):
+    try:
+        for p in (os.path.join(ROOT, "oracle"), os.path.join(ROOT, "domain-decomposed-pde-solver_b200")):
+            sys.path.insert(0, p)
+        import heat_b200 as hb
+        import oracle as O
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        ref = O.assemble(O.read_exodus(mesh_path(name)), O.GRAPH_LAPLACIAN)
+        part = hb.partition_rows(ref.row_ptr, ref.col, partitioner, world)
+        pl = hb.plan_build(ref.row_ptr, ref.col, part, world, rank)
+        owned, ghost = pl["owned"], pl["ghost"]
+        g2l = {int(g): i for i, g in enumerate(np.concatenate([owned, ghost]))}
+        A = ref.csr()[owned]                                    # local rows, global columns
+        lcol = np.array([g2l[int(c)] for c in A.indices], dtype=np.int64)
+        n_own = len(owned)
+        send_local = np.array([g2l[int(g)] for g in pl["send_gids"]], dtype=np.int64)
+        assert np.all(send_local < n_own)
+
+        def halo(x):                                            # x: [owned | ghosts]
+            reqs, bufs = [], []
+            for s, nb in enumerate(pl["nbr"]):
+                sb = torch.from_numpy(x[send_local[pl["send_ptr"][s]:pl["send_ptr"][s + 1]]].copy())
+                rb = torch.empty(int(pl["recv_ptr"][s + 1] - pl["recv_ptr"][s]), dtype=torch.float64)
+                if sb.numel():
+                    reqs.append(dist.isend(sb, int(nb)))
+                if rb.numel():
+                    reqs.append(dist.irecv(rb, int(nb)))
+                bufs.append((s, rb))
+            for r in reqs:
+                r.wait()
+            for s, rb in bufs:
+                x[n_own + pl["recv_ptr"][s]: n_own + pl["recv_ptr"][s + 1]] = rb.numpy()
+
+        def spmv(x):
+            halo(x)
+            prod = A.data * x[lcol]
+            return np.add.reduceat(prod, A.indptr[:-1])
+
+        def allsum(*v):
+            t = torch.tensor(v, dtype=torch.float64)
+            dist.all_reduce(t)
+            return t.numpy()
+
+        # halo + SpMV reproduce the global operator
+        xg = np.random.default_rng(7).uniform(-1, 1, ref.n)
+        x = np.zeros(n_own + len(ghost)); x[:n_own] = xg[owned]
+        y = spmv(x)
+        np.testing.assert_allclose(y, (ref.csr() @ xg)[owned], rtol=0, atol=1e-12)
+        np.testing.assert_array_equal(x[n_own:], xg[ghost])     # ghosts landed in ghost order
+        # Chronopoulos-Gear PCG, one all-reduce per iteration
+        dinv = 1.0 / ref.csr().diagonal()[owned]
+        b = ref.b[owned]
+        X = np.zeros(n_own); r = b.copy()
+        u = np.zeros(n_own + len(ghost)); u[:n_own] = dinv * r
+        w = spmv(u)
+        gam, dlt, rr = allsum(r @ u[:n_own], w @ u[:n_own], r @ r)
+        rr0, p, s = rr, np.zeros(n_own), np.zeros(n_own)
+        gam_old = alpha_old = None
+        it = 0
+        while rr > (1e-10 ** 2) * rr0 and it < 2000:
+            beta = 0.0 if it == 0 else gam / gam_old
+            alpha = gam / (dlt if it == 0 else dlt - beta * gam / alpha_old)
+            p = u[:n_own] + beta * p; s = w + beta * s
+            X += alpha * p; r -= alpha * s
+            u[:n_own] = dinv * r
+            w = spmv(u)
+            gam_old, alpha_old = gam, alpha
+            gam, dlt, rr = allsum(r @ u[:n_own], w @ u[:n_own], r @ r)
+            it += 1
+        x_ref, it_ref, _, _ = O.pcg(ref, tol=1e-10, max_iters=2000)
+        err = np.abs(X - x_ref[owned]).max() / np.abs(x_ref).max()
+        q.put((rank, it, it_ref, float(err), None))
+        dist.destroy_process_group()
+    except Exception as e:  # noqa: BLE001
+        import traceback
+        q.put((rank, -1, -1, 1.0, traceback.format_exc()))
+
+
+@pytest.mark.parametrize("name,partitioner", [("bolted_bracket", 1), ("bolted_bracket", 0), ("mitchell_tri", 1)])
+def test_plan_drives_distributed_pcg_gloo(name, partitioner):
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29640 + partitioner + (7 if name == "mitchell_tri" else 0)
+    procs = [ctx.Process(target=_worker, args=(r, world, port, name, partitioner, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, it, it_ref, err, tb in res:
+        assert tb is None, tb
+        assert abs(it - it_ref) <= 2, (rank, it, it_ref)
+        assert err <= 1e-8, (rank, err)

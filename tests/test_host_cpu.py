@@ -1,0 +1,189 @@
+"""CPU-only tests of the host logic of libheat_b200 (no compute calls — there is no CPU fallback):
+the C ABI exports, the netCDF/Exodus reader and writer, METIS decomposition, row partitioning and
+the owned/ghost/send plan, all against independent numpy / scipy restatements."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import MESHES, ROOT, mesh_path
+
+ALL_MESHES = ["rectangle-tris-boundary", "rectangle-tris", "2blocks", "bolted_bracket", "tet-cube-heat", "mitchell_tri"]
+
+
+@pytest.fixture(scope="module")
+def hb():
+    import heat_b200
+    if not os.path.exists(heat_b200.LIB_PATH):
+        import __graft_entry__ as g
+        g.build()
+    return heat_b200
+
+
+@pytest.fixture()
+def host_io(hb):
+    """host-only context (device = -1): file I/O and decompose only"""
+    h = C.c_void_p()
+    assert hb.lib().heat_ctx_create(-1, C.byref(h)) == 0
+    io = hb.IO.__new__(hb.IO)
+    io.h = h
+    yield io
+    io.close()
+
+
+def test_abi_exports_every_declared_symbol(hb):
+    header = open(os.path.join(ROOT, "include", "heat_b200.h")).read()
+    declared = set(re.findall(r"\b(heat_[a-z0-9_]+)\s*\(", header))
+    declared -= {"heat_ctx", "heat_matrix", "heat_vector"}
+    L = hb.lib()
+    missing = [s for s in sorted(declared) if not hasattr(L, s)]
+    assert not missing, missing
+    assert set(hb.ABI_SYMBOLS) == declared
+    assert L.heat_version() == 100
+
+
+def test_compute_fails_loudly_without_gpu(hb, host_io):
+    host_io.open(mesh_path("rectangle-tris-boundary"), True)
+    with pytest.raises(hb.HeatError, match="no CPU fallback"):
+        host_io.assemble()
+    if hb.device_count() == 0:
+        with pytest.raises(hb.HeatError, match="no CUDA device"):
+            hb.IO(0)
+
+
+def test_open_errors(hb, host_io, tmp_path):
+    with pytest.raises(hb.HeatError, match="cannot open"):
+        host_io.open(str(tmp_path / "nope.exo"), True)
+    bad = tmp_path / "bad.exo"
+    bad.write_bytes(b"not a netcdf file at all")
+    with pytest.raises(hb.HeatError, match="not a netCDF classic"):
+        host_io.open(str(bad), True)
+    hdf = tmp_path / "hdf.exo"
+    hdf.write_bytes(b"\x89HDF\r\n\x1a\n" + b"\0" * 64)
+    with pytest.raises(hb.HeatError, match="HDF5"):
+        host_io.open(str(hdf), True)
+    trunc = tmp_path / "trunc.exo"
+    trunc.write_bytes(open(mesh_path("rectangle-tris-boundary"), "rb").read()[:600])
+    with pytest.raises(hb.HeatError):
+        host_io.open(str(trunc), True)
+
+
+@pytest.mark.parametrize("name", ALL_MESHES)
+def test_decompose_copies_mesh_and_matches_metis(hb, host_io, oracle, name, tmp_path):
+    """IO::decompose (ExodusIO.hpp:1496-1969): METIS_PartMeshDual with the reference's arguments, one
+    element block per partition, ids from 0; everything else copied.  Our C++ reader + writer are
+    checked against scipy.io.netcdf_file (independent implementation)."""
+    from scipy.io import netcdf_file
+    src = mesh_path(name)
+    host_io.open(src, True)
+    m = oracle.read_exodus(src)
+    ncommon = 2 if m.conn.shape[1] == 3 else 3
+    for parts in (2, 3):
+        obj, epart, npart = host_io.decompose_partition(parts, m.conn.shape[0], m.num_nodes)
+        o2, e2, n2 = oracle.metis_part_mesh_dual(m.conn, m.num_nodes, ncommon, parts)
+        assert obj == o2
+        np.testing.assert_array_equal(epart, e2)          # partition bit-exact vs the bundled METIS
+        np.testing.assert_array_equal(npart, n2)
+        out = str(tmp_path / f"{name}.{parts}.exo")
+        host_io.create(out)
+        host_io.decompose(parts)
+        a, b = netcdf_file(src, "r", mmap=False), netcdf_file(out, "r", mmap=False)
+        assert b.dimensions["num_nodes"] == m.num_nodes and b.dimensions["num_elem"] == m.conn.shape[0]
+        nonempty = [p for p in range(parts) if (epart == p).any()]
+        assert b.dimensions["num_el_blk"] == len(nonempty)
+        np.testing.assert_array_equal(b.variables["eb_prop1"].data, np.arange(len(nonempty)))
+        for k, p in enumerate(nonempty, 1):
+            conn = np.array(b.variables[f"connect{k}"].data)
+            np.testing.assert_array_equal(conn, m.conn[epart == p] + 1)
+            assert b.variables[f"connect{k}"].elem_type.decode().strip() == m.elem_type
+        for v in ("coordx", "coordy", "coordz", "node_num_map", "elem_map", "ns_prop1", "ss_prop1", "qa_records", "coor_names"):
+            if v in a.variables:
+                np.testing.assert_array_equal(np.array(a.variables[v].data), np.array(b.variables[v].data), err_msg=v)
+        for v in a.variables:
+            if v.startswith(("node_ns", "dist_fact_ns", "elem_ss", "side_ss", "dist_fact_ss")):
+                np.testing.assert_array_equal(np.array(a.variables[v].data), np.array(b.variables[v].data), err_msg=v)
+        assert b.title == a.title and b.floating_point_word_size == 8
+        a.close(); b.close()
+        # the file we wrote can be opened again by our own reader
+        h2 = C.c_void_p()
+        assert hb.lib().heat_ctx_create(-1, C.byref(h2)) == 0
+        io2 = hb.IO.__new__(hb.IO); io2.h = h2
+        io2.open(out, True)
+        io2.close()
+
+
+def test_decompose_rejects_unsupported_element_type(hb, host_io):
+    x = np.array([0.0, 1.0, 2.0]); conn = np.array([[0, 1], [1, 2]], dtype=np.int32)
+    host_io.mesh_set(x, x * 0, None, conn, {1: [0]}, num_dim=2)
+    with pytest.raises(hb.HeatError, match="unsupported element type"):
+        host_io.decompose_partition(2, 2, 3)
+
+
+# ---- partition + plan -----------------------------------------------------------------------------
+def plan_numpy(row_ptr, col, part, P, rank):
+    """Independent restatement of the Tpetra column-map / Import conventions."""
+    n = len(row_ptr) - 1
+    rows = np.repeat(np.arange(n), np.diff(row_ptr))
+
+    def ghosts(q):
+        c = col[(part[rows] == q) & (part[col] != q)]
+        c = np.unique(c)
+        return c[np.lexsort((c, part[c]))]
+
+    owned = np.flatnonzero(part == rank)
+    gh = ghosts(rank)
+    nbr, send, recv_ptr, send_ptr = [], [], [0], [0]
+    for q in range(P):
+        if q == rank:
+            continue
+        gq = ghosts(q)
+        sl = gq[part[gq] == rank]
+        nrecv = int((part[gh] == q).sum())
+        if len(sl) or nrecv:
+            nbr.append(q); send.append(sl)
+            send_ptr.append(send_ptr[-1] + len(sl)); recv_ptr.append(recv_ptr[-1] + nrecv)
+    return dict(owned=owned, ghost=gh, ghost_owner=part[gh], nbr=np.array(nbr, dtype=np.int32),
+                send_ptr=np.array(send_ptr), recv_ptr=np.array(recv_ptr),
+                send_gids=np.concatenate(send) if send else np.zeros(0, dtype=np.int64))
+
+
+@pytest.mark.parametrize("name", ["bolted_bracket", "tet-cube-heat", "mitchell_tri"])
+@pytest.mark.parametrize("P", [2, 4, 8])
+def test_partition_and_plan_bit_exact(hb, oracle, name, P):
+    s = oracle.assemble(oracle.read_exodus(mesh_path(name)), 0)
+    # METIS k-way on the row graph: same library, same arguments, from the oracle side
+    A = s.csr().copy()
+    A.setdiag(0); A.eliminate_zeros()
+    obj, part_o = oracle.metis_part_graph_kway(A.indptr, A.indices, P)
+    part = hb.partition_rows(s.row_ptr, s.col, hb.PART_METIS_KWAY, P)
+    np.testing.assert_array_equal(part, part_o)
+    assert np.bincount(part, minlength=P).min() > 0
+    # contiguous uniform map (Tpetra::Map(n, 0, comm), ExodusIO.hpp:252)
+    pc = hb.partition_rows(s.row_ptr, s.col, hb.PART_CONTIGUOUS, P)
+    cnt = np.bincount(pc, minlength=P)
+    assert np.all(np.diff(pc) >= 0) and cnt.max() - cnt.min() <= 1 and cnt[0] == -(-s.n // P)
+    for prt in (part, pc):
+        total_send = 0
+        for r in range(P):
+            got = hb.plan_build(s.row_ptr, s.col, prt, P, r)
+            exp = plan_numpy(s.row_ptr, s.col, prt, P, r)
+            for k in exp:
+                np.testing.assert_array_equal(got[k], exp[k], err_msg=f"{k} rank {r}")
+            total_send += len(got["send_gids"])
+            assert np.all(prt[got["send_gids"]] == r)
+        assert total_send == sum(len(hb.plan_build(s.row_ptr, s.col, prt, P, r)["ghost"]) for r in range(P))
+
+
+def test_single_rank_plan_is_trivial(hb, oracle):
+    s = oracle.assemble(oracle.read_exodus(mesh_path("rectangle-tris-boundary")), 0)
+    p = hb.plan_build(s.row_ptr, s.col, np.zeros(s.n, dtype=np.int32), 1, 0)
+    assert len(p["owned"]) == 3 and len(p["ghost"]) == 0 and len(p["nbr"]) == 0
+
+
+def test_cli_driver_usage(hb):
+    import subprocess
+    exe = os.path.join(ROOT, "domain-decomposed-pde-solver_b200", "bin", "heat_solver")
+    p = subprocess.run([exe], capture_output=True, text=True)
+    assert p.returncode != 0 and "No input file was provided; use the '--input' parameter!" in p.stderr
