@@ -47,8 +47,8 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 // Sum NV per-thread values over the block; result valid in thread 0.
-template <int NV>
-__device__ __forceinline__ void block_sum(double (&v)[NV], double (*sm)[kWarpsPerBlock]) {
+template <int NV, int NW = kWarpsPerBlock>
+__device__ __forceinline__ void block_sum(double (&v)[NV], double (*sm)[NW]) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int q = 0; q < NV; ++q) {
@@ -59,7 +59,7 @@ __device__ __forceinline__ void block_sum(double (&v)[NV], double (*sm)[kWarpsPe
     if (warp == 0) {
 #pragma unroll
         for (int q = 0; q < NV; ++q) {
-            double s = (lane < kWarpsPerBlock) ? sm[q][lane] : 0.0;
+            double s = (lane < NW) ? sm[q][lane] : 0.0;
             v[q] = warp_sum(s);
         }
     }
@@ -71,12 +71,13 @@ __device__ __forceinline__ void block_sum(double (&v)[NV], double (*sm)[kWarpsPe
 // Returns true in thread 0 of that last block (after out[] is written) so the caller can run
 // scalar epilogue logic.  Works across several launches sharing one counter (interior + boundary
 // SpMV): `part_offset` places this launch's partials, `total_blocks` counts all launches.
-template <int NV>
+template <int NV, int NW = kWarpsPerBlock>
 __device__ __forceinline__ bool grid_sum(double (&v)[NV], double *partials, int part_offset,
                                          int total_blocks, int *counter, double *const (&out)[NV]) {
-    __shared__ double sm[NV][kWarpsPerBlock];
+    static_assert(NW <= 32, "at most 32 warps per block");
+    __shared__ double sm[NV][NW];
     __shared__ int is_last;
-    block_sum<NV>(v, sm);
+    block_sum<NV, NW>(v, sm);
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int q = 0; q < NV; ++q) partials[q * kMaxPartials + part_offset + blockIdx.x] = v[q];
@@ -91,9 +92,9 @@ __device__ __forceinline__ bool grid_sum(double (&v)[NV], double *partials, int 
 #pragma unroll
     for (int q = 0; q < NV; ++q) {
         acc[q] = 0.0;
-        for (int i = threadIdx.x; i < total_blocks; i += kBlock) acc[q] += __ldcg(partials + q * kMaxPartials + i);
+        for (int i = threadIdx.x; i < total_blocks; i += NW * 32) acc[q] += __ldcg(partials + q * kMaxPartials + i);
     }
-    block_sum<NV>(acc, sm);
+    block_sum<NV, NW>(acc, sm);
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int q = 0; q < NV; ++q) *out[q] = acc[q];

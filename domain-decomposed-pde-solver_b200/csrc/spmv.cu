@@ -3,14 +3,23 @@
 // explicit use at ExodusMatrixTest.cpp:101).
 //
 // Format: SELL-C with C = 64 rows per slice = one warp, R = 2 adjacent rows per lane.  Entry k of
-// the two rows of a lane is one 16-byte (val) + one 8-byte (col) load, consecutive lanes are
-// consecutive in memory: every warp-level load is a fully coalesced 512 B / 256 B request.
-// val/col are read exactly once -> ld.global.nc.L1::no_allocate keeps L1 for the x gather.
-// Per-row accumulation runs left to right in CSR column order with fma() — bit-identical to
-// the CPU oracle's oracle_spmv.  Optional fused dot sum_i y_i*x_i (p.Ap of CG) is reduced
-// deterministically (device_utils.cuh: grid_sum).
+// the two rows of a lane is one 16-byte (val) + one 8-byte (col) element, consecutive lanes are
+// consecutive in memory, so a slice (or any run of k-entries of it) is ONE contiguous byte range of
+// val and ONE of col.
+//
+// Two kernels over that format, bit-identical results (per-row fma() in CSR column order, the same
+// order as the CPU oracle's oracle_spmv):
+//   * sell_spmv_tma_kernel  — the matrix stream is staged through shared memory with TMA bulk copies
+//     (cp.async.bulk.shared::cluster.global + mbarrier complete_tx), one private multi-stage ring per
+//     warp, so ~100+ KB of matrix data per SM are in flight regardless of occupancy; the consumer side
+//     reads val/col from shared memory and issues all x gathers of a chunk back to back (__ldg, L1).
+//   * sell_spmv_kernel      — direct 128-bit ld.global.nc.L1::no_allocate loads (fallback when the
+//     stage does not fit / tiny matrices, and the baseline the TMA kernel is measured against).
+// Optional fused dot sum_i y_i*x_i (p.Ap of CG) is reduced deterministically (grid_sum).
 //
 // Algorithmic bytes per launch: 12*nnz + 16*n + 4*(n+1).
+#include <cstdlib>
+
 #include "device_utils.cuh"
 #include "kernels.cuh"
 
@@ -23,6 +32,9 @@ __device__ __forceinline__ bool gate_done(const CgGate &g) {
     return !(rr > g.S[S_TOL2] * rr0);
 }
 
+// =================================================================================================
+// direct-load kernel
+// =================================================================================================
 template <bool DOT>
 __global__ void __launch_bounds__(kBlock)
 sell_spmv_kernel(const int64_t *__restrict__ slice_ptr, const int32_t *__restrict__ col,
@@ -63,15 +75,212 @@ sell_spmv_kernel(const int64_t *__restrict__ slice_ptr, const int32_t *__restric
     }
 }
 
+// =================================================================================================
+// TMA-staged kernel
+// =================================================================================================
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    }
+}
+// 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier (TMA engine, UBLKCP)
+__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <int KC, int NSTAGE>
+struct TmaSmem {
+    static constexpr int kValBytes = KC * kSellChunk * 8;
+    static constexpr int kColBytes = KC * kSellChunk * 4;
+    static constexpr int kStageBytes = kValBytes + kColBytes;
+    static constexpr int kWarpBytes = NSTAGE * kStageBytes;
+    static constexpr size_t total(int nwarps) { return (size_t)nwarps * kWarpBytes + (size_t)nwarps * NSTAGE * 8; }
+};
+
+template <bool DOT, int KC, int NSTAGE, int NWARPS>
+__global__ void __launch_bounds__(NWARPS * 32, 1)
+sell_spmv_tma_kernel(const int64_t *__restrict__ slice_ptr, const int32_t *__restrict__ col,
+                     const double *__restrict__ val, const double *__restrict__ x, double *__restrict__ y,
+                     int64_t n_rows, const int32_t *__restrict__ slice_list, int64_t n_list, CgGate gate,
+                     DotOut dot) {
+    if (gate_done(gate)) return;
+    using L = TmaSmem<KC, NSTAGE>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char *my = smem_raw + (size_t)warp * L::kWarpBytes;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)NWARPS * L::kWarpBytes) + warp * NSTAGE;
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < NSTAGE; ++s) mbar_init(bars + s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncwarp();
+
+    const int64_t W = (int64_t)gridDim.x * NWARPS;
+    const int64_t first = (int64_t)blockIdx.x * NWARPS + warp;
+    auto slice_of = [&](int64_t t) -> int64_t { return slice_list ? (int64_t)slice_list[t] : t; };
+    auto width_of = [&](int64_t s) -> int { return (int)((slice_ptr[s + 1] - slice_ptr[s]) >> 6); };
+
+    // issue cursor (runs NSTAGE chunks ahead of the consume cursor)
+    int64_t ti = first;
+    int ki = 0, wi = 0;
+    int64_t si = 0, basei = 0;
+    if (ti < n_list) { si = slice_of(ti); basei = slice_ptr[si]; wi = width_of(si); }
+    auto issue = [&](int stage) {
+        const int kc = (wi - ki) < KC ? (wi - ki) : KC;
+        if (lane == 0) {
+            if (kc > 0) {
+                unsigned char *dst = my + stage * L::kStageBytes;
+                const uint32_t vb = (uint32_t)kc * kSellChunk * 8, cb = (uint32_t)kc * kSellChunk * 4;
+                mbar_arrive_expect_tx(bars + stage, vb + cb);
+                tma_load_1d(dst, val + basei + (int64_t)ki * kSellChunk, vb, bars + stage);
+                tma_load_1d(dst + L::kValBytes, col + basei + (int64_t)ki * kSellChunk, cb, bars + stage);
+            } else {
+                mbar_arrive(bars + stage);                              // empty slice: complete the phase
+            }
+        }
+        ki += KC;
+        if (ki >= wi) {
+            ti += W; ki = 0; wi = 0;
+            if (ti < n_list) { si = slice_of(ti); basei = slice_ptr[si]; wi = width_of(si); }
+        }
+    };
+#pragma unroll
+    for (int s = 0; s < NSTAGE; ++s)
+        if (ti < n_list) issue(s);
+
+    // consume cursor
+    int64_t tc = first;
+    int kc0 = 0, wc = 0;
+    int64_t sc = 0;
+    if (tc < n_list) { sc = slice_of(tc); wc = width_of(sc); }
+    int stage = 0;
+    uint32_t parity = 0;
+    double acc0 = 0.0, acc1 = 0.0, dsum = 0.0;
+    while (tc < n_list) {
+        mbar_wait(bars + stage, parity);
+        const int kc = (wc - kc0) < KC ? (wc - kc0) : KC;
+        const double *vs = reinterpret_cast<const double *>(my + stage * L::kStageBytes) + 2 * lane;
+        const int32_t *cs = reinterpret_cast<const int32_t *>(my + stage * L::kStageBytes + L::kValBytes) + 2 * lane;
+        if (kc == KC) {
+#pragma unroll
+            for (int k = 0; k < KC; ++k) {
+                const double2 v = *reinterpret_cast<const double2 *>(vs + k * kSellChunk);
+                const int2 c = *reinterpret_cast<const int2 *>(cs + k * kSellChunk);
+                acc0 = fma(v.x, __ldg(x + c.x), acc0);
+                acc1 = fma(v.y, __ldg(x + c.y), acc1);
+            }
+        } else {
+#pragma unroll 4
+            for (int k = 0; k < kc; ++k) {
+                const double2 v = *reinterpret_cast<const double2 *>(vs + k * kSellChunk);
+                const int2 c = *reinterpret_cast<const int2 *>(cs + k * kSellChunk);
+                acc0 = fma(v.x, __ldg(x + c.x), acc0);
+                acc1 = fma(v.y, __ldg(x + c.y), acc1);
+            }
+        }
+        __syncwarp();                                    // every lane is done with this stage
+        if (ti < n_list) issue(stage);                   // refill it NSTAGE chunks ahead
+        kc0 += KC;
+        if (kc0 >= wc) {                                 // slice finished: write its 64 rows
+            const int64_t row = sc * kSellChunk + 2 * lane;
+            if (row + 1 < n_rows) {
+                *reinterpret_cast<double2 *>(y + row) = make_double2(acc0, acc1);
+                if (DOT) dsum += acc0 * __ldg(x + row) + acc1 * __ldg(x + row + 1);
+            } else if (row < n_rows) {
+                y[row] = acc0;
+                if (DOT) dsum += acc0 * __ldg(x + row);
+            }
+            acc0 = 0.0; acc1 = 0.0;
+            tc += W; kc0 = 0; wc = 0;
+            if (tc < n_list) { sc = slice_of(tc); wc = width_of(sc); }
+        }
+        if (++stage == NSTAGE) { stage = 0; parity ^= 1u; }
+    }
+    if (DOT) {
+        double acc[1] = {dsum};
+        double *const out[1] = {dot.out};
+        grid_sum<1, NWARPS>(acc, dot.partials, dot.part_offset, dot.total_blocks, dot.counter, out);
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// launch
+// -------------------------------------------------------------------------------------------------
+// variant: 0 = direct loads; 1 = TMA KC=16 x 2 stages x 8 warps; 2 = TMA KC=8 x 3 stages x 12 warps;
+//          3 = TMA KC=8 x 2 stages x 16 warps.  HEAT_SPMV_VARIANT overrides the default.
+static int spmv_variant() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("HEAT_SPMV_VARIANT");
+        v = e ? atoi(e) : 1;
+        if (v < 0 || v > 3) v = 1;
+    }
+    return v;
+}
+
+static int tma_warps(int variant) { return variant == 1 ? 8 : variant == 2 ? 12 : 16; }
+
 int spmv_grid(int64_t n_list, int sm_count) {
-    int64_t blocks = (n_list + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    return grid_for(blocks, sm_count, 8);
+    const int v = spmv_variant();
+    if (v == 0) {
+        int64_t blocks = (n_list + kWarpsPerBlock - 1) / kWarpsPerBlock;
+        return grid_for(blocks, sm_count, 8);
+    }
+    const int nw = tma_warps(v);
+    int64_t blocks = (n_list + nw - 1) / nw;
+    return grid_for(blocks, sm_count, 1);                 // persistent: one CTA per SM
+}
+
+template <bool DOT, int KC, int NSTAGE, int NWARPS>
+static int launch_tma(const heat_matrix *A, const double *x, double *y, const int32_t *slice_list, int64_t n_list,
+                      CgGate gate, DotOut dot, int grid, cudaStream_t st) {
+    auto kern = sell_spmv_tma_kernel<DOT, KC, NSTAGE, NWARPS>;
+    const size_t smem = TmaSmem<KC, NSTAGE>::total(NWARPS);
+    static bool configured = false;
+    if (!configured) {
+        HEAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    kern<<<grid, NWARPS * 32, smem, st>>>(A->slice_ptr.p, A->sell_col.p, A->sell_val.p, x, y, A->n_owned, slice_list,
+                                         n_list, gate, dot);
+    HEAT_CUDA(cudaGetLastError());
+    return 0;
 }
 
 int launch_spmv(const heat_matrix *A, const double *x, double *y, const int32_t *slice_list,
                 int64_t n_list, CgGate gate, DotOut dot, int grid, cudaStream_t st) {
     if (n_list <= 0 && dot.out == nullptr) return 0;
-    if (dot.out)
+    const int v = spmv_variant();
+    const bool d = dot.out != nullptr;
+    switch (v) {
+        case 1: return d ? launch_tma<true, 16, 2, 8>(A, x, y, slice_list, n_list, gate, dot, grid, st)
+                         : launch_tma<false, 16, 2, 8>(A, x, y, slice_list, n_list, gate, dot, grid, st);
+        case 2: return d ? launch_tma<true, 8, 3, 12>(A, x, y, slice_list, n_list, gate, dot, grid, st)
+                         : launch_tma<false, 8, 3, 12>(A, x, y, slice_list, n_list, gate, dot, grid, st);
+        case 3: return d ? launch_tma<true, 8, 2, 16>(A, x, y, slice_list, n_list, gate, dot, grid, st)
+                         : launch_tma<false, 8, 2, 16>(A, x, y, slice_list, n_list, gate, dot, grid, st);
+        default: break;
+    }
+    if (d)
         sell_spmv_kernel<true><<<grid, kBlock, 0, st>>>(A->slice_ptr.p, A->sell_col.p, A->sell_val.p, x, y,
                                                        A->n_owned, slice_list, n_list, gate, dot);
     else
