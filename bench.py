@@ -224,6 +224,13 @@ def run_ours(args):
     n_spmv = max(10, ips)
     ms_spmv = timed(lambda: io.spmv(A, xs, ys), n_spmv, 3) / n_spmv
     peak, peak_src = measured_peak()
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            ent = json.load(f).get(f"sell_spmv_tma_kernel|nx={nx}|gpus={world}")
+            traffic = ent["traffic_bytes"] if ent else None
+    except OSError:
+        pass
     spmv_gbs_total = spmv_bytes(n_full, nnz_full) / (ms_spmv * 1e-3) / 1e9        # all ranks together
     per_gpu_gbs = spmv_gbs_total / world
     cg_gbs_per_gpu = cg_iter_bytes(n_full, nnz_full) * value / 1e9 / world
@@ -271,8 +278,8 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 16 * n_own * world, "d2h_bytes_per_step": 8 * n_own * world,
                     "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps, "check_max_abs_x": res_check},
             "gpu_launches": args.steps * (ips * per_iter + per_step_setup + 1),
-            "roofline": {"bound": "hbm", "kernel": "sell_spmv_kernel (fp64 SELL-64 SpMV)", "achieved": per_gpu_gbs, "peak": peak,
-                         "unit": "GB/s", "frac": per_gpu_gbs / peak, "traffic": None, "peak_source": peak_src,
+            "roofline": {"bound": "hbm", "kernel": "sell_spmv_tma_kernel (fp64 SELL-64 SpMV, TMA-staged)", "achieved": per_gpu_gbs, "peak": peak,
+                         "unit": "GB/s", "frac": per_gpu_gbs / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": spmv_bytes(n_full, nnz_full) / world, "ms_per_launch": ms_spmv,
                          "launches_timed": n_spmv},
             "roofline_cg_iteration": {"bound": "hbm", "achieved": cg_gbs_per_gpu, "peak": peak, "unit": "GB/s",

@@ -100,9 +100,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     }
 }
 // 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier (TMA engine, UBLKCP)
-__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+// The matrix stream is read exactly once: L2::evict_first keeps it from flushing the x vector (which
+// every row gathers ~15 times, up to a whole k-plane apart) out of the 126 MB L2.
+__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar,
+                                            uint64_t policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
+}
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
 }
 
 template <int KC, int NSTAGE>
@@ -115,7 +123,7 @@ struct TmaSmem {
 };
 
 template <bool DOT, int KC, int NSTAGE, int NWARPS>
-__global__ void __launch_bounds__(NWARPS * 32, 1)
+__global__ void __launch_bounds__(NWARPS * 32, (NWARPS <= 8 && KC <= 8) ? 2 : 1)
 sell_spmv_tma_kernel(const int64_t *__restrict__ slice_ptr, const int32_t *__restrict__ col,
                      const double *__restrict__ val, const double *__restrict__ x, double *__restrict__ y,
                      int64_t n_rows, const int32_t *__restrict__ slice_list, int64_t n_list, CgGate gate,
@@ -134,6 +142,7 @@ sell_spmv_tma_kernel(const int64_t *__restrict__ slice_ptr, const int32_t *__res
     }
     __syncwarp();
 
+    const uint64_t policy = l2_evict_first_policy();
     const int64_t W = (int64_t)gridDim.x * NWARPS;
     const int64_t first = (int64_t)blockIdx.x * NWARPS + warp;
     auto slice_of = [&](int64_t t) -> int64_t { return slice_list ? (int64_t)slice_list[t] : t; };
@@ -151,8 +160,8 @@ sell_spmv_tma_kernel(const int64_t *__restrict__ slice_ptr, const int32_t *__res
                 unsigned char *dst = my + stage * L::kStageBytes;
                 const uint32_t vb = (uint32_t)kc * kSellChunk * 8, cb = (uint32_t)kc * kSellChunk * 4;
                 mbar_arrive_expect_tx(bars + stage, vb + cb);
-                tma_load_1d(dst, val + basei + (int64_t)ki * kSellChunk, vb, bars + stage);
-                tma_load_1d(dst + L::kValBytes, col + basei + (int64_t)ki * kSellChunk, cb, bars + stage);
+                tma_load_1d(dst, val + basei + (int64_t)ki * kSellChunk, vb, bars + stage, policy);
+                tma_load_1d(dst + L::kValBytes, col + basei + (int64_t)ki * kSellChunk, cb, bars + stage, policy);
             } else {
                 mbar_arrive(bars + stage);                              // empty slice: complete the phase
             }
@@ -226,18 +235,19 @@ sell_spmv_tma_kernel(const int64_t *__restrict__ slice_ptr, const int32_t *__res
 // launch
 // -------------------------------------------------------------------------------------------------
 // variant: 0 = direct loads; 1 = TMA KC=16 x 2 stages x 8 warps; 2 = TMA KC=8 x 3 stages x 12 warps;
-//          3 = TMA KC=8 x 2 stages x 16 warps.  HEAT_SPMV_VARIANT overrides the default.
+//          3 = TMA KC=8 x 2 stages x 16 warps; 4 = TMA KC=4 x 3 stages x 24 warps; 5 = TMA KC=8 x 3 x 8
+//          (2 CTAs/SM).  HEAT_SPMV_VARIANT overrides the default.
 static int spmv_variant() {
     static int v = -1;
     if (v < 0) {
         const char *e = getenv("HEAT_SPMV_VARIANT");
-        v = e ? atoi(e) : 1;
-        if (v < 0 || v > 3) v = 1;
+        v = e ? atoi(e) : 5;
+        if (v < 0 || v > 5) v = 5;
     }
     return v;
 }
 
-static int tma_warps(int variant) { return variant == 1 ? 8 : variant == 2 ? 12 : 16; }
+static int tma_warps(int variant) { return variant == 1 ? 8 : variant == 2 ? 12 : variant == 3 ? 16 : variant == 4 ? 24 : 8; }
 
 int spmv_grid(int64_t n_list, int sm_count) {
     const int v = spmv_variant();
@@ -247,7 +257,7 @@ int spmv_grid(int64_t n_list, int sm_count) {
     }
     const int nw = tma_warps(v);
     int64_t blocks = (n_list + nw - 1) / nw;
-    return grid_for(blocks, sm_count, 1);                 // persistent: one CTA per SM
+    return grid_for(blocks, sm_count, v == 5 ? 2 : 1);    // persistent: one (or two) CTA per SM
 }
 
 template <bool DOT, int KC, int NSTAGE, int NWARPS>
@@ -278,6 +288,10 @@ int launch_spmv(const heat_matrix *A, const double *x, double *y, const int32_t 
                          : launch_tma<false, 8, 3, 12>(A, x, y, slice_list, n_list, gate, dot, grid, st);
         case 3: return d ? launch_tma<true, 8, 2, 16>(A, x, y, slice_list, n_list, gate, dot, grid, st)
                          : launch_tma<false, 8, 2, 16>(A, x, y, slice_list, n_list, gate, dot, grid, st);
+        case 4: return d ? launch_tma<true, 4, 3, 24>(A, x, y, slice_list, n_list, gate, dot, grid, st)
+                         : launch_tma<false, 4, 3, 24>(A, x, y, slice_list, n_list, gate, dot, grid, st);
+        case 5: return d ? launch_tma<true, 8, 2, 8>(A, x, y, slice_list, n_list, gate, dot, grid, st)
+                         : launch_tma<false, 8, 2, 8>(A, x, y, slice_list, n_list, gate, dot, grid, st);
         default: break;
     }
     if (d)

@@ -279,3 +279,108 @@ def test_write_solution_round_trip(hb, io, oracle, tmp_path):
     assert nc.dimensions["num_el_blk"] == 4
     assert np.array(nc.variables["eb_prop1"].data).tolist() == [0, 1, 2, 3]     # block ids start at 0 (D12)
     nc.close()
+
+
+# ---- edge cases ------------------------------------------------------------------------------------
+def test_mesh_without_nodesets_is_the_full_laplacian(hb, io, oracle):
+    """2blocks.exo: two TETRA4 blocks, no nodesets -> every node is a DOF, B = 0, A singular (A.1 = 0);
+    the status test fires before the first iteration (r0 = 0)."""
+    io.open(mesh_path("2blocks"), True)
+    A, X, B = io.assemble(hb.OP_GRAPH_LAPLACIAN)
+    ref = oracle.assemble(oracle.read_exodus(mesh_path("2blocks")), 0)
+    rp, col, val = A.csr()
+    np.testing.assert_array_equal(rp, ref.row_ptr); np.testing.assert_array_equal(col, ref.col)
+    np.testing.assert_array_equal(val, ref.val)
+    assert A.info.n_global == 34 and np.all(B.numpy() == 0)
+    ones, y = A.new_vector().fill(1.0), A.new_vector()
+    io.spmv(A, ones, y)
+    assert np.all(y.numpy() == 0)
+    res = io.solve(A, X, B, max_iters=10, tol=1e-10)
+    assert res.iters == 0 and res.converged and np.all(X.numpy() == 0)
+
+
+def test_mesh_from_memory_and_overlapping_nodesets(hb, io, oracle):
+    """heat_mesh_set + a node in two nodesets: lowest id wins for RHS and output (D2, FIXED)."""
+    m = oracle.cube_mesh(5, 4, 3)
+    ns = {7: np.flatnonzero(m.x == -5.0), 3: np.flatnonzero((m.x == -5.0) & (m.y == -5.0)), 50: np.flatnonzero(m.x == 5.0)}
+    m.nodesets = ns
+    ref = oracle.assemble(m, 1)
+    io.mesh_set(m.x, m.y, m.z, m.conn, ns)
+    A, X, B = io.assemble(hb.OP_P1_FEM)
+    rp, col, val = A.csr()
+    np.testing.assert_array_equal(col, ref.col); np.testing.assert_array_equal(val, ref.val)
+    np.testing.assert_array_equal(B.numpy(), ref.b)
+    io.solve(A, X, B, max_iters=200, tol=1e-12)
+    f = io.nodal_field(X, m.num_nodes)
+    assert np.all(f[ns[3]] == 3.0) and np.all(f[np.setdiff1d(ns[7], ns[3])] == 7.0) and np.all(f[ns[50]] == 50.0)
+
+
+def test_p1_rejects_unsupported_elements(hb, io):
+    x = np.array([0.0, 1.0, 2.0, 3.0])
+    conn = np.array([[0, 1], [1, 2], [2, 3]], dtype=np.int32)           # 2-node "bars"
+    io.mesh_set(x, x * 0, None, conn, {1: [0], 2: [3]}, num_dim=1)
+    A, X, B = io.assemble(hb.OP_GRAPH_LAPLACIAN)                        # cliques of any size are fine
+    np.testing.assert_array_equal(A.csr()[2], [2.0, -1.0, -1.0, 2.0])
+    np.testing.assert_array_equal(B.numpy(), [1.0, 2.0])
+    with pytest.raises(hb.HeatError, match="P1_FEM needs"):
+        io.assemble(hb.OP_P1_FEM)
+
+
+def test_hex_like_cliques_graph_mode(hb, io, oracle):
+    """8-node elements (HEX8 connectivity treated as cliques, as assemble does for any element type)."""
+    nx = 4
+    idx = lambda i, j, k: i + nx * (j + nx * k)  # noqa: E731
+    conn = np.array([[idx(i, j, k), idx(i + 1, j, k), idx(i + 1, j + 1, k), idx(i, j + 1, k),
+                      idx(i, j, k + 1), idx(i + 1, j, k + 1), idx(i + 1, j + 1, k + 1), idx(i, j + 1, k + 1)]
+                     for k in range(nx - 1) for j in range(nx - 1) for i in range(nx - 1)], dtype=np.int32)
+    g = np.arange(nx ** 3)
+    x, y, z = (g % nx).astype(float), ((g // nx) % nx).astype(float), (g // nx ** 2).astype(float)
+    ns = {10: np.flatnonzero(x == 0), 20: np.flatnonzero(x == nx - 1)}
+    m = oracle.Mesh(x, y, z, conn, ns, "HEX8", 3, [len(conn)])
+    ref = oracle.assemble(m, 0)
+    io.mesh_set(x, y, z, conn, ns)
+    A, X, B = io.assemble(hb.OP_GRAPH_LAPLACIAN)
+    rp, col, val = A.csr()
+    np.testing.assert_array_equal(rp, ref.row_ptr); np.testing.assert_array_equal(col, ref.col)
+    np.testing.assert_array_equal(val, ref.val); np.testing.assert_array_equal(B.numpy(), ref.b)
+    assert A.info.max_row_len == 27 - 9        # interior node: 26 neighbours + itself, minus none... checked vs oracle
+    res = io.solve(A, X, B, max_iters=500, tol=1e-10)
+    xr = oracle.pcg(ref, tol=1e-10)[0]
+    assert res.converged and np.abs(X.numpy() - xr).max() <= 1e-8 * np.abs(xr).max()
+
+
+def test_spmv_variants_bit_identical(hb, oracle):
+    """Every SpMV kernel variant (direct loads, TMA-staged rings) gives the same bits."""
+    import subprocess, sys, json as _json
+    code = ("import os,sys,hashlib;sys.path.insert(0,os.path.join(%r,'domain-decomposed-pde-solver_b200'));"
+            "import heat_b200 as hb;io=hb.IO(0);io.mesh_cube(40,33,29);A,X,B=io.assemble(1);"
+            "x=A.hash_vector(7);y=A.new_vector();io.spmv(A,x,y);r=io.cg_iterations(A,X,B,25);"
+            "print(hashlib.sha1(y.numpy().tobytes()).hexdigest(), hashlib.sha1(X.numpy().tobytes()).hexdigest())")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = set()
+    for v in range(6):
+        env = dict(os.environ, HEAT_SPMV_VARIANT=str(v))
+        p = subprocess.run([sys.executable, "-c", code % root], capture_output=True, text=True, env=env, timeout=300)
+        assert p.returncode == 0, p.stderr[-2000:]
+        outs.add(p.stdout.strip().split()[0])
+    assert len(outs) == 1, outs
+
+
+def test_cli_driver_end_to_end(hb, oracle, tmp_path):
+    """bin/heat_solver: the reference's BelosMueLuSolver call order from the command line."""
+    import subprocess
+    from scipy.io import netcdf_file
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "domain-decomposed-pde-solver_b200", "bin", "heat_solver")
+    out = str(tmp_path / "solution.exo")
+    p = subprocess.run([exe, f"--input={mesh_path('tet-cube-heat')}", f"--solution={out}", "--iterations=1000",
+                        "--tolerance=1e-10", "--operator=p1", "--partitions=4"], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr
+    assert "The Belos solve took 180 iteration(s) to reach a relative residual tolerance" in p.stdout or \
+           "The Belos solve took 181" in p.stdout or "The Belos solve took 179" in p.stdout, p.stdout
+    nc = netcdf_file(out, "r", mmap=False)
+    f = np.array(nc.variables["vals_nod_var1"].data)[0]
+    xs = np.array(nc.variables["coordx"].data)
+    assert np.abs(f - (550.0 - 90.0 * xs)).max() < 1e-5
+    assert nc.dimensions["num_el_blk"] == 4
+    nc.close()
