@@ -405,6 +405,7 @@ extern "C" int heat_matrix_get_info(const heat_matrix *A, heat_matrix_info *info
     info->sell_chunk = kSellChunk; info->sell_padded_nnz = A->sell_padded;
     info->n_boundary_slices = A->n_bnd_slices; info->n_slices = A->n_slices;
     info->assemble_ms = A->assemble_ms;
+    info->peer_path = A->peer ? 1 : 0;
     return 0;
 }
 
@@ -466,7 +467,7 @@ extern "C" int heat_matrix_export_red2orig(const heat_matrix *A, int64_t *out) {
 }
 
 extern "C" int heat_matrix_free(heat_matrix *A) {
-    if (A) { cudaSetDevice(A->ctx->device); cudaStreamSynchronize(A->ctx->stream); delete A; }
+    if (A) { cudaSetDevice(A->ctx->device); cudaStreamSynchronize(A->ctx->stream); peer_matrix_teardown(A); delete A; }
     return 0;
 }
 

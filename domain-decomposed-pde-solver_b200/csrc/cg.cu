@@ -16,6 +16,7 @@
 //   spmv+dot    : w = A u ; H[k+1].delta = w.u     -> ONE all-reduce of {rz, delta, rr}
 #include "device_utils.cuh"
 #include "kernels.cuh"
+#include "peer.cuh"
 
 namespace heat {
 
@@ -142,6 +143,149 @@ __global__ void __launch_bounds__(kBlock) cg_update_p_kernel(int64_t n, double *
 int launch_cg_update_p(int64_t n, double *p, const double *r, const double *dinv, CgGate gate,
                        int grid, cudaStream_t st) {
     cg_update_p_kernel<<<grid, kBlock, 0, st>>>(n, p, r, dinv, gate);
+    HEAT_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+// peer-memory variants (peer.cuh): no NCCL inside the iteration
+// -------------------------------------------------------------------------------------------------
+// classical update_xr: alpha needs the GLOBAL p.Ap -> wait for reduction `seq_in`; the local sums
+// r.z, r.r are published to every rank as reduction `seq_out` by the last block.
+__global__ void __launch_bounds__(kBlock) cg_update_xr_peer_kernel(int64_t n, double *__restrict__ x,
+                                                                   double *__restrict__ r,
+                                                                   const double *__restrict__ p,
+                                                                   const double *__restrict__ ap,
+                                                                   const double *__restrict__ dinv, CgGate g,
+                                                                   CgRec *H, double *S, int *I, double *partials,
+                                                                   int *counter, PeerRed pr,
+                                                                   unsigned long long seq_in,
+                                                                   unsigned long long seq_out) {
+    if (cg_done(g)) return;
+    __shared__ double sh[2];
+    if (threadIdx.x == 0) {
+        double o[3];
+        const bool ok = peer_red_wait(pr, seq_in, o, I);
+        sh[0] = o[0]; sh[1] = ok ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    if (sh[1] == 0.0) return;                              // communication timeout: I_STATUS = 3
+    const double pap = sh[0];
+    if (!(pap > 0.0)) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) I[I_STATUS] = 2;
+        return;
+    }
+    const double alpha = H[g.it].rz / pap;
+    double acc[2] = {0.0, 0.0};
+    const int64_t n2 = n >> 1, stride = (int64_t)gridDim.x * kBlock;
+    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n2; i += stride) {
+        double2 pv = ld_stream_f64x2(p + 2 * i), av = ld_stream_f64x2(ap + 2 * i), dv = ld_stream_f64x2(dinv + 2 * i);
+        double2 xv = *reinterpret_cast<const double2 *>(x + 2 * i);
+        double2 rv = *reinterpret_cast<const double2 *>(r + 2 * i);
+        xv.x = fma(alpha, pv.x, xv.x); xv.y = fma(alpha, pv.y, xv.y);
+        rv.x = fma(-alpha, av.x, rv.x); rv.y = fma(-alpha, av.y, rv.y);
+        *reinterpret_cast<double2 *>(x + 2 * i) = xv;
+        *reinterpret_cast<double2 *>(r + 2 * i) = rv;
+        acc[0] += (dv.x * rv.x) * rv.x + (dv.y * rv.y) * rv.y;
+        acc[1] += rv.x * rv.x + rv.y * rv.y;
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        const int64_t i = n - 1;
+        double xv = fma(alpha, p[i], x[i]), rv = fma(-alpha, ap[i], r[i]);
+        x[i] = xv; r[i] = rv;
+        acc[0] += (dinv[i] * rv) * rv; acc[1] += rv * rv;
+    }
+    double *const out[2] = {S + S_TMP0, S + S_TMP1};
+    if (grid_sum<2>(acc, partials, 0, gridDim.x, counter, out)) {
+        H[g.it].alpha = alpha;
+        peer_red_push(pr, seq_out, S[S_TMP0], S[S_TMP1], 0.0);
+    }
+}
+
+int launch_cg_update_xr_peer(int64_t n, double *x, double *r, const double *p, const double *ap, const double *dinv,
+                             CgGate gate, CgRec *H, double *S, int *I, double *partials, int *counter, PeerRed pr,
+                             unsigned long long seq_in, unsigned long long seq_out, int grid, cudaStream_t st) {
+    cg_update_xr_peer_kernel<<<grid, kBlock, 0, st>>>(n, x, r, p, ap, dinv, gate, H, S, I, partials, counter, pr, seq_in, seq_out);
+    HEAT_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// boundary entries of v = (compute(i)) go straight into the neighbours' ghost segments, then the
+// epoch flags are raised by the last of the pushing blocks
+template <typename F>
+__device__ __forceinline__ void peer_push_phase(const PeerPush &push, F value_of) {
+    if ((int)blockIdx.x >= push.n_blocks) return;
+    const long long total = push.send_ptr[push.n_nbr];
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)push.n_blocks * blockDim.x) {
+        int s = 0;
+        while (t >= push.send_ptr[s + 1]) ++s;
+        push.dst[s][t - push.send_ptr[s]] = value_of(push.send_idx[t]);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int tk = atomicAdd(push.ticket, 1);
+        if (tk == push.n_blocks - 1) {
+            __threadfence_system();
+            for (int s = 0; s < push.n_nbr; ++s) st_release_sys(push.flag[s], push.epoch);
+            *push.ticket = 0;
+        }
+    }
+}
+
+// classical update_p: beta needs the GLOBAL r.z (reduction `seq_in`); block 0 records the global
+// {r.z, r.r} in H[it+1]; p_out = D^-1 r + beta p_in (ping-pong buffers) and the halo push of p_out.
+__global__ void __launch_bounds__(kBlock) cg_update_p_peer_kernel(int64_t n, double *p_out, const double *p_in,
+                                                                  const double *__restrict__ r,
+                                                                  const double *__restrict__ dinv, CgGate g,
+                                                                  CgRec *H, int *I, PeerRed pr,
+                                                                  unsigned long long seq_in, PeerPush push) {
+    if (cg_done(g)) return;
+    __shared__ double sh[3];
+    if (threadIdx.x == 0) {
+        double o[3];
+        const bool ok = peer_red_wait(pr, seq_in, o, I);
+        sh[0] = o[0]; sh[1] = o[1]; sh[2] = ok ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    if (sh[2] == 0.0) return;
+    const double rz_new = sh[0], rr_new = sh[1];
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        H[g.it + 1].rz = rz_new; H[g.it + 1].rr = rr_new;
+        I[I_ITERS] = g.it + 1;
+    }
+    if (!(rr_new > g.S[S_TOL2] * g.H[0].rr)) return;        // converged: p is never used again
+    const double beta = rz_new / g.H[g.it].rz;
+    peer_push_phase(push, [&](int32_t i) { return fma(beta, p_in[i], dinv[i] * r[i]); });
+    const int64_t n2 = n >> 1, stride = (int64_t)gridDim.x * kBlock;
+    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n2; i += stride) {
+        double2 rv = ld_stream_f64x2(r + 2 * i), dv = ld_stream_f64x2(dinv + 2 * i);
+        double2 pv = *reinterpret_cast<const double2 *>(p_in + 2 * i);
+        pv.x = fma(beta, pv.x, dv.x * rv.x); pv.y = fma(beta, pv.y, dv.y * rv.y);
+        *reinterpret_cast<double2 *>(p_out + 2 * i) = pv;
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        const int64_t i = n - 1;
+        p_out[i] = fma(beta, p_in[i], dinv[i] * r[i]);
+    }
+}
+
+int launch_cg_update_p_peer(int64_t n, double *p_out, const double *p_in, const double *r, const double *dinv,
+                            CgGate gate, CgRec *H, int *I, PeerRed pr, unsigned long long seq_in, PeerPush push,
+                            int grid, cudaStream_t st) {
+    if (push.n_blocks > grid) push.n_blocks = grid;
+    cg_update_p_peer_kernel<<<grid, kBlock, 0, st>>>(n, p_out, p_in, r, dinv, gate, H, I, pr, seq_in, push);
+    HEAT_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// stand-alone halo push of an existing vector (the first SpMV input of a solve)
+__global__ void __launch_bounds__(kBlock) halo_push_kernel(const double *__restrict__ x, PeerPush push) {
+    peer_push_phase(push, [&](int32_t i) { return x[i]; });
+}
+int launch_halo_push(const double *x, PeerPush push, cudaStream_t st) {
+    if (push.n_blocks < 1) push.n_blocks = 1;
+    halo_push_kernel<<<push.n_blocks, kBlock, 0, st>>>(x, push);
     HEAT_CUDA(cudaGetLastError());
     return 0;
 }

@@ -11,6 +11,7 @@
 
 #include "comm.cuh"
 #include "kernels.cuh"
+#include "peer.cuh"
 
 namespace heat {
 
@@ -60,7 +61,9 @@ static int nccl_load() {
         if (r__ != ncclSuccess) HEAT_FAIL(41, "%s:%d: %s -> %s", __FILE__, __LINE__, #call, heat::g_nccl.GetErrorString(r__)); \
     } while (0)
 
+void peer_arena_teardown(heat_ctx *ctx);
 int comm_destroy(heat_ctx *ctx) {
+    peer_arena_teardown(ctx);
     if (ctx->nccl_comm && g_nccl.handle) g_nccl.CommDestroy((ncclComm_t)ctx->nccl_comm);
     ctx->nccl_comm = nullptr;
     return 0;
@@ -99,6 +102,158 @@ int halo_end(heat_ctx *ctx, heat_matrix *A) {
     if (ctx->nranks <= 1 || A->halo.n_neighbors == 0) return 0;
     HEAT_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_halo, 0));
     return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+// peer-memory path set-up (peer.cuh): CUDA-IPC exchange of the arenas and of the SpMV-input buffers
+// -------------------------------------------------------------------------------------------------
+static int allgather_bytes(heat_ctx *ctx, const void *mine, size_t bytes, std::vector<unsigned char> &all) {
+    const int P = ctx->nranks;
+    DevBuf<unsigned char> d;
+    HEAT_TRY(d.alloc(bytes * (size_t)P));
+    HEAT_CUDA(cudaMemcpyAsync(d.p + bytes * (size_t)ctx->rank, mine, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    HEAT_NCCL(g_nccl.AllGather(d.p + bytes * (size_t)ctx->rank, d.p, bytes, ncclChar, (ncclComm_t)ctx->nccl_comm, ctx->stream));
+    all.resize(bytes * (size_t)P);
+    HEAT_CUDA(cudaMemcpyAsync(all.data(), d.p, all.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    HEAT_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// every rank must reach the same verdict: all-reduce (min) of a local ok flag through the gather
+static int all_agree(heat_ctx *ctx, int ok_local, int *ok_all) {
+    std::vector<unsigned char> all;
+    unsigned char mine = ok_local ? 1 : 0;
+    HEAT_TRY(allgather_bytes(ctx, &mine, 1, all));
+    int ok = 1;
+    for (unsigned char c : all) ok &= (c != 0);
+    *ok_all = ok;
+    return 0;
+}
+
+int peer_arena_setup(heat_ctx *ctx) {
+    ctx->peer_enabled = false;
+    const char *env = getenv("HEAT_COMM");
+    if (env && strcmp(env, "nccl") == 0) return 0;
+    if (ctx->nranks < 2 || ctx->nranks > kPeerMaxRanks) return 0;
+    int ok = 1;
+    cudaIpcMemHandle_t mine;
+    memset(&mine, 0, sizeof(mine));
+    if (cudaMalloc((void **)&ctx->peer_arena, sizeof(unsigned long long) * kPeerArenaWords) != cudaSuccess) ok = 0;
+    if (ok && cudaMemset(ctx->peer_arena, 0, sizeof(unsigned long long) * kPeerArenaWords) != cudaSuccess) ok = 0;
+    if (ok && cudaIpcGetMemHandle(&mine, ctx->peer_arena) != cudaSuccess) ok = 0;
+    cudaGetLastError();
+    std::vector<unsigned char> all;
+    HEAT_TRY(allgather_bytes(ctx, &mine, sizeof(mine), all));
+    if (ok) {
+        for (int q = 0; q < ctx->nranks && ok; ++q) {
+            if (q == ctx->rank) { ctx->peer_arena_of[q] = ctx->peer_arena; continue; }
+            cudaIpcMemHandle_t h;
+            memcpy(&h, all.data() + sizeof(h) * (size_t)q, sizeof(h));
+            void *mapped = nullptr;
+            if (cudaIpcOpenMemHandle(&mapped, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); }
+            ctx->peer_arena_of[q] = (unsigned long long *)mapped;
+        }
+    }
+    int ok_all = 0;
+    HEAT_TRY(all_agree(ctx, ok, &ok_all));
+    ctx->peer_enabled = ok_all != 0;
+    return 0;
+}
+
+void peer_arena_teardown(heat_ctx *ctx) {
+    for (int q = 0; q < kPeerMaxRanks; ++q) {
+        if (ctx->peer_arena_of[q] && ctx->peer_arena_of[q] != ctx->peer_arena) cudaIpcCloseMemHandle(ctx->peer_arena_of[q]);
+        ctx->peer_arena_of[q] = nullptr;
+    }
+    if (ctx->peer_arena) cudaFree(ctx->peer_arena);
+    ctx->peer_arena = nullptr;
+    ctx->peer_enabled = false;
+}
+
+PeerRed peer_red_of(const heat_ctx *ctx) {
+    PeerRed pr;
+    if (!ctx->peer_enabled) return pr;
+    pr.P = ctx->nranks; pr.rank = ctx->rank;
+    for (int q = 0; q < ctx->nranks; ++q) pr.inbox[q] = ctx->peer_arena_of[q];
+    return pr;
+}
+
+struct PeerRecord {                   // what every rank tells the others about one matrix
+    cudaIpcMemHandle_t h_p[2];
+    long long n_owned;
+    int n_nbr;
+    int nbr_rank[kPeerMaxNbr];
+    long long recv_ptr[kPeerMaxNbr + 1];
+};
+
+// Collective.  Allocates the ping-pong SpMV-input buffers (w_p, w_p2), exchanges their IPC handles and
+// builds the two push plans.  On any failure on any rank the matrix silently stays on the NCCL path.
+int peer_matrix_setup(heat_ctx *ctx, heat_matrix *A) {
+    if (A->peer || !ctx->peer_enabled) return 0;
+    const HaloPlan &h = A->halo;
+    const size_t nv = (size_t)(A->n_owned + A->n_ghost);
+    int ok = (h.n_neighbors <= kPeerMaxNbr) && spmv_peer_supported() && (A->n_ghost == 0 || A->slices_all.p != nullptr);
+    PeerRecord mine;
+    memset(&mine, 0, sizeof(mine));
+    if (!A->w_p.p && A->w_p.alloc(nv)) ok = 0;
+    if (!A->w_p2.p && A->w_p2.alloc(nv)) ok = 0;
+    if (ok) {
+        if (cudaIpcGetMemHandle(&mine.h_p[0], A->w_p.p) != cudaSuccess) ok = 0;
+        if (cudaIpcGetMemHandle(&mine.h_p[1], A->w_p2.p) != cudaSuccess) ok = 0;
+        cudaGetLastError();
+        mine.n_owned = A->n_owned; mine.n_nbr = h.n_neighbors;
+        for (int s = 0; s < h.n_neighbors && s < kPeerMaxNbr; ++s) { mine.nbr_rank[s] = h.nbr_rank[s]; mine.recv_ptr[s] = h.recv_ptr[s]; }
+        if (h.n_neighbors <= kPeerMaxNbr) mine.recv_ptr[h.n_neighbors] = h.n_neighbors ? h.recv_ptr[h.n_neighbors] : 0;
+    }
+    std::vector<unsigned char> all;
+    HEAT_TRY(allgather_bytes(ctx, &mine, sizeof(mine), all));
+    PeerMatrixState *st = new PeerMatrixState();
+    if (ok) {
+        for (int b = 0; b < 2; ++b) {
+            PeerPush &pp = st->push[b];
+            pp.n_nbr = h.n_neighbors;
+            pp.send_idx = h.d_send_idx.p;
+            pp.ticket = A->iscal.p + I_COUNTER + 2;                   // I[4]: push ticket
+            for (int s = 0; s <= h.n_neighbors; ++s) pp.send_ptr[s] = h.n_neighbors ? h.send_ptr[s] : 0;
+        }
+        for (int s = 0; s < h.n_neighbors && ok; ++s) {
+            const int q = h.nbr_rank[s];
+            PeerRecord rec;
+            memcpy(&rec, all.data() + sizeof(rec) * (size_t)q, sizeof(rec));
+            int sp = -1;
+            for (int t = 0; t < rec.n_nbr && t < kPeerMaxNbr; ++t) if (rec.nbr_rank[t] == ctx->rank) sp = t;
+            if (sp < 0 || rec.recv_ptr[sp + 1] - rec.recv_ptr[sp] != h.send_ptr[s + 1] - h.send_ptr[s]) { ok = 0; break; }
+            for (int b = 0; b < 2; ++b) {
+                void *mapped = nullptr;
+                if (cudaIpcOpenMemHandle(&mapped, rec.h_p[b], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); break; }
+                st->mapped.push_back(mapped);
+                st->push[b].dst[s] = (double *)mapped + rec.n_owned + rec.recv_ptr[sp];
+                st->push[b].flag[s] = ctx->peer_arena_of[q] + kPeerInboxWords + sp;
+            }
+        }
+    }
+    int ok_all = 0;
+    HEAT_TRY(all_agree(ctx, ok, &ok_all));
+    if (!ok_all) {
+        for (void *m : st->mapped) cudaIpcCloseMemHandle(m);
+        delete st;
+        return 0;
+    }
+    const long long total = h.n_neighbors ? h.send_ptr[h.n_neighbors] : 0;
+    int nb = (int)((total + 4 * 256 - 1) / (4 * 256));
+    nb = nb < 1 ? 1 : nb > 64 ? 64 : nb;
+    st->push[0].n_blocks = st->push[1].n_blocks = nb;
+    st->halo.n_nbr = h.n_neighbors;
+    st->halo.flags = ctx->peer_arena + kPeerInboxWords;
+    A->peer = st;
+    return 0;
+}
+
+void peer_matrix_teardown(heat_matrix *A) {
+    if (!A->peer) return;
+    for (void *m : A->peer->mapped) cudaIpcCloseMemHandle(m);
+    delete A->peer;
+    A->peer = nullptr;
 }
 
 // Gather every rank's owned values on rank 0 in reduced-id order (the blocking Send/Recv gather of
@@ -188,11 +343,13 @@ extern "C" int heat_comm_init(heat_ctx *ctx, int rank, int nranks, const char id
     ctx->nccl_comm = comm;
     ctx->rank = rank;
     ctx->nranks = nranks;
+    if (!ctx->ev_halo) HEAT_FAIL(3, "heat_comm_init: context has no CUDA resources");
     if (!ctx->comm_stream) {
         int lo = 0, hi = 0;
         HEAT_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
         HEAT_CUDA(cudaStreamCreateWithPriority(&ctx->comm_stream, cudaStreamNonBlocking, hi));
     }
+    HEAT_TRY(heat::peer_arena_setup(ctx));
     return 0;
 }
 

@@ -1,6 +1,7 @@
 // comm.cuh — multi-GPU plumbing (definitions in comm.cu).
 #pragma once
 #include "common.cuh"
+#include "peer.cuh"
 
 namespace heat {
 int comm_destroy(heat_ctx *ctx);
@@ -9,4 +10,14 @@ int halo_begin(heat_ctx *ctx, heat_matrix *A, double *x);           // pack + se
 int halo_end(heat_ctx *ctx, heat_matrix *A);                        // main stream waits for the ghosts
 int comm_gather_reduced(heat_ctx *ctx, const std::vector<double> &x_owned, int64_t n_global,
                         std::vector<double> &x_global_on_root);
+// peer-memory path (peer.cuh)
+PeerRed peer_red_of(const heat_ctx *ctx);
+int peer_matrix_setup(heat_ctx *ctx, heat_matrix *A);          // collective; leaves A->peer null on failure
+void peer_matrix_teardown(heat_matrix *A);
 }  // namespace heat
+
+struct PeerMatrixState {
+    heat::PeerPush push[2];            // push plan into the neighbours' buffer 0 / buffer 1
+    heat::PeerHalo halo;               // my flags
+    std::vector<void *> mapped;        // cudaIpcOpenMemHandle mappings to close
+};

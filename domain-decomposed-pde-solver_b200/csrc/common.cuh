@@ -89,6 +89,8 @@ enum { I_ITERS = 0, I_STATUS = 1, I_COUNTER = 2, I_COUNTER2 = 3, I_COUNT = 8 };
 
 }  // namespace heat
 
+struct PeerMatrixState;    // comm.cu: CUDA-IPC mappings + push plans of one matrix (peer-memory halo path)
+
 struct heat_vector {
     heat_ctx *ctx = nullptr;
     int64_t n_owned = 0, n_ghost = 0;
@@ -121,6 +123,7 @@ struct heat_matrix {
     heat::DevBuf<int32_t> sell_col;
     heat::DevBuf<double> sell_val;
     heat::DevBuf<int32_t> slices_interior, slices_boundary;   // slice id lists (multi-GPU overlap)
+    heat::DevBuf<int32_t> slices_all;                         // interior list followed by boundary list
     int64_t n_int_slices = 0, n_bnd_slices = 0;
     heat::DevBuf<double> dinv;           // 1/diag (owned)
     heat::DevBuf<double> diag;
@@ -132,7 +135,8 @@ struct heat_matrix {
     heat::DevBuf<int64_t> d_owned_gids;  // only when !owned_contiguous
     HaloPlan halo;
     // solver workspace (lazily allocated)
-    heat::DevBuf<double> w_r, w_p, w_ap, w_s, w_u, w_t, w_w;
+    heat::DevBuf<double> w_r, w_p, w_p2, w_ap, w_s, w_u, w_t, w_w;
+    PeerMatrixState *peer = nullptr;     // non-null once the peer-memory halo path is set up
     heat::DevBuf<double> partials;       // [2 * kMaxPartials * 4]
     heat::DevBuf<double> scal;           // [S_COUNT]
     heat::DevBuf<int> iscal;             // [I_COUNT]
@@ -162,6 +166,11 @@ struct heat_ctx {
     cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_halo = nullptr, ev_pack = nullptr;
     int rank = 0, nranks = 1;
     void *nccl_comm = nullptr;           // ncclComm_t
+    // peer-memory path (peer.cuh): IPC-mapped arenas of all ranks of the node
+    bool peer_enabled = false;
+    unsigned long long *peer_arena = nullptr;                 // my arena (device)
+    unsigned long long *peer_arena_of[8] = {};                // every rank's arena as mapped here
+    unsigned long long peer_red_seq = 0, peer_halo_epoch = 0; // monotonic, identical on all ranks
     HostMesh mesh;
     ExoFile *read_file = nullptr;        // readFID  (ExodusIO.hpp:2082)
     ExoFile *write_file = nullptr;       // writeFID (ExodusIO.hpp:2083)

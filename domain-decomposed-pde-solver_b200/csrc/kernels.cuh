@@ -1,6 +1,7 @@
 // kernels.cuh — launch interfaces of the sm_100a kernels (definitions in *.cu).
 #pragma once
 #include "common.cuh"
+#include "peer.cuh"
 
 namespace heat {
 
@@ -20,6 +21,15 @@ struct DotOut {               // where a fused dot product is reduced to
     double *partials; int part_offset; int total_blocks; int *counter; double *out;
 };
 
+struct SpmvPeer {             // peer-memory mode of the SpMV (single launch over interior+boundary slices)
+    bool on = false;
+    int64_t n_interior = 0;   // leading entries of the slice list that never touch a ghost column
+    PeerHalo halo;            // flags to wait for before the first boundary slice
+    PeerRed red;              // where the fused dot goes (all ranks' inboxes)
+    unsigned long long seq_out = 0;
+    int *I = nullptr;
+};
+
 // ---- sell.cu ----
 int sell_from_csr(heat_matrix *A, cudaStream_t st);
 // ---- spmv.cu ----
@@ -27,6 +37,9 @@ int sell_from_csr(heat_matrix *A, cudaStream_t st);
 // disables the CG stopping test; dot.out == nullptr disables the fused sum_i y_i * x_i.
 int launch_spmv(const heat_matrix *A, const double *x, double *y, const int32_t *slice_list,
                 int64_t n_list, CgGate gate, DotOut dot, int grid, cudaStream_t st);
+int launch_spmv_peer(const heat_matrix *A, const double *x, double *y, CgGate gate, DotOut dot, SpmvPeer peer,
+                     int grid, cudaStream_t st);
+bool spmv_peer_supported();
 int spmv_grid(int64_t n_list, int sm_count);
 // ---- cg.cu ----
 int launch_cg_init(int64_t n, const double *b, const double *ax, const double *dinv, double *r,
@@ -36,6 +49,13 @@ int launch_cg_update_xr(int64_t n, double *x, double *r, const double *p, const 
                         double *partials, int *counter, int grid, cudaStream_t st);
 int launch_cg_update_p(int64_t n, double *p, const double *r, const double *dinv, CgGate gate,
                        int grid, cudaStream_t st);
+int launch_cg_update_xr_peer(int64_t n, double *x, double *r, const double *p, const double *ap, const double *dinv,
+                             CgGate gate, CgRec *H, double *S, int *I, double *partials, int *counter, PeerRed pr,
+                             unsigned long long seq_in, unsigned long long seq_out, int grid, cudaStream_t st);
+int launch_cg_update_p_peer(int64_t n, double *p_out, const double *p_in, const double *r, const double *dinv,
+                            CgGate gate, CgRec *H, int *I, PeerRed pr, unsigned long long seq_in, PeerPush push,
+                            int grid, cudaStream_t st);
+int launch_halo_push(const double *x, PeerPush push, cudaStream_t st);
 int launch_cg_fused_update(int64_t n, double *x, double *r, double *p, double *s, double *u,
                            const double *w, const double *dinv, CgGate gate, CgRec *H, int *I,
                            double *partials, int *counter, int grid, cudaStream_t st);

@@ -116,6 +116,14 @@ int sell_from_csr(heat_matrix *A, cudaStream_t st) {
             A->n_bnd_slices = (int64_t)lb.size();
             HEAT_TRY(A->slices_interior.alloc(li.size()));
             HEAT_TRY(A->slices_boundary.alloc(lb.size()));
+            {
+                std::vector<int32_t> all(li);
+                all.insert(all.end(), lb.begin(), lb.end());
+                HEAT_TRY(A->slices_all.alloc(all.size()));
+                if (!all.empty())
+                    HEAT_CUDA(cudaMemcpyAsync(A->slices_all.p, all.data(), sizeof(int32_t) * all.size(), cudaMemcpyHostToDevice, st));
+                HEAT_CUDA(cudaStreamSynchronize(st));
+            }
             if (!li.empty())
                 HEAT_CUDA(cudaMemcpyAsync(A->slices_interior.p, li.data(), sizeof(int32_t) * li.size(), cudaMemcpyHostToDevice, st));
             if (!lb.empty())

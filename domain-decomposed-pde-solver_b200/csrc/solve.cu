@@ -127,6 +127,9 @@ int solve_device(heat_ctx *ctx, heat_matrix *A, double *x, const double *b, cons
     if (cheb && single) HEAT_FAIL(2, "heat_solve: Chebyshev is implemented for HEAT_SOLVER_CG only");
     if (o.max_iters < 0 || !(o.tol >= 0.0)) HEAT_FAIL(2, "heat_solve: bad max_iters/tol");
     HEAT_TRY(ensure_workspace(A, single, cheb));
+    // peer-memory path (peer.cuh): classical CG with the fused Jacobi/identity preconditioner
+    if (!single && !cheb && ctx->nranks > 1 && ctx->peer_enabled && !A->peer) HEAT_TRY(peer_matrix_setup(ctx, A));
+    const bool peer = !single && !cheb && ctx->nranks > 1 && A->peer != nullptr;
     const int64_t n = A->n_owned;
     const int sms = sm_count(ctx->device);
     const int vgrid = vec_grid(n, sms);
@@ -171,6 +174,11 @@ int solve_device(heat_ctx *ctx, heat_matrix *A, double *x, const double *b, cons
     } else if (!cheb) {
         HEAT_TRY(launch_cg_init(n, b, ap, dinv, r, p, H, A->partials.p, I + I_COUNTER2, vgrid, st));
         HEAT_TRY(comm_allreduce_sum(ctx, &H[0].rz, 3));
+        if (peer) {                                   // ghosts of p0 go to the neighbours by peer stores
+            PeerPush pp = A->peer->push[0];
+            pp.epoch = ctx->peer_halo_epoch + 1;
+            HEAT_TRY(launch_halo_push(p, pp, st));
+        }
     } else {
         double *z = A->w_u.p;
         HEAT_TRY(launch_cg_init(n, b, ap, A->dinv.p, r, z, H, A->partials.p, I + I_COUNTER2, vgrid, st));   // r (z overwritten below)
@@ -193,6 +201,23 @@ int solve_device(heat_ctx *ctx, heat_matrix *A, double *x, const double *b, cons
                 HEAT_TRY(launch_cg_fused_update(n, x, r, p, s, u, w, dinv, gate, H, I, A->partials.p, I + I_COUNTER2, vgrid, st));
                 HEAT_TRY(spmv_halo(ctx, A, u, w, gate, &H[it + 1].delta));
                 HEAT_TRY(comm_allreduce_sum(ctx, &H[it + 1].rz, 3));
+            } else if (peer) {
+                // 3 launches, no NCCL: halo = peer stores fused into update_p, dots = peer inboxes
+                double *pbuf[2] = {A->w_p.p, A->w_p2.p};
+                double *pin = pbuf[it & 1], *pout = pbuf[(it + 1) & 1];
+                const unsigned long long s1 = ctx->peer_red_seq + 2ull * (unsigned)it + 1, s2 = s1 + 1;
+                const PeerRed pr = peer_red_of(ctx);
+                SpmvPeer sp;
+                sp.on = true; sp.n_interior = A->n_int_slices; sp.halo = A->peer->halo;
+                sp.halo.epoch = ctx->peer_halo_epoch + 1 + (unsigned)it;
+                sp.red = pr; sp.seq_out = s1; sp.I = I;
+                const int g = spmv_grid(A->n_slices, sms);
+                DotOut d{A->partials.p, 0, g, I + I_COUNTER, S + S_TMP2};
+                HEAT_TRY(launch_spmv_peer(A, pin, ap, gate, d, sp, g, st));
+                HEAT_TRY(launch_cg_update_xr_peer(n, x, r, pin, ap, dinv, gate, H, S, I, A->partials.p, I + I_COUNTER2, pr, s1, s2, vgrid, st));
+                PeerPush pp = A->peer->push[(it + 1) & 1];
+                pp.epoch = ctx->peer_halo_epoch + 2 + (unsigned)it;
+                HEAT_TRY(launch_cg_update_p_peer(n, pout, pin, r, dinv, gate, H, I, pr, s2, pp, vgrid, st));
             } else if (!cheb) {
                 HEAT_TRY(spmv_halo(ctx, A, p, ap, gate, S + S_PAP0));
                 HEAT_TRY(comm_allreduce_sum(ctx, S + S_PAP0, 1));
@@ -218,6 +243,10 @@ int solve_device(heat_ctx *ctx, heat_matrix *A, double *x, const double *b, cons
         if (h_iters < launched) break;              // the stopping test fired (or breakdown): frozen
     }
     HEAT_CUDA(cudaEventRecord(ctx->ev_b, st));
+    if (peer) {                                       // identical on every rank: same launches everywhere
+        ctx->peer_red_seq += 2ull * (unsigned)o.max_iters + 4;
+        ctx->peer_halo_epoch += (unsigned)o.max_iters + 4;
+    }
     CgRec h0, hk;
     HEAT_CUDA(cudaMemcpyAsync(&h0, H, sizeof(CgRec), cudaMemcpyDeviceToHost, st));
     HEAT_CUDA(cudaMemcpyAsync(&hk, H + h_iters, sizeof(CgRec), cudaMemcpyDeviceToHost, st));
@@ -231,6 +260,7 @@ int solve_device(heat_ctx *ctx, heat_matrix *A, double *x, const double *b, cons
         info->converged = (hk.rr <= o.tol * o.tol * h0.rr) ? 1 : 0;
         info->solve_ms = ms;
     }
+    if (h_status == 3) HEAT_FAIL(51, "heat_solve: peer-memory communication timed out at iteration %d (a rank left the solve?)", h_iters);
     if (h_status == 2) HEAT_FAIL(50, "heat_solve: CG breakdown (p.Ap <= 0) at iteration %d — matrix not SPD?", h_iters);
     return 0;
 }

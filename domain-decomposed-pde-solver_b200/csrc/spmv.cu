@@ -22,6 +22,7 @@
 
 #include "device_utils.cuh"
 #include "kernels.cuh"
+#include "peer.cuh"
 
 namespace heat {
 
@@ -122,12 +123,12 @@ struct TmaSmem {
     static constexpr size_t total(int nwarps) { return (size_t)nwarps * kWarpBytes + (size_t)nwarps * NSTAGE * 8; }
 };
 
-template <bool DOT, int KC, int NSTAGE, int NWARPS>
+template <bool DOT, int KC, int NSTAGE, int NWARPS, bool PEER = false>
 __global__ void __launch_bounds__(NWARPS * 32, (NWARPS <= 8 && KC <= 8) ? 2 : 1)
 sell_spmv_tma_kernel(const int64_t *__restrict__ slice_ptr, const int32_t *__restrict__ col,
                      const double *__restrict__ val, const double *__restrict__ x, double *__restrict__ y,
                      int64_t n_rows, const int32_t *__restrict__ slice_list, int64_t n_list, CgGate gate,
-                     DotOut dot) {
+                     DotOut dot, SpmvPeer peer) {
     if (gate_done(gate)) return;
     using L = TmaSmem<KC, NSTAGE>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -184,12 +185,28 @@ sell_spmv_tma_kernel(const int64_t *__restrict__ slice_ptr, const int32_t *__res
     int stage = 0;
     uint32_t parity = 0;
     double acc0 = 0.0, acc1 = 0.0, dsum = 0.0;
+    bool halo_ready = !PEER;
     while (tc < n_list) {
         mbar_wait(bars + stage, parity);
         const int kc = (wc - kc0) < KC ? (wc - kc0) : KC;
         const double *vs = reinterpret_cast<const double *>(my + stage * L::kStageBytes) + 2 * lane;
         const int32_t *cs = reinterpret_cast<const int32_t *>(my + stage * L::kStageBytes + L::kValBytes) + 2 * lane;
-        if (kc == KC) {
+        if (PEER && tc >= peer.n_interior) {
+            // boundary slice: its ghost columns are written by the neighbours' GPUs (peer stores).
+            // Wait once per warp for their epoch flags, then gather through L2 (coherent), not L1.
+            if (!halo_ready) {
+                if (lane == 0) peer_halo_wait(peer.halo, peer.I);
+                __syncwarp();
+                halo_ready = true;
+            }
+#pragma unroll 4
+            for (int k = 0; k < kc; ++k) {
+                const double2 v = *reinterpret_cast<const double2 *>(vs + k * kSellChunk);
+                const int2 c = *reinterpret_cast<const int2 *>(cs + k * kSellChunk);
+                acc0 = fma(v.x, __ldcg(x + c.x), acc0);
+                acc1 = fma(v.y, __ldcg(x + c.y), acc1);
+            }
+        } else if (kc == KC) {
 #pragma unroll
             for (int k = 0; k < KC; ++k) {
                 const double2 v = *reinterpret_cast<const double2 *>(vs + k * kSellChunk);
@@ -227,7 +244,8 @@ sell_spmv_tma_kernel(const int64_t *__restrict__ slice_ptr, const int32_t *__res
     if (DOT) {
         double acc[1] = {dsum};
         double *const out[1] = {dot.out};
-        grid_sum<1, NWARPS>(acc, dot.partials, dot.part_offset, dot.total_blocks, dot.counter, out);
+        const bool last = grid_sum<1, NWARPS>(acc, dot.partials, dot.part_offset, dot.total_blocks, dot.counter, out);
+        if (PEER && last) peer_red_push(peer.red, peer.seq_out, *dot.out, 0.0, 0.0);   // p.Ap of this rank -> all ranks
     }
 }
 
@@ -271,7 +289,28 @@ static int launch_tma(const heat_matrix *A, const double *x, double *y, const in
         configured = true;
     }
     kern<<<grid, NWARPS * 32, smem, st>>>(A->slice_ptr.p, A->sell_col.p, A->sell_val.p, x, y, A->n_owned, slice_list,
-                                         n_list, gate, dot);
+                                         n_list, gate, dot, SpmvPeer());
+    HEAT_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// peer-memory mode: ONE launch over [interior slices | boundary slices]; needs the default TMA config
+bool spmv_peer_supported() { return spmv_variant() == 5; }
+
+int launch_spmv_peer(const heat_matrix *A, const double *x, double *y, CgGate gate, DotOut dot, SpmvPeer peer,
+                     int grid, cudaStream_t st) {
+    auto kern = sell_spmv_tma_kernel<true, 8, 2, 8, true>;
+    const size_t smem = TmaSmem<8, 2>::total(8);
+    static bool configured = false;
+    if (!configured) {
+        HEAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    const bool have_list = A->slices_all.p != nullptr && A->n_ghost > 0;
+    const int64_t n_list = have_list ? A->n_int_slices + A->n_bnd_slices : A->n_slices;
+    if (!have_list) peer.n_interior = n_list;
+    kern<<<grid, 8 * 32, smem, st>>>(A->slice_ptr.p, A->sell_col.p, A->sell_val.p, x, y, A->n_owned,
+                                    have_list ? A->slices_all.p : nullptr, n_list, gate, dot, peer);
     HEAT_CUDA(cudaGetLastError());
     return 0;
 }

@@ -47,7 +47,7 @@ class MatrixInfo(C.Structure):
                 ("max_row_len", C.c_int32), ("npe", C.c_int32), ("num_dim", C.c_int32), ("num_node_sets", C.c_int32),
                 ("rank", C.c_int32), ("nranks", C.c_int32), ("n_neighbors", C.c_int32), ("sell_chunk", C.c_int32),
                 ("sell_padded_nnz", C.c_int64), ("n_boundary_slices", C.c_int64), ("n_slices", C.c_int64),
-                ("assemble_ms", C.c_double)]
+                ("assemble_ms", C.c_double), ("peer_path", C.c_int32), ("reserved", C.c_int32)]
 
 
 class PlanSizes(C.Structure):

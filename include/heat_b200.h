@@ -134,6 +134,8 @@ typedef struct {
     int32_t rank, nranks, n_neighbors, sell_chunk;
     int64_t sell_padded_nnz, n_boundary_slices, n_slices;
     double  assemble_ms;      /* device time of pattern+values+SELL (CUDA events)                 */
+    int32_t peer_path;        /* 1 once the NVLink peer-memory halo/all-reduce path is set up      */
+    int32_t reserved;
 } heat_matrix_info;
 int  heat_matrix_get_info(const heat_matrix *A, heat_matrix_info *info);
 /* local CSR: row_ptr[n_owned+1] (int64), col[nnz_local] LOCAL column ids (int32), val.           */

@@ -85,7 +85,9 @@ def check_system(io, A, X, B, ref, part, rank, world, tag, log):
         assert res.converged and abs(res.iters - it_ref) <= 2, (tag, solver, res, it_ref)
         err = np.abs(X.numpy() - x_ref[owned]).max() / np.abs(x_ref).max()
         assert err <= 1e-8, (tag, solver, err)
-        log.append(f"{tag} solver={solver} iters={res.iters} (oracle {it_ref}) err={err:.2e} ghosts={len(ghost)} nbrs={len(nbr)}")
+        log.append(f"{tag} solver={solver} iters={res.iters} (oracle {it_ref}) err={err:.2e} ghosts={len(ghost)} nbrs={len(nbr)} peer={A.info.peer_path}")
+        if solver == hb.SOLVER_CG and os.environ.get("HEAT_COMM", "peer") != "nccl" and os.environ.get("HEAT_REQUIRE_PEER"):
+            assert A.info.peer_path == 1, f"{tag}: peer-memory path was not set up"
     # Chebyshev (extra halo exchanges inside the preconditioner)
     X.fill(0.0)
     res = io.solve(A, X, B, prec=hb.PREC_CHEBYSHEV, cheb_degree=3, cheb_lambda_max=2.5, max_iters=3000, tol=1e-10)
