@@ -163,10 +163,10 @@ __global__ void __launch_bounds__(kBlock) cg_update_xr_peer_kernel(int64_t n, do
                                                                    unsigned long long seq_out) {
     if (cg_done(g)) return;
     __shared__ double sh[2];
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < 32) {
         double o[3];
-        const bool ok = peer_red_wait(pr, seq_in, o, I);
-        sh[0] = o[0]; sh[1] = ok ? 1.0 : 0.0;
+        const bool ok = peer_red_wait_warp(pr, seq_in, o, I);
+        if (threadIdx.x == 0) { sh[0] = o[0]; sh[1] = ok ? 1.0 : 0.0; }
     }
     __syncthreads();
     if (sh[1] == 0.0) return;                              // communication timeout: I_STATUS = 3
@@ -196,9 +196,9 @@ __global__ void __launch_bounds__(kBlock) cg_update_xr_peer_kernel(int64_t n, do
         acc[0] += (dinv[i] * rv) * rv; acc[1] += rv * rv;
     }
     double *const out[2] = {S + S_TMP0, S + S_TMP1};
-    if (grid_sum<2>(acc, partials, 0, gridDim.x, counter, out)) {
-        H[g.it].alpha = alpha;
-        peer_red_push(pr, seq_out, S[S_TMP0], S[S_TMP1], 0.0);
+    if (grid_sum_block<2>(acc, partials, 0, gridDim.x, counter, out)) {
+        if (threadIdx.x == 0) H[g.it].alpha = alpha;
+        if (threadIdx.x < 32) peer_red_push_warp(pr, seq_out, S[S_TMP0], S[S_TMP1], 0.0);
     }
 }
 
@@ -242,10 +242,10 @@ __global__ void __launch_bounds__(kBlock) cg_update_p_peer_kernel(int64_t n, dou
                                                                   unsigned long long seq_in, PeerPush push) {
     if (cg_done(g)) return;
     __shared__ double sh[3];
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < 32) {
         double o[3];
-        const bool ok = peer_red_wait(pr, seq_in, o, I);
-        sh[0] = o[0]; sh[1] = o[1]; sh[2] = ok ? 1.0 : 0.0;
+        const bool ok = peer_red_wait_warp(pr, seq_in, o, I);
+        if (threadIdx.x == 0) { sh[0] = o[0]; sh[1] = o[1]; sh[2] = ok ? 1.0 : 0.0; }
     }
     __syncthreads();
     if (sh[2] == 0.0) return;

@@ -105,6 +105,19 @@ __device__ __forceinline__ bool grid_sum(double (&v)[NV], double *partials, int 
     return false;
 }
 
+// Same reduction, but EVERY thread of the last block gets `true` (after out[] is written and visible
+// to the block), so a whole warp can take part in the epilogue (peer-memory pushes).
+template <int NV, int NW = kWarpsPerBlock>
+__device__ __forceinline__ bool grid_sum_block(double (&v)[NV], double *partials, int part_offset,
+                                               int total_blocks, int *counter, double *const (&out)[NV]) {
+    __shared__ int last_flag;
+    if (threadIdx.x == 0) last_flag = 0;
+    __syncthreads();
+    if (grid_sum<NV, NW>(v, partials, part_offset, total_blocks, counter, out)) last_flag = 1;
+    __syncthreads();
+    return last_flag != 0;
+}
+
 inline int grid_for(int64_t work_items_per_thread_block, int sm_count, int blocks_per_sm) {
     int64_t cap = (int64_t)sm_count * blocks_per_sm;
     int64_t g = work_items_per_thread_block < cap ? work_items_per_thread_block : cap;

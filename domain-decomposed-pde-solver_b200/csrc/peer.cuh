@@ -66,10 +66,12 @@ __device__ __forceinline__ double ld_relaxed_sys_f64(const double *p) {
     return v;
 }
 
-// one thread: publish this rank's partial sums under sequence number `seq` to every rank
-__device__ __forceinline__ void peer_red_push(const PeerRed &pr, unsigned long long seq, double v0, double v1, double v2) {
-    const int slot = (int)(seq % kPeerSlots);
-    for (int q = 0; q < pr.P; ++q) {
+// lanes 0..P-1 of ONE warp: lane q publishes this rank's partial sums under sequence number `seq` to
+// rank q (payload, then a release store of the stamp) -- P NVLink round trips in parallel
+__device__ __forceinline__ void peer_red_push_warp(const PeerRed &pr, unsigned long long seq, double v0, double v1, double v2) {
+    const int q = threadIdx.x & 31;
+    if (q < pr.P) {
+        const int slot = (int)(seq % kPeerSlots);
         unsigned long long *e = pr.inbox[q] + ((size_t)slot * kPeerMaxRanks + pr.rank) * 4;
         double *d = reinterpret_cast<double *>(e);
         d[0] = v0; d[1] = v1; d[2] = v2;
@@ -77,21 +79,30 @@ __device__ __forceinline__ void peer_red_push(const PeerRed &pr, unsigned long l
     }
 }
 
-// one thread: wait for all P contributions of `seq` in MY inbox and add them in rank order
-__device__ __forceinline__ bool peer_red_wait(const PeerRed &pr, unsigned long long seq, double (&out)[3], int *I) {
+// ONE full warp: lane q waits for rank q's contribution of `seq` in MY inbox; the P payloads are then
+// added in rank order by every lane (identical bits on every rank).  Returns false on timeout.
+__device__ __forceinline__ bool peer_red_wait_warp(const PeerRed &pr, unsigned long long seq, double (&out)[3], int *I) {
+    const int q = threadIdx.x & 31;
     const int slot = (int)(seq % kPeerSlots);
-    const unsigned long long *base = pr.inbox[pr.rank] + (size_t)slot * kPeerMaxRanks * 4;
-    out[0] = 0.0; out[1] = 0.0; out[2] = 0.0;
-    const long long t0 = clock64();
-    for (int q = 0; q < pr.P; ++q) {
-        const unsigned long long *e = base + (size_t)q * 4;
+    double v0 = 0.0, v1 = 0.0, v2 = 0.0;
+    int ok = 1;
+    if (q < pr.P) {
+        const unsigned long long *e = pr.inbox[pr.rank] + ((size_t)slot * kPeerMaxRanks + q) * 4;
+        const long long t0 = clock64();
         while (ld_acquire_sys(e + 3) != seq) {
-            if (clock64() - t0 > kPeerSpinBudget || ((volatile int *)I)[I_STATUS] == 3) { I[I_STATUS] = 3; return false; }
+            if (clock64() - t0 > kPeerSpinBudget || ((volatile int *)I)[I_STATUS] == 3) { I[I_STATUS] = 3; ok = 0; break; }
         }
         const double *d = reinterpret_cast<const double *>(e);
-        out[0] += ld_relaxed_sys_f64(d); out[1] += ld_relaxed_sys_f64(d + 1); out[2] += ld_relaxed_sys_f64(d + 2);
+        v0 = ld_relaxed_sys_f64(d); v1 = ld_relaxed_sys_f64(d + 1); v2 = ld_relaxed_sys_f64(d + 2);
     }
-    return true;
+    ok = __all_sync(0xffffffffu, ok);
+    out[0] = 0.0; out[1] = 0.0; out[2] = 0.0;
+    for (int r = 0; r < pr.P; ++r) {
+        out[0] += __shfl_sync(0xffffffffu, v0, r);
+        out[1] += __shfl_sync(0xffffffffu, v1, r);
+        out[2] += __shfl_sync(0xffffffffu, v2, r);
+    }
+    return ok != 0;
 }
 
 // one thread: wait until every neighbour has delivered halo epoch >= h.epoch

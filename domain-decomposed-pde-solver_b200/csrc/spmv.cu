@@ -146,31 +146,41 @@ sell_spmv_tma_kernel(const int64_t *__restrict__ slice_ptr, const int32_t *__res
     const uint64_t policy = l2_evict_first_policy();
     const int64_t W = (int64_t)gridDim.x * NWARPS;
     const int64_t first = (int64_t)blockIdx.x * NWARPS + warp;
-    auto slice_of = [&](int64_t t) -> int64_t { return slice_list ? (int64_t)slice_list[t] : t; };
-    auto width_of = [&](int64_t s) -> int { return (int)((slice_ptr[s + 1] - slice_ptr[s]) >> 6); };
+    // slice metadata is loaded ONE SLICE AHEAD of its use (slice_list -> slice_ptr is a chain of two
+    // dependent global loads; it must never sit on the path that issues the next TMA copy)
+    struct Meta { int64_t s, base; int w; };
+    auto load_meta = [&](int64_t t) -> Meta {
+        Meta m{0, 0, 0};
+        if (t < n_list) {
+            m.s = slice_list ? (int64_t)slice_list[t] : t;
+            m.base = slice_ptr[m.s];
+            m.w = (int)((slice_ptr[m.s + 1] - m.base) >> 6);
+        }
+        return m;
+    };
 
     // issue cursor (runs NSTAGE chunks ahead of the consume cursor)
     int64_t ti = first;
-    int ki = 0, wi = 0;
-    int64_t si = 0, basei = 0;
-    if (ti < n_list) { si = slice_of(ti); basei = slice_ptr[si]; wi = width_of(si); }
+    int ki = 0;
+    Meta mi = load_meta(ti), mi_next = load_meta(ti + W);
     auto issue = [&](int stage) {
-        const int kc = (wi - ki) < KC ? (wi - ki) : KC;
+        const int kc = (mi.w - ki) < KC ? (mi.w - ki) : KC;
         if (lane == 0) {
             if (kc > 0) {
                 unsigned char *dst = my + stage * L::kStageBytes;
                 const uint32_t vb = (uint32_t)kc * kSellChunk * 8, cb = (uint32_t)kc * kSellChunk * 4;
                 mbar_arrive_expect_tx(bars + stage, vb + cb);
-                tma_load_1d(dst, val + basei + (int64_t)ki * kSellChunk, vb, bars + stage, policy);
-                tma_load_1d(dst + L::kValBytes, col + basei + (int64_t)ki * kSellChunk, cb, bars + stage, policy);
+                tma_load_1d(dst, val + mi.base + (int64_t)ki * kSellChunk, vb, bars + stage, policy);
+                tma_load_1d(dst + L::kValBytes, col + mi.base + (int64_t)ki * kSellChunk, cb, bars + stage, policy);
             } else {
                 mbar_arrive(bars + stage);                              // empty slice: complete the phase
             }
         }
         ki += KC;
-        if (ki >= wi) {
-            ti += W; ki = 0; wi = 0;
-            if (ti < n_list) { si = slice_of(ti); basei = slice_ptr[si]; wi = width_of(si); }
+        if (ki >= mi.w) {
+            ti += W; ki = 0;
+            mi = mi_next;
+            mi_next = load_meta(ti + W);
         }
     };
 #pragma unroll
@@ -179,16 +189,15 @@ sell_spmv_tma_kernel(const int64_t *__restrict__ slice_ptr, const int32_t *__res
 
     // consume cursor
     int64_t tc = first;
-    int kc0 = 0, wc = 0;
-    int64_t sc = 0;
-    if (tc < n_list) { sc = slice_of(tc); wc = width_of(sc); }
+    int kc0 = 0;
+    Meta mc = load_meta(tc), mc_next = load_meta(tc + W);
     int stage = 0;
     uint32_t parity = 0;
     double acc0 = 0.0, acc1 = 0.0, dsum = 0.0;
     bool halo_ready = !PEER;
     while (tc < n_list) {
         mbar_wait(bars + stage, parity);
-        const int kc = (wc - kc0) < KC ? (wc - kc0) : KC;
+        const int kc = (mc.w - kc0) < KC ? (mc.w - kc0) : KC;
         const double *vs = reinterpret_cast<const double *>(my + stage * L::kStageBytes) + 2 * lane;
         const int32_t *cs = reinterpret_cast<const int32_t *>(my + stage * L::kStageBytes + L::kValBytes) + 2 * lane;
         if (PEER && tc >= peer.n_interior) {
@@ -226,8 +235,8 @@ sell_spmv_tma_kernel(const int64_t *__restrict__ slice_ptr, const int32_t *__res
         __syncwarp();                                    // every lane is done with this stage
         if (ti < n_list) issue(stage);                   // refill it NSTAGE chunks ahead
         kc0 += KC;
-        if (kc0 >= wc) {                                 // slice finished: write its 64 rows
-            const int64_t row = sc * kSellChunk + 2 * lane;
+        if (kc0 >= mc.w) {                               // slice finished: write its 64 rows
+            const int64_t row = mc.s * kSellChunk + 2 * lane;
             if (row + 1 < n_rows) {
                 *reinterpret_cast<double2 *>(y + row) = make_double2(acc0, acc1);
                 if (DOT) dsum += acc0 * __ldg(x + row) + acc1 * __ldg(x + row + 1);
@@ -236,16 +245,21 @@ sell_spmv_tma_kernel(const int64_t *__restrict__ slice_ptr, const int32_t *__res
                 if (DOT) dsum += acc0 * __ldg(x + row);
             }
             acc0 = 0.0; acc1 = 0.0;
-            tc += W; kc0 = 0; wc = 0;
-            if (tc < n_list) { sc = slice_of(tc); wc = width_of(sc); }
+            tc += W; kc0 = 0;
+            mc = mc_next;
+            mc_next = load_meta(tc + W);
         }
         if (++stage == NSTAGE) { stage = 0; parity ^= 1u; }
     }
     if (DOT) {
         double acc[1] = {dsum};
         double *const out[1] = {dot.out};
-        const bool last = grid_sum<1, NWARPS>(acc, dot.partials, dot.part_offset, dot.total_blocks, dot.counter, out);
-        if (PEER && last) peer_red_push(peer.red, peer.seq_out, *dot.out, 0.0, 0.0);   // p.Ap of this rank -> all ranks
+        if (PEER) {        // p.Ap of this rank -> all ranks' inboxes, one lane per destination
+            if (grid_sum_block<1, NWARPS>(acc, dot.partials, dot.part_offset, dot.total_blocks, dot.counter, out) && threadIdx.x < 32)
+                peer_red_push_warp(peer.red, peer.seq_out, *dot.out, 0.0, 0.0);
+        } else {
+            grid_sum<1, NWARPS>(acc, dot.partials, dot.part_offset, dot.total_blocks, dot.counter, out);
+        }
     }
 }
 

@@ -6,7 +6,9 @@ import argparse, hashlib, json, os, sys
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--nx", type=int, default=512)
-ap.add_argument("--variant", type=int, default=1)
+ap.add_argument("--ny", type=int, default=0)
+ap.add_argument("--nz", type=int, default=0)
+ap.add_argument("--variant", type=int, default=5)
 ap.add_argument("--reps", type=int, default=30)
 ap.add_argument("--solver", default="cg")
 ap.add_argument("--operator", default="p1")
@@ -19,7 +21,7 @@ import heat_b200 as hb
 
 stream = torch.cuda.current_stream()
 io = hb.IO(0, stream)
-io.mesh_cube(args.nx, args.nx, args.nx)
+io.mesh_cube(args.nx, args.ny or args.nx, args.nz or args.nx)
 A, X, B = io.assemble(hb.OP_P1_FEM if args.operator == "p1" else hb.OP_GRAPH_LAPLACIAN)
 mi = A.info
 x, y = A.hash_vector(12345), A.new_vector()
@@ -51,7 +53,7 @@ def step():
 
 
 ms_it = timed(step, 3, 1) / ips
-print(json.dumps({"variant": args.variant, "nx": args.nx, "spmv_ms": ms, "spmv_GBs": bytes_spmv / ms / 1e6,
+print(json.dumps({"variant": args.variant, "nx": args.nx, "ny": args.ny or args.nx, "nz": args.nz or args.nx, "spmv_ms": ms, "spmv_GBs": bytes_spmv / ms / 1e6,
                   "frac_of_6546.9": bytes_spmv / ms / 1e6 / 6546.9, "cg_ms_per_iter": ms_it, "cg_it_per_s": 1e3 / ms_it,
                   "cg_GBs": (bytes_spmv + 88 * mi.n_global) / ms_it / 1e6, "solver": args.solver,
                   "y_sha1": hashlib.sha1(yh.tobytes()).hexdigest()[:16]}))
