@@ -173,15 +173,19 @@ def run_ours(args):
         io.comm_init(rank, world, bytes(idt.cpu().numpy().tobytes()))
 
     nx = args.nx
-    n_full, nnz_full = cube_counts(nx, nx, nx)
+    ny, nz = nx, nx
+    if args.workload == "weak":          # BASELINE.json configs[4]: 64 Mi nodes per GPU (512 x 512 x 256 slab each)
+        nz = (nx // 2) * world
+    n_full, nnz_full = cube_counts(nx, ny, nz)
     op = hb.OP_P1_FEM if args.operator == "p1" else hb.OP_GRAPH_LAPLACIAN
-    io.mesh_cube(nx, nx, nx, False)
+    io.mesh_cube(nx, ny, nz, False)
     A, X, B = io.assemble(op, hb.PART_SLAB)
     mi = A.info
     assert (mi.n_global, mi.nnz_global) == (n_full, nnz_full), (mi.n_global, mi.nnz_global)
     solver = hb.SOLVER_CG_SINGLE_REDUCE if args.solver == "cg1" else hb.SOLVER_CG
     ips = args.iters_per_step
-    kw = dict(solver=solver, prec=hb.PREC_JACOBI, check_every=ips)
+    prec = {"jacobi": hb.PREC_JACOBI, "chebyshev": hb.PREC_CHEBYSHEV, "none": hb.PREC_NONE}[args.prec]
+    kw = dict(solver=solver, prec=prec, check_every=ips, cheb_degree=args.cheb_degree, cheb_lambda_max=args.cheb_lambda_max)
 
     def barrier():
         if dist is not None:
@@ -214,7 +218,17 @@ def run_ours(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ms_total = timed(step, args.steps, args.warmup)
+    launch_mark = {}
+
+    def timed_counted(fn, steps, warmup):        # `timed`, also counting this library's launches inside the timed steps
+        for _ in range(warmup):
+            fn()
+        launch_mark["l0"] = hb.kernel_launches()
+        ms = timed(fn, steps, 0)
+        launch_mark["l1"] = hb.kernel_launches()
+        return ms
+
+    ms_total = timed_counted(step, args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
     ms_per_step = ms_total / args.steps
     value = ips * args.steps / (ms_total * 1e-3)
@@ -244,7 +258,7 @@ def run_ours(args):
 
     def step_e2e():
         x_host.zero_()
-        r = io.solve_host(A, b_host, x_host, solver=solver, prec=hb.PREC_JACOBI, check_every=ips, max_iters=ips, tol=0.0)
+        r = io.solve_host(A, b_host, x_host, max_iters=ips, tol=0.0, **kw)
         assert r.iters == ips
 
     e2e_steps = max(1, min(args.steps, 3))
@@ -262,28 +276,28 @@ def run_ours(args):
                           f"CPU assembly {t_asm:.1f} s")}
 
     if rank == 0:
-        kernels_per_iter = 2 if solver == hb.SOLVER_CG_SINGLE_REDUCE else 3
-        split = 2 if world > 1 else 1            # interior + boundary SpMV launches, + 1 pack kernel
-        per_iter = kernels_per_iter - 1 + split + (1 if world > 1 else 0)
-        per_step_setup = 1 + split + (1 if world > 1 else 0) + 1 + (3 if solver == hb.SOLVER_CG_SINGLE_REDUCE else 0)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak" if args.workload == "weak" else "strong",
+            "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"synthetic {nx}^3-node Kuhn tet cube ({'P1 FEM' if op else 'graph Laplacian'}), "
-                                   f"slab-partitioned over {world} GPU(s), Jacobi-PCG ({args.solver})",
+            "config": {"workload": f"synthetic {nx}x{ny}x{nz}-node Kuhn tet cube ({'P1 FEM' if op else 'graph Laplacian'}), "
+                                   f"slab-partitioned over {world} GPU(s), {args.prec}-PCG ({args.solver})",
+                       "comm": "peer-memory" if mi.nranks > 1 and A.info.peer_path else ("nccl" if mi.nranks > 1 else "none"),
                        "n_dof": n_full, "nnz": nnz_full, "iters_per_step": ips, "solver": args.solver,
                        "l2_policy": "inputs (>=38 GB per iteration sweep) far exceed the 126 MB L2; no flush",
                        "assemble_ms": mi.assemble_ms, "sell_padding": mi.sell_padded_nnz / max(mi.nnz_local, 1) - 1.0},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 16 * n_own * world, "d2h_bytes_per_step": 8 * n_own * world,
                     "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps, "check_max_abs_x": res_check},
-            "gpu_launches": args.steps * (ips * per_iter + per_step_setup + 1),
+            "gpu_launches": launch_mark["l1"] - launch_mark["l0"],     # counted by the library (heat_kernel_launches), rank 0
             "roofline": {"bound": "hbm", "kernel": "sell_spmv_tma_kernel (fp64 SELL-64 SpMV, TMA-staged)", "achieved": per_gpu_gbs, "peak": peak,
                          "unit": "GB/s", "frac": per_gpu_gbs / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": spmv_bytes(n_full, nnz_full) / world, "ms_per_launch": ms_spmv,
                          "launches_timed": n_spmv},
-            "roofline_cg_iteration": {"bound": "hbm", "achieved": cg_gbs_per_gpu, "peak": peak, "unit": "GB/s",
-                                      "frac": cg_gbs_per_gpu / peak, "algorithmic_bytes_per_iteration": cg_iter_bytes(n_full, nnz_full) / world},
+            "roofline_cg_iteration": ({"bound": "hbm", "achieved": cg_gbs_per_gpu, "peak": peak, "unit": "GB/s",
+                                       "frac": cg_gbs_per_gpu / peak,
+                                       "algorithmic_bytes_per_iteration": cg_iter_bytes(n_full, nnz_full) / world}
+                                      if args.prec == "jacobi" else None),
             "clocks": clocks,
         }
         if cpu:
@@ -309,6 +323,11 @@ def main():
     ap.add_argument("--iters-per-step", type=int, default=50)
     ap.add_argument("--solver", default="cg", choices=["cg", "cg1"])
     ap.add_argument("--operator", default="p1", choices=["p1", "graph"])
+    ap.add_argument("--workload", default="strong", choices=["strong", "weak"],
+                    help="strong: nx^3 cube over N GPUs (configs[3]); weak: nx*nx*(nx/2) nodes PER GPU (configs[4])")
+    ap.add_argument("--prec", default="jacobi", choices=["jacobi", "chebyshev", "none"])
+    ap.add_argument("--cheb-degree", type=int, default=3)
+    ap.add_argument("--cheb-lambda-max", type=float, default=0.0)
     ap.add_argument("--cpu-sample", type=int, default=160, help="cube edge of the bounded CPU sample")
     ap.add_argument("--cpu-iters", type=int, default=40)
     ap.add_argument("--no-cpu-baseline", action="store_true")

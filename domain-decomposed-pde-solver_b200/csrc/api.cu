@@ -20,6 +20,9 @@ void set_error(const char *fmt, ...) {
     va_end(ap);
 }
 
+static unsigned long long g_launches = 0;
+void count_launch() { ++g_launches; }
+
 void contiguous_partition(int64_t n, int nranks, int32_t *part);
 int metis_kway_partition(int64_t n, const int64_t *row_ptr, const int32_t *col, int nranks, int32_t *part);
 
@@ -216,6 +219,7 @@ using namespace heat;
 
 extern "C" const char *heat_last_error(void) { return heat::g_err; }
 extern "C" int heat_version(void) { return HEAT_B200_VERSION; }
+extern "C" unsigned long long heat_kernel_launches(void) { return heat::g_launches; }
 extern "C" int heat_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }

@@ -253,9 +253,9 @@ int GeneralAssembler::make_cube(int nx, int ny, int nz, cudaStream_t st) {
     HEAT_TRY(x.alloc((size_t)N)); HEAT_TRY(y.alloc((size_t)N)); HEAT_TRY(z.alloc((size_t)N));
     HEAT_TRY(conn.alloc((size_t)(ne * 4))); HEAT_TRY(bc.alloc((size_t)N));
     cube_nodes_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(nx, ny, nz, x.p, y.p, z.p, bc.p);
-    HEAT_CUDA(cudaGetLastError());
+    HEAT_LAUNCHED();
     cube_conn_kernel<<<(unsigned)((ne + 255) / 256), 256, 0, st>>>(nx, ny, nz, conn.p);
-    HEAT_CUDA(cudaGetLastError());
+    HEAT_LAUNCHED();
     return 0;
 }
 
@@ -264,7 +264,7 @@ int GeneralAssembler::build_pattern(cudaStream_t st) {
     DevBuf<int32_t> flag;
     HEAT_TRY(flag.alloc((size_t)N)); HEAT_TRY(red.alloc((size_t)N));
     dof_flag_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(N, bc.p, flag.p);
-    HEAT_CUDA(cudaGetLastError());
+    HEAT_LAUNCHED();
     {
         size_t tb = 0;
         HEAT_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, flag.p, red.p, N, st));
@@ -278,7 +278,7 @@ int GeneralAssembler::build_pattern(cudaStream_t st) {
     }
     HEAT_TRY(red2orig.alloc((size_t)n));
     red_finish_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(N, flag.p, red.p, red2orig.p);
-    HEAT_CUDA(cudaGetLastError());
+    HEAT_LAUNCHED();
     flag.release();
 
     // ---- node -> incident elements, ascending element id: stable radix sort of (node, elem) ----
@@ -290,7 +290,7 @@ int GeneralAssembler::build_pattern(cudaStream_t st) {
         HEAT_TRY(n2e_ptr.alloc((size_t)N + 1));
         if (total > 0) {
             n2e_keys_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(total, npe, conn.p, keys_in.p, elems_in.p);
-            HEAT_CUDA(cudaGetLastError());
+            HEAT_LAUNCHED();
             int end_bit = 1;
             while (end_bit < 31 && (1ll << end_bit) < N) ++end_bit;
             size_t tb = 0;
@@ -299,7 +299,7 @@ int GeneralAssembler::build_pattern(cudaStream_t st) {
             HEAT_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, keys_in.p, keys_out.p, elems_in.p, n2e.p, total, 0, end_bit, st));
         }
         n2e_ptr_kernel<<<(unsigned)((N + 1 + 255) / 256), 256, 0, st>>>(N, total, keys_out.p, n2e_ptr.p);
-        HEAT_CUDA(cudaGetLastError());
+        HEAT_LAUNCHED();
         HEAT_CUDA(cudaStreamSynchronize(st));
     }
 
@@ -312,7 +312,7 @@ int GeneralAssembler::build_pattern(cudaStream_t st) {
     if (n > 0) {
         pattern_count_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(n, red2orig.p, red.p, n2e_ptr.p, n2e.p, npe,
                                                                        conn.p, row_len.p, ovf.p);
-        HEAT_CUDA(cudaGetLastError());
+        HEAT_LAUNCHED();
     }
     {
         size_t tb = 0;
@@ -336,7 +336,7 @@ int GeneralAssembler::build_pattern(cudaStream_t st) {
     if (n > 0) {
         pattern_fill_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(n, red2orig.p, red.p, n2e_ptr.p, n2e.p, npe,
                                                                       conn.p, grow_ptr.p, gcol.p, ovf.p);
-        HEAT_CUDA(cudaGetLastError());
+        HEAT_LAUNCHED();
     }
     return 0;
 }
@@ -352,7 +352,7 @@ int GeneralAssembler::fill_values(int mode, int64_t n_owned, const int32_t *d_ow
     values_kernel<<<(unsigned)((n_owned + 127) / 128), 128, 0, st>>>(
         n_owned, d_owned, d_g2l, red2orig.p, red.p, n2e_ptr.p, n2e.p, npe, conn.p, x.p, y.p, has_z ? z.p : nullptr,
         bc.p, grow_ptr.p, gcol.p, d_lrow_ptr, d_lcol, d_lval, d_b, mode, ovf.p);
-    HEAT_CUDA(cudaGetLastError());
+    HEAT_LAUNCHED();
     return 0;
 }
 
@@ -484,7 +484,7 @@ int cube_assemble(const CubeGeom &c, int mode, heat_matrix *A, double *d_b, cuda
     HEAT_CUDA(cudaMemsetAsync(row_len.p, 0, sizeof(int64_t) * (size_t)(n + 1), st));
     if (n > 0) {
         cube_count_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c, row_len.p);
-        HEAT_CUDA(cudaGetLastError());
+        HEAT_LAUNCHED();
     }
     size_t tb = 0;
     HEAT_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, row_len.p, A->row_ptr.p, n + 1, st));
@@ -498,7 +498,7 @@ int cube_assemble(const CubeGeom &c, int mode, heat_matrix *A, double *d_b, cuda
     HEAT_TRY(A->val.alloc((size_t)A->nnz));
     if (n > 0) {
         cube_fill_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(c, mode, A->row_ptr.p, A->col.p, A->val.p, d_b);
-        HEAT_CUDA(cudaGetLastError());
+        HEAT_LAUNCHED();
     }
     return 0;
 }

@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(kBlock) cg_init_kernel(int64_t n, const double
 int launch_cg_init(int64_t n, const double *b, const double *ax, const double *dinv, double *r,
                    double *q, CgRec *H, double *partials, int *counter, int grid, cudaStream_t st) {
     cg_init_kernel<<<grid, kBlock, 0, st>>>(n, b, ax, dinv, r, q, H, partials, counter);
-    HEAT_CUDA(cudaGetLastError());
+    HEAT_LAUNCHED();
     return 0;
 }
 
@@ -115,7 +115,7 @@ int launch_cg_update_xr(int64_t n, double *x, double *r, const double *p, const 
                         const double *dinv, CgGate gate, CgRec *H, double *S, int *I,
                         double *partials, int *counter, int grid, cudaStream_t st) {
     cg_update_xr_kernel<<<grid, kBlock, 0, st>>>(n, x, r, p, ap, dinv, gate, H, S, I, partials, counter);
-    HEAT_CUDA(cudaGetLastError());
+    HEAT_LAUNCHED();
     return 0;
 }
 
@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(kBlock) cg_update_p_kernel(int64_t n, double *
 int launch_cg_update_p(int64_t n, double *p, const double *r, const double *dinv, CgGate gate,
                        int grid, cudaStream_t st) {
     cg_update_p_kernel<<<grid, kBlock, 0, st>>>(n, p, r, dinv, gate);
-    HEAT_CUDA(cudaGetLastError());
+    HEAT_LAUNCHED();
     return 0;
 }
 
@@ -206,7 +206,7 @@ int launch_cg_update_xr_peer(int64_t n, double *x, double *r, const double *p, c
                              CgGate gate, CgRec *H, double *S, int *I, double *partials, int *counter, PeerRed pr,
                              unsigned long long seq_in, unsigned long long seq_out, int grid, cudaStream_t st) {
     cg_update_xr_peer_kernel<<<grid, kBlock, 0, st>>>(n, x, r, p, ap, dinv, gate, H, S, I, partials, counter, pr, seq_in, seq_out);
-    HEAT_CUDA(cudaGetLastError());
+    HEAT_LAUNCHED();
     return 0;
 }
 
@@ -275,7 +275,7 @@ int launch_cg_update_p_peer(int64_t n, double *p_out, const double *p_in, const 
                             int grid, cudaStream_t st) {
     if (push.n_blocks > grid) push.n_blocks = grid;
     cg_update_p_peer_kernel<<<grid, kBlock, 0, st>>>(n, p_out, p_in, r, dinv, gate, H, I, pr, seq_in, push);
-    HEAT_CUDA(cudaGetLastError());
+    HEAT_LAUNCHED();
     return 0;
 }
 
@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(kBlock) halo_push_kernel(const double *__restr
 int launch_halo_push(const double *x, PeerPush push, cudaStream_t st) {
     if (push.n_blocks < 1) push.n_blocks = 1;
     halo_push_kernel<<<push.n_blocks, kBlock, 0, st>>>(x, push);
-    HEAT_CUDA(cudaGetLastError());
+    HEAT_LAUNCHED();
     return 0;
 }
 
@@ -354,7 +354,7 @@ int launch_cg_fused_update(int64_t n, double *x, double *r, double *p, double *s
                            const double *w, const double *dinv, CgGate gate, CgRec *H, int *I,
                            double *partials, int *counter, int grid, cudaStream_t st) {
     cg_fused_update_kernel<<<grid, kBlock, 0, st>>>(n, x, r, p, s, u, w, dinv, gate, H, I, partials, counter);
-    HEAT_CUDA(cudaGetLastError());
+    HEAT_LAUNCHED();
     return 0;
 }
 
@@ -369,7 +369,7 @@ __global__ void __launch_bounds__(kBlock) axpby_kernel(int64_t n, double a, cons
 }
 int launch_axpby(int64_t n, double a, const double *x, double b, double *y, int grid, cudaStream_t st) {
     axpby_kernel<<<grid, kBlock, 0, st>>>(n, a, x, b, y);
-    HEAT_CUDA(cudaGetLastError());
+    HEAT_LAUNCHED();
     return 0;
 }
 
@@ -390,7 +390,7 @@ __global__ void __launch_bounds__(kBlock) dot2_kernel(int64_t n, const double *_
 int launch_dot2(int64_t n, const double *a, const double *b, const double *c, const double *d,
                 double *out_ab, double *out_cd, double *partials, int *counter, int grid, cudaStream_t st) {
     dot2_kernel<<<grid, kBlock, 0, st>>>(n, a, b, c, d, out_ab, out_cd, partials, counter);
-    HEAT_CUDA(cudaGetLastError());
+    HEAT_LAUNCHED();
     return 0;
 }
 
@@ -409,7 +409,7 @@ __global__ void __launch_bounds__(kBlock) cheb_first_kernel(int64_t n, const dou
 int launch_cheb_first(int64_t n, const double *dinv, const double *r, double inv_theta, double *w,
                       double *z, CgGate gate, int grid, cudaStream_t st) {
     cheb_first_kernel<<<grid, kBlock, 0, st>>>(n, dinv, r, inv_theta, w, z, gate);
-    HEAT_CUDA(cudaGetLastError());
+    HEAT_LAUNCHED();
     return 0;
 }
 // W = c1 W + c2 D^-1 (r - A Z) ; Z += W
@@ -428,7 +428,7 @@ __global__ void __launch_bounds__(kBlock) cheb_step_kernel(int64_t n, const doub
 int launch_cheb_step(int64_t n, const double *dinv, const double *r, const double *az, double c1,
                      double c2, double *w, double *z, CgGate gate, int grid, cudaStream_t st) {
     cheb_step_kernel<<<grid, kBlock, 0, st>>>(n, dinv, r, az, c1, c2, w, z, gate);
-    HEAT_CUDA(cudaGetLastError());
+    HEAT_LAUNCHED();
     return 0;
 }
 
@@ -454,7 +454,7 @@ __global__ void __launch_bounds__(kBlock) cg_xr_plain_kernel(int64_t n, double *
 int launch_cg_xr_plain(int64_t n, double *x, double *r, const double *p, const double *ap,
                        CgGate gate, double *S, int *I, int grid, cudaStream_t st) {
     cg_xr_plain_kernel<<<grid, kBlock, 0, st>>>(n, x, r, p, ap, gate, S, I);
-    HEAT_CUDA(cudaGetLastError());
+    HEAT_LAUNCHED();
     return 0;
 }
 
@@ -476,7 +476,7 @@ __global__ void __launch_bounds__(kBlock) cg_dots_kernel(int64_t n, const double
 int launch_cg_dots(int64_t n, const double *r, const double *z, CgGate gate, CgRec *H, int *I,
                    double *partials, int *counter, int grid, cudaStream_t st) {
     cg_dots_kernel<<<grid, kBlock, 0, st>>>(n, r, z, gate, H, I, partials, counter);
-    HEAT_CUDA(cudaGetLastError());
+    HEAT_LAUNCHED();
     return 0;
 }
 
@@ -492,7 +492,7 @@ __global__ void __launch_bounds__(kBlock) cg_p_plain_kernel(int64_t n, double *_
 }
 int launch_cg_p_plain(int64_t n, double *p, const double *z, CgGate gate, int grid, cudaStream_t st) {
     cg_p_plain_kernel<<<grid, kBlock, 0, st>>>(n, p, z, gate);
-    HEAT_CUDA(cudaGetLastError());
+    HEAT_LAUNCHED();
     return 0;
 }
 
@@ -505,7 +505,7 @@ int launch_fill(int64_t n, double *x, double v, cudaStream_t st) {
     if (n <= 0) return 0;
     int grid = (int)((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096);
     fill_kernel<<<grid, 256, 0, st>>>(n, x, v);
-    HEAT_CUDA(cudaGetLastError());
+    HEAT_LAUNCHED();
     return 0;
 }
 
@@ -528,7 +528,7 @@ int launch_fill_hash(int64_t n, double *x, const int64_t *gids, int64_t gid0, ui
     if (n <= 0) return 0;
     int grid = (int)((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096);
     fill_hash_kernel<<<grid, 256, 0, st>>>(n, x, gids, gid0, seed);
-    HEAT_CUDA(cudaGetLastError());
+    HEAT_LAUNCHED();
     return 0;
 }
 
@@ -542,7 +542,7 @@ int launch_gather(int64_t n, const double *x, const int32_t *idx, double *out, c
     if (n <= 0) return 0;
     int grid = (int)((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184);
     gather_kernel<<<grid, 256, 0, st>>>(n, x, idx, out);
-    HEAT_CUDA(cudaGetLastError());
+    HEAT_LAUNCHED();
     return 0;
 }
 

@@ -14,6 +14,7 @@
 namespace heat {
 
 void set_error(const char *fmt, ...);
+void count_launch();
 
 #define HEAT_CUDA(call)                                                                          \
     do {                                                                                         \
@@ -22,6 +23,13 @@ void set_error(const char *fmt, ...);
             heat::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
             return 100;                                                                          \
         }                                                                                        \
+    } while (0)
+
+// placed right after every <<<>>> launch: counts it (heat_kernel_launches) and checks for launch errors
+#define HEAT_LAUNCHED()                                                                          \
+    do {                                                                                         \
+        heat::count_launch();                                                                    \
+        HEAT_CUDA(cudaGetLastError());                                                           \
     } while (0)
 
 #define HEAT_TRY(call)                                                                           \

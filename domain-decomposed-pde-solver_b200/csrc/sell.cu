@@ -71,7 +71,7 @@ int launch_extract_diag(const heat_matrix *A, cudaStream_t st) {
     const int64_t n = A->n_owned;
     extract_diag_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(A->row_ptr.p, A->col.p, A->val.p, n,
                                                                     A->diag.p, A->dinv.p);
-    HEAT_CUDA(cudaGetLastError());
+    HEAT_LAUNCHED();
     return 0;
 }
 
@@ -87,7 +87,7 @@ int sell_from_csr(heat_matrix *A, cudaStream_t st) {
         DevBuf<int64_t> entries;
         HEAT_TRY(entries.alloc((size_t)ns));
         sell_width_kernel<<<(unsigned)((ns + 255) / 256), 256, 0, st>>>(A->row_ptr.p, n, ns, entries.p);
-        HEAT_CUDA(cudaGetLastError());
+        HEAT_LAUNCHED();
         size_t tmp_bytes = 0;
         HEAT_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, entries.p, A->slice_ptr.p + 1, ns, st));
         DevBuf<char> tmp;
@@ -103,7 +103,7 @@ int sell_from_csr(heat_matrix *A, cudaStream_t st) {
         sell_fill_kernel<<<(unsigned)((ns + kWarpsPerBlock - 1) / kWarpsPerBlock), kBlock, 0, st>>>(
             A->row_ptr.p, A->col.p, A->val.p, n, A->n_owned, ns, A->slice_ptr.p, A->sell_col.p, A->sell_val.p,
             need_split ? flags.p : nullptr);
-        HEAT_CUDA(cudaGetLastError());
+        HEAT_LAUNCHED();
         A->n_int_slices = ns;
         A->n_bnd_slices = 0;
         if (need_split) {

@@ -304,7 +304,7 @@ static int launch_tma(const heat_matrix *A, const double *x, double *y, const in
     }
     kern<<<grid, NWARPS * 32, smem, st>>>(A->slice_ptr.p, A->sell_col.p, A->sell_val.p, x, y, A->n_owned, slice_list,
                                          n_list, gate, dot, SpmvPeer());
-    HEAT_CUDA(cudaGetLastError());
+    HEAT_LAUNCHED();
     return 0;
 }
 
@@ -325,7 +325,7 @@ int launch_spmv_peer(const heat_matrix *A, const double *x, double *y, CgGate ga
     if (!have_list) peer.n_interior = n_list;
     kern<<<grid, 8 * 32, smem, st>>>(A->slice_ptr.p, A->sell_col.p, A->sell_val.p, x, y, A->n_owned,
                                     have_list ? A->slices_all.p : nullptr, n_list, gate, dot, peer);
-    HEAT_CUDA(cudaGetLastError());
+    HEAT_LAUNCHED();
     return 0;
 }
 
@@ -353,7 +353,7 @@ int launch_spmv(const heat_matrix *A, const double *x, double *y, const int32_t 
     else
         sell_spmv_kernel<false><<<grid, kBlock, 0, st>>>(A->slice_ptr.p, A->sell_col.p, A->sell_val.p, x, y,
                                                         A->n_owned, slice_list, n_list, gate, dot);
-    HEAT_CUDA(cudaGetLastError());
+    HEAT_LAUNCHED();
     return 0;
 }
 

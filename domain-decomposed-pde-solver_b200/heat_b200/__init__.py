@@ -56,7 +56,7 @@ class PlanSizes(C.Structure):
 
 # every symbol include/heat_b200.h declares (tests check the .so exports all of them)
 ABI_SYMBOLS = [
-    "heat_last_error", "heat_version", "heat_device_count", "heat_ctx_create", "heat_ctx_set_stream", "heat_open",
+    "heat_last_error", "heat_version", "heat_device_count", "heat_kernel_launches", "heat_ctx_create", "heat_ctx_set_stream", "heat_open",
     "heat_create", "heat_close", "heat_mesh_set", "heat_mesh_cube", "heat_comm_unique_id", "heat_comm_init",
     "heat_comm_rank", "heat_assemble", "heat_solve_opts_default", "heat_solve", "heat_solve_host", "heat_spmv",
     "heat_cg_iterations", "heat_decompose", "heat_write_solution", "heat_nodal_field", "heat_decompose_partition",
@@ -80,6 +80,7 @@ def lib():
     L = C.CDLL(LIB_PATH)
     vp, i64p, i32p, dp = C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_double)
     L.heat_last_error.restype = C.c_char_p
+    L.heat_kernel_launches.restype = C.c_ulonglong
     L.heat_ctx_create.argtypes = [C.c_int, C.POINTER(vp)]
     L.heat_ctx_set_stream.argtypes = [vp, vp]
     L.heat_open.argtypes = [vp, C.c_char_p, C.c_int]
@@ -135,6 +136,11 @@ def _ptr(a: np.ndarray, t):
 
 def device_count() -> int:
     return int(lib().heat_device_count())
+
+
+def kernel_launches() -> int:
+    """Kernels of libheat_b200 launched by this process so far."""
+    return int(lib().heat_kernel_launches())
 
 
 def _as_pointer(obj):

@@ -48,6 +48,8 @@ enum { HEAT_PART_CONTIGUOUS = 0,         /* Tpetra uniform contiguous map, Exodu
 const char *heat_last_error(void);
 int  heat_version(void);
 int  heat_device_count(void);            /* CUDA devices visible; 0 => every compute call fails  */
+/* number of this library's own kernels launched by this process so far (CUB/NCCL not counted)   */
+unsigned long long heat_kernel_launches(void);
 
 /* ---- lifecycle: IO() / open / create / ~IO  (ExodusIO.hpp:85, :88-100, :103-114, :2072-2079) */
 int  heat_ctx_create(int device, heat_ctx **out);
