@@ -125,7 +125,10 @@ static int assemble_cube_analytic(heat_ctx *ctx, int mode, heat_matrix *A, heat_
 }
 
 // ---- explicit connectivity (Exodus meshes, explicit cubes), any rank count -------------------------
-static int assemble_general(heat_ctx *ctx, int mode, int partitioner, heat_matrix *A, heat_vector **B) {
+// node_bc: NaN = DOF node, else its prescribed value.  node_owner (may be null): owner rank of every
+// ORIGINAL node — overrides `partitioner` (IO::getMatrix distributes rows by element partition).
+static int assemble_general(heat_ctx *ctx, int mode, int partitioner, const std::vector<double> &node_bc,
+                            const int32_t *node_owner, heat_matrix *A, heat_vector **B) {
     const HostMesh &m = ctx->mesh;
     GeneralAssembler ga;
     cudaStream_t st = ctx->stream;
@@ -133,7 +136,7 @@ static int assemble_general(heat_ctx *ctx, int mode, int partitioner, heat_matri
         HEAT_TRY(ga.make_cube(m.nx, m.ny, m.nz, st));
     } else {
         if (m.num_nodes >= (1ll << 31) || m.num_elem >= (1ll << 31)) HEAT_FAIL(2, "mesh too large for int32 ids");
-        HEAT_TRY(ga.upload(m, ctx->node_bc, st));
+        HEAT_TRY(ga.upload(m, node_bc, st));
     }
     HEAT_TRY(ga.build_pattern(st));
     A->n_global = ga.n; A->nnz_global = ga.nnz; A->max_row_len = ga.max_row;
@@ -160,7 +163,9 @@ static int assemble_general(heat_ctx *ctx, int mode, int partitioner, heat_matri
     std::vector<int64_t> r2o((size_t)ga.n);
     if (ga.n > 0) HEAT_CUDA(cudaMemcpy(r2o.data(), ga.red2orig.p, sizeof(int64_t) * r2o.size(), cudaMemcpyDeviceToHost));
     std::vector<int32_t> part((size_t)ga.n);
-    if (partitioner == HEAT_PART_METIS_KWAY) {
+    if (node_owner) {
+        for (int64_t i = 0; i < ga.n; ++i) part[(size_t)i] = node_owner[(size_t)r2o[(size_t)i]];
+    } else if (partitioner == HEAT_PART_METIS_KWAY) {
         HEAT_TRY(metis_kway_partition(ga.n, grow.data(), gcol.data(), P, part.data()));
     } else if (partitioner == HEAT_PART_SLAB && m.is_cube) {
         const int64_t nxy = (int64_t)m.nx * m.ny;
@@ -331,7 +336,7 @@ extern "C" int heat_assemble(heat_ctx *ctx, int op_mode, int partitioner, heat_m
     heat_vector *B = nullptr, *X = nullptr;
     HEAT_CUDA(cudaEventRecord(ctx->ev_a, ctx->stream));
     int rc = (m.is_cube && !m.cube_explicit) ? assemble_cube_analytic(ctx, op_mode, A, &B)
-                                             : assemble_general(ctx, op_mode, partitioner, A, &B);
+                                             : assemble_general(ctx, op_mode, partitioner, ctx->node_bc, nullptr, A, &B);
     if (!rc) rc = finish_matrix(ctx, A);
     if (!rc) rc = new_vector(ctx, A, &X);
     if (rc) { delete A; delete B; delete X; return rc; }
@@ -346,6 +351,83 @@ extern "C" int heat_assemble(heat_ctx *ctx, int op_mode, int partitioner, heat_m
     else ctx->owned_gids = A->owned_gids;
     *A_out = A; *X_out = X; *B_out = B;
     return 0;
+}
+
+// IO::getMatrix (ExodusIO.hpp:733-1489): the Laplacian of the WHOLE mesh (nodesets are not applied, so
+// the matrix is singular, :729-731), one row per node, rows distributed by element partition + the
+// node-ownership rule of :1191-1295.  Element partition: METIS_PartMeshDual with the reference's
+// ncommon (the serial counterpart of ParMETIS_V3_PartMeshKway at :919, which does not exist here).
+extern "C" int heat_get_matrix(heat_ctx *ctx, int op_mode, heat_matrix **A_out) {
+    if (!ctx || !A_out) HEAT_FAIL(2, "heat_get_matrix: null argument");
+    if (!ctx->mesh.valid) HEAT_FAIL(4, "heat_get_matrix: no mesh (readFID == -1)");
+    if (ctx->mesh.is_cube) HEAT_FAIL(4, "heat_get_matrix: needs a mesh from heat_open / heat_mesh_set");
+    if (op_mode != HEAT_OP_GRAPH_LAPLACIAN && op_mode != HEAT_OP_P1_FEM) HEAT_FAIL(2, "heat_get_matrix: unknown operator %d", op_mode);
+    HEAT_NEED_GPU(ctx, "heat_get_matrix");
+    HEAT_CUDA(cudaSetDevice(ctx->device));
+    const HostMesh &m = ctx->mesh;
+    std::vector<int32_t> owner;
+    if (ctx->nranks > 1) {
+        std::vector<int64_t> epart((size_t)m.num_elem), npart((size_t)m.num_nodes);
+        int64_t obj = 0;
+        HEAT_TRY(heat_decompose_partition(ctx, ctx->nranks, &obj, epart.data(), npart.data()));
+        owner.resize((size_t)m.num_nodes);
+        HEAT_TRY(heat_node_owners(m.num_nodes, m.num_elem, m.npe, m.conn.data(), epart.data(), ctx->nranks, owner.data()));
+    }
+    const std::vector<double> no_bc((size_t)m.num_nodes, std::numeric_limits<double>::quiet_NaN());
+    heat_matrix *A = new heat_matrix();
+    A->ctx = ctx; A->op_mode = op_mode;
+    heat_vector *B = nullptr;
+    HEAT_CUDA(cudaEventRecord(ctx->ev_a, ctx->stream));
+    int rc = assemble_general(ctx, op_mode, HEAT_PART_CONTIGUOUS, no_bc, owner.empty() ? nullptr : owner.data(), A, &B);
+    if (!rc) rc = finish_matrix(ctx, A);
+    delete B;                                            // no Dirichlet nodes => the load vector is zero
+    if (rc) { delete A; return rc; }
+    HEAT_CUDA(cudaEventRecord(ctx->ev_b, ctx->stream));
+    HEAT_CUDA(cudaStreamSynchronize(ctx->stream));
+    float ms = 0.f;
+    HEAT_CUDA(cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b));
+    A->assemble_ms = ms;
+    *A_out = A;
+    return 0;
+}
+
+// nodeSetMap of getMatrix (ExodusIO.hpp:1447-1466): the nodes of nodeset `set_id` whose rows this rank owns
+extern "C" int heat_matrix_owned_nodeset(const heat_matrix *A, int64_t set_id, int64_t *count, int64_t *nodes_out) {
+    if (!A || !count) HEAT_FAIL(2, "heat_matrix_owned_nodeset: null argument");
+    const HostMesh &m = A->ctx->mesh;
+    auto it = m.nodesets.find(set_id);
+    if (it == m.nodesets.end()) HEAT_FAIL(5, "heat_matrix_owned_nodeset: no nodeset with id %lld", (long long)set_id);
+    std::vector<int64_t> r2o((size_t)A->n_owned);
+    HEAT_TRY(heat_matrix_export_red2orig(A, r2o.data()));
+    std::vector<char> mine((size_t)m.num_nodes, 0);
+    for (int64_t g : r2o) mine[(size_t)g] = 1;
+    std::vector<int64_t> out;
+    for (int64_t g : it->second)
+        if (mine[(size_t)g]) out.push_back(g);
+    std::sort(out.begin(), out.end());                               // std::set<idx_t> order
+    out.erase(std::unique(out.begin(), out.end()), out.end());
+    *count = (int64_t)out.size();
+    if (nodes_out) std::copy(out.begin(), out.end(), nodes_out);
+    return 0;
+}
+
+// ex_get_ids(readFID, EX_NODE_SET, ids) (ExodusIO.hpp:172, :1443): ascending ids of the mesh's nodesets
+extern "C" int heat_mesh_nodeset_ids(const heat_ctx *ctx, int *count, int64_t *ids_out) {
+    if (!ctx || !count) HEAT_FAIL(2, "heat_mesh_nodeset_ids: null argument");
+    if (!ctx->mesh.valid) HEAT_FAIL(4, "heat_mesh_nodeset_ids: no mesh");
+    *count = (int)ctx->mesh.nodesets.size();
+    if (ids_out) {
+        int w = 0;
+        for (const auto &kv : ctx->mesh.nodesets) ids_out[w++] = kv.first;
+    }
+    return 0;
+}
+
+extern "C" int heat_power_method(heat_ctx *ctx, heat_matrix *A, int niters, double tolerance, uint64_t seed,
+                                 heat_power_info *info) {
+    if (!ctx || !A) HEAT_FAIL(2, "heat_power_method: null argument");
+    HEAT_NEED_GPU(ctx, "heat_power_method");
+    return power_method_device(ctx, A, niters, tolerance, seed, info);
 }
 
 extern "C" void heat_solve_opts_default(heat_solve_opts *o) {

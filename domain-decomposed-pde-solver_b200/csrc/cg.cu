@@ -394,6 +394,46 @@ int launch_dot2(int64_t n, const double *a, const double *b, const double *c, co
     return 0;
 }
 
+// -------------------------------------------------------------------------------------------------
+// power method (ExodusMatrixTest.cpp:97-100): q = z / ||z||, the norm read from a device scalar
+// (||z||^2 comes out of the previous SpMV's fused reduction, so no host round trip per iteration)
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) pm_scale_kernel(int64_t n, const double *__restrict__ z,
+                                                          const double *__restrict__ zz, double *__restrict__ q) {
+    const double inv = 1.0 / sqrt(*zz);
+    const int64_t n2 = n >> 1, stride = (int64_t)gridDim.x * kBlock;
+    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n2; i += stride) {
+        const double2 v = ld_stream_f64x2(z + 2 * i);
+        *reinterpret_cast<double2 *>(q + 2 * i) = make_double2(inv * v.x, inv * v.y);
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) q[n - 1] = inv * z[n - 1];
+}
+int launch_pm_scale(int64_t n, const double *z, const double *zz, double *q, int grid, cudaStream_t st) {
+    pm_scale_kernel<<<grid, kBlock, 0, st>>>(n, z, zz, q);
+    HEAT_LAUNCHED();
+    return 0;
+}
+// ||z - lambda q||^2 (ExodusMatrixTest.cpp:104-105), lambda read from a device scalar
+__global__ void __launch_bounds__(kBlock) pm_resid_kernel(int64_t n, const double *__restrict__ z,
+                                                          const double *__restrict__ q, const double *__restrict__ lambda,
+                                                          double *out, double *partials, int *counter) {
+    const double lam = *lambda;
+    double acc[1] = {0.0};
+    const int64_t stride = (int64_t)gridDim.x * kBlock;
+    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += stride) {
+        const double d = z[i] - lam * q[i];
+        acc[0] += d * d;
+    }
+    double *const o[1] = {out};
+    grid_sum<1>(acc, partials, 0, gridDim.x, counter, o);
+}
+int launch_pm_resid(int64_t n, const double *z, const double *q, const double *lambda, double *out,
+                    double *partials, int *counter, int grid, cudaStream_t st) {
+    pm_resid_kernel<<<grid, kBlock, 0, st>>>(n, z, q, lambda, out, partials, counter);
+    HEAT_LAUNCHED();
+    return 0;
+}
+
 // Ifpack2 Chebyshev, zero start: W = D^-1 r / theta ; Z = W
 __global__ void __launch_bounds__(kBlock) cheb_first_kernel(int64_t n, const double *__restrict__ dinv,
                                                             const double *__restrict__ r, double inv_theta,

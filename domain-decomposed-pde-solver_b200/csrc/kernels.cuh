@@ -19,6 +19,7 @@ struct CgGate {               // stopping test evaluated by every block of every
 
 struct DotOut {               // where a fused dot product is reduced to
     double *partials; int part_offset; int total_blocks; int *counter; double *out;
+    bool with_yy = false;     // SpMV only: also reduce sum_i y_i^2 into out[1]
 };
 
 struct SpmvPeer {             // peer-memory mode of the SpMV (single launch over interior+boundary slices)
@@ -72,6 +73,9 @@ int launch_cg_xr_plain(int64_t n, double *x, double *r, const double *p, const d
 int launch_cg_p_plain(int64_t n, double *p, const double *z, CgGate gate, int grid, cudaStream_t st);
 int launch_cg_dots(int64_t n, const double *r, const double *z, CgGate gate, CgRec *H, int *I,
                    double *partials, int *counter, int grid, cudaStream_t st);
+int launch_pm_scale(int64_t n, const double *z, const double *zz, double *q, int grid, cudaStream_t st);
+int launch_pm_resid(int64_t n, const double *z, const double *q, const double *lambda, double *out,
+                    double *partials, int *counter, int grid, cudaStream_t st);
 int launch_fill(int64_t n, double *x, double v, cudaStream_t st);
 int launch_fill_hash(int64_t n, double *x, const int64_t *gids, int64_t gid0, uint64_t seed, cudaStream_t st);
 int launch_gather(int64_t n, const double *x, const int32_t *idx, double *out, cudaStream_t st);

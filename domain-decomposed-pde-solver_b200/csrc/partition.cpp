@@ -72,6 +72,55 @@ int metis_part_mesh_dual(int64_t ne, int64_t nn, int npe, const int32_t *conn, i
 
 }  // namespace heat
 
+// Node ownership of IO::getMatrix (ExodusIO.hpp:1089-1295).  Each rank holds the elements METIS gave
+// it; a node shared by several ranks goes to the rank in whose LOCAL adjacency (cliques of its own
+// elements, :1089-1097) the node has the most distinct neighbours (nodeToFreq, :1163-1168), ties to
+// the lowest rank (:1268-1270).  The reference finds the sharers with one-sided MPI_Gets and
+// exchanges (node, freq) lists (with the request-array overflow D9); the rule itself is a pure
+// function of (connectivity, epart), evaluated here for every node at once.  Nodes in no element
+// (absent from every rank's nodeIndices in the reference) are given to rank 0.
+extern "C" int heat_node_owners(int64_t num_nodes, int64_t num_elem, int npe, const int32_t *conn,
+                                const int64_t *epart, int nparts, int32_t *owner_out) {
+    if (num_nodes < 0 || num_elem < 0 || npe < 1 || nparts < 1 || !owner_out || (num_elem > 0 && (!conn || !epart)))
+        HEAT_FAIL(2, "heat_node_owners: bad arguments");
+    std::vector<int64_t> ptr((size_t)num_nodes + 1, 0);
+    for (int64_t q = 0; q < num_elem * npe; ++q) {
+        if (conn[q] < 0 || conn[q] >= num_nodes) HEAT_FAIL(2, "heat_node_owners: connectivity entry out of range");
+        ptr[(size_t)conn[q] + 1]++;
+    }
+    for (int64_t e = 0; e < num_elem; ++e)
+        if (epart[e] < 0 || epart[e] >= nparts) HEAT_FAIL(2, "heat_node_owners: epart[%lld] = %lld out of range", (long long)e, (long long)epart[e]);
+    for (int64_t v = 0; v < num_nodes; ++v) ptr[(size_t)v + 1] += ptr[(size_t)v];
+    std::vector<int64_t> n2e((size_t)(num_elem * npe)), fill(ptr.begin(), ptr.end() - 1);
+    for (int64_t e = 0; e < num_elem; ++e)
+        for (int k = 0; k < npe; ++k) n2e[(size_t)fill[(size_t)conn[e * npe + k]]++] = e;
+    std::vector<int64_t> keys;                       // (part << 40 | neighbour), distinct per node
+    std::vector<int64_t> freq((size_t)nparts);
+    for (int64_t v = 0; v < num_nodes; ++v) {
+        keys.clear();
+        for (int64_t t = ptr[(size_t)v]; t < ptr[(size_t)v + 1]; ++t) {
+            const int64_t e = n2e[(size_t)t];
+            for (int k = 0; k < npe; ++k) {
+                const int64_t u = conn[e * npe + k];
+                if (u != v) keys.push_back((epart[e] << 40) | u);
+            }
+        }
+        std::sort(keys.begin(), keys.end());
+        keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
+        std::fill(freq.begin(), freq.end(), -1);     // -1: the rank does not hold the node at all
+        for (int64_t t = ptr[(size_t)v]; t < ptr[(size_t)v + 1]; ++t) {
+            int64_t &f = freq[(size_t)epart[(size_t)n2e[(size_t)t]]];
+            if (f < 0) f = 0;
+        }
+        for (int64_t key : keys) freq[(size_t)(key >> 40)]++;
+        int32_t best = 0;
+        for (int p = 1; p < nparts; ++p)
+            if (freq[(size_t)p] > freq[(size_t)best]) best = p;     // strict '>' keeps the lowest rank on ties
+        owner_out[v] = best;
+    }
+    return 0;
+}
+
 extern "C" int heat_partition_rows(int64_t n_global, const int64_t *row_ptr, const int32_t *col, int partitioner,
                                    int nranks, int32_t *part_out) {
     if (nranks < 1 || n_global < 0 || !part_out) HEAT_FAIL(2, "heat_partition_rows: bad arguments");

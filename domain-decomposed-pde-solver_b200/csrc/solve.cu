@@ -24,10 +24,11 @@ int sm_count(int device) {
 }
 
 // y = A x with the halo exchange of x overlapped with the interior slices
-int spmv_halo(heat_ctx *ctx, heat_matrix *A, double *x, double *y, CgGate gate, double *dot_out) {
+int spmv_halo(heat_ctx *ctx, heat_matrix *A, double *x, double *y, CgGate gate, double *dot_out, bool with_yy) {
     const int sms = sm_count(ctx->device);
     const bool split = ctx->nranks > 1 && A->halo.n_neighbors > 0;
     DotOut d{A->partials.p, 0, 0, A->iscal.p + I_COUNTER, dot_out};
+    d.with_yy = with_yy;
     if (!split) {
         const int g = spmv_grid(A->n_slices, sms);
         d.total_blocks = g;
@@ -114,6 +115,59 @@ static int estimate_lambda_max(heat_ctx *ctx, heat_matrix *A, double *lmax_out) 
         HEAT_TRY(launch_axpby(A->n_owned, 1.0 / ny, y, 0.0, x, grid, ctx->stream));
     }
     *lmax_out = lam;
+    return 0;
+}
+
+// Power method of ExodusMatrixTest.cpp:56-129: q = z/||z|| ; z = A q ; lambda = q.z ; every 50
+// iterations (and at the last one) ||z - lambda q|| is compared with the tolerance.  Two launches
+// per iteration (scale, SpMV with fused q.z and z.z); the host is only involved at the reports.
+// The reference starts from Tpetra's randomize(); here the start vector is the counter-based hash
+// of the global row id, so the estimate is reproducible and GPU-count invariant.
+int power_method_device(heat_ctx *ctx, heat_matrix *A, int niters, double tol, uint64_t seed, heat_power_info *info) {
+    HEAT_CUDA(cudaSetDevice(ctx->device));
+    if (niters < 0) HEAT_FAIL(2, "heat_power_method: negative iteration count");
+    HEAT_TRY(ensure_workspace(A, false, false));
+    const int64_t n = A->n_owned;
+    const int vgrid = vec_grid(n, sm_count(ctx->device));
+    cudaStream_t st = ctx->stream;
+    double *q = A->w_p.p, *z = A->w_ap.p, *S = A->scal.p;
+    int *I = A->iscal.p;
+    CgGate nogate{nullptr, nullptr, nullptr, 0};
+    const int reportFrequency = 50;                                     // ExodusMatrixTest.cpp:91
+    HEAT_CUDA(cudaMemsetAsync(I, 0, sizeof(int) * I_COUNT, st));
+    HEAT_CUDA(cudaEventRecord(ctx->ev_a, st));
+    HEAT_TRY(launch_fill_hash(n, z, A->owned_contiguous ? nullptr : A->d_owned_gids.p, A->gid0, seed, st));
+    HEAT_TRY(launch_dot2(n, z, z, z, z, S + S_TMP1, S + S_TMP2, A->partials.p, I + I_COUNTER2, vgrid, st));
+    HEAT_TRY(comm_allreduce_sum(ctx, S + S_TMP1, 1));
+    double lambda = 0.0, residual = 0.0;
+    int iters = niters, converged = 0, n_reports = 0;
+    for (int iter = 0; iter < niters; ++iter) {
+        HEAT_TRY(launch_pm_scale(n, z, S + S_TMP1, q, vgrid, st));                        // q := z / normz
+        HEAT_TRY(spmv_halo(ctx, A, q, z, nogate, S + S_TMP0, true));                      // z := A q ; q.z ; z.z
+        HEAT_TRY(comm_allreduce_sum(ctx, S + S_TMP0, 2));
+        if (iter % reportFrequency == 0 || iter + 1 == niters) {
+            HEAT_TRY(launch_pm_resid(n, z, q, S + S_TMP0, S + S_TMP2, A->partials.p, I + I_COUNTER2, vgrid, st));
+            HEAT_TRY(comm_allreduce_sum(ctx, S + S_TMP2, 1));
+            double h[3];
+            HEAT_CUDA(cudaMemcpyAsync(h, S + S_TMP0, sizeof(h), cudaMemcpyDeviceToHost, st));
+            HEAT_CUDA(cudaStreamSynchronize(st));
+            lambda = h[0];
+            residual = sqrt(h[2]);
+            if (info && info->report_buf && n_reports < info->report_capacity) {
+                double *rep = info->report_buf + 3 * (size_t)n_reports++;
+                rep[0] = (double)iter; rep[1] = lambda; rep[2] = residual;
+            }
+            if (residual < tol) { iters = iter; converged = 1; break; }
+        }
+    }
+    HEAT_CUDA(cudaEventRecord(ctx->ev_b, st));
+    HEAT_CUDA(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    HEAT_CUDA(cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b));
+    if (info) {
+        info->lambda = lambda; info->residual = residual; info->iters = iters; info->converged = converged;
+        info->solve_ms = ms; info->report_count = n_reports;
+    }
     return 0;
 }
 

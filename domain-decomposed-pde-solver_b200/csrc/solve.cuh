@@ -5,7 +5,8 @@
 
 namespace heat {
 int sm_count(int device);
-int spmv_halo(heat_ctx *ctx, heat_matrix *A, double *x, double *y, CgGate gate, double *dot_out);
+int spmv_halo(heat_ctx *ctx, heat_matrix *A, double *x, double *y, CgGate gate, double *dot_out, bool with_yy = false);
+int power_method_device(heat_ctx *ctx, heat_matrix *A, int niters, double tol, uint64_t seed, heat_power_info *info);
 int ensure_workspace(heat_matrix *A, bool single_reduce, bool cheb);
 int solve_device(heat_ctx *ctx, heat_matrix *A, double *x, const double *b, const heat_solve_opts &o,
                  heat_solve_info *info);

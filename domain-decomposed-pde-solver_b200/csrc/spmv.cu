@@ -36,7 +36,8 @@ __device__ __forceinline__ bool gate_done(const CgGate &g) {
 // =================================================================================================
 // direct-load kernel
 // =================================================================================================
-template <bool DOT>
+// DOT: 0 = none, 1 = sum_i y_i x_i, 2 = also sum_i y_i^2 (power method: lambda and ||A q||^2 in one pass)
+template <int DOT>
 __global__ void __launch_bounds__(kBlock)
 sell_spmv_kernel(const int64_t *__restrict__ slice_ptr, const int32_t *__restrict__ col,
                  const double *__restrict__ val, const double *__restrict__ x, double *__restrict__ y,
@@ -45,7 +46,7 @@ sell_spmv_kernel(const int64_t *__restrict__ slice_ptr, const int32_t *__restric
     if (gate_done(gate)) return;
     const int lane = threadIdx.x & 31;
     const int64_t warps_total = (int64_t)gridDim.x * kWarpsPerBlock;
-    double dsum = 0.0;
+    double dsum = 0.0, ysum = 0.0;
     for (int64_t t = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); t < n_list; t += warps_total) {
         const int64_t s = slice_list ? (int64_t)slice_list[t] : t;
         const int64_t base = slice_ptr[s];
@@ -64,15 +65,21 @@ sell_spmv_kernel(const int64_t *__restrict__ slice_ptr, const int32_t *__restric
         if (row + 1 < n_rows) {
             *reinterpret_cast<double2 *>(y + row) = make_double2(acc0, acc1);
             if (DOT) dsum += acc0 * __ldg(x + row) + acc1 * __ldg(x + row + 1);
+            if (DOT == 2) ysum += acc0 * acc0 + acc1 * acc1;
         } else if (row < n_rows) {
             y[row] = acc0;
             if (DOT) dsum += acc0 * __ldg(x + row);
+            if (DOT == 2) ysum += acc0 * acc0;
         }
     }
-    if (DOT) {
+    if (DOT == 1) {
         double acc[1] = {dsum};
         double *const out[1] = {dot.out};
         grid_sum<1>(acc, dot.partials, dot.part_offset, dot.total_blocks, dot.counter, out);
+    } else if (DOT == 2) {
+        double acc[2] = {dsum, ysum};
+        double *const out[2] = {dot.out, dot.out + 1};
+        grid_sum<2>(acc, dot.partials, dot.part_offset, dot.total_blocks, dot.counter, out);
     }
 }
 
@@ -123,7 +130,7 @@ struct TmaSmem {
     static constexpr size_t total(int nwarps) { return (size_t)nwarps * kWarpBytes + (size_t)nwarps * NSTAGE * 8; }
 };
 
-template <bool DOT, int KC, int NSTAGE, int NWARPS, bool PEER = false>
+template <int DOT, int KC, int NSTAGE, int NWARPS, bool PEER = false>
 __global__ void __launch_bounds__(NWARPS * 32, (NWARPS <= 8 && KC <= 8) ? 2 : 1)
 sell_spmv_tma_kernel(const int64_t *__restrict__ slice_ptr, const int32_t *__restrict__ col,
                      const double *__restrict__ val, const double *__restrict__ x, double *__restrict__ y,
@@ -193,7 +200,7 @@ sell_spmv_tma_kernel(const int64_t *__restrict__ slice_ptr, const int32_t *__res
     Meta mc = load_meta(tc), mc_next = load_meta(tc + W);
     int stage = 0;
     uint32_t parity = 0;
-    double acc0 = 0.0, acc1 = 0.0, dsum = 0.0;
+    double acc0 = 0.0, acc1 = 0.0, dsum = 0.0, ysum = 0.0;
     bool halo_ready = !PEER;
     while (tc < n_list) {
         mbar_wait(bars + stage, parity);
@@ -240,9 +247,11 @@ sell_spmv_tma_kernel(const int64_t *__restrict__ slice_ptr, const int32_t *__res
             if (row + 1 < n_rows) {
                 *reinterpret_cast<double2 *>(y + row) = make_double2(acc0, acc1);
                 if (DOT) dsum += acc0 * __ldg(x + row) + acc1 * __ldg(x + row + 1);
+                if (DOT == 2) ysum += acc0 * acc0 + acc1 * acc1;
             } else if (row < n_rows) {
                 y[row] = acc0;
                 if (DOT) dsum += acc0 * __ldg(x + row);
+                if (DOT == 2) ysum += acc0 * acc0;
             }
             acc0 = 0.0; acc1 = 0.0;
             tc += W; kc0 = 0;
@@ -251,7 +260,11 @@ sell_spmv_tma_kernel(const int64_t *__restrict__ slice_ptr, const int32_t *__res
         }
         if (++stage == NSTAGE) { stage = 0; parity ^= 1u; }
     }
-    if (DOT) {
+    if (DOT == 2) {
+        double acc[2] = {dsum, ysum};
+        double *const out[2] = {dot.out, dot.out + 1};
+        grid_sum<2, NWARPS>(acc, dot.partials, dot.part_offset, dot.total_blocks, dot.counter, out);
+    } else if (DOT) {
         double acc[1] = {dsum};
         double *const out[1] = {dot.out};
         if (PEER) {        // p.Ap of this rank -> all ranks' inboxes, one lane per destination
@@ -292,7 +305,7 @@ int spmv_grid(int64_t n_list, int sm_count) {
     return grid_for(blocks, sm_count, v == 5 ? 2 : 1);    // persistent: one (or two) CTA per SM
 }
 
-template <bool DOT, int KC, int NSTAGE, int NWARPS>
+template <int DOT, int KC, int NSTAGE, int NWARPS>
 static int launch_tma(const heat_matrix *A, const double *x, double *y, const int32_t *slice_list, int64_t n_list,
                       CgGate gate, DotOut dot, int grid, cudaStream_t st) {
     auto kern = sell_spmv_tma_kernel<DOT, KC, NSTAGE, NWARPS>;
@@ -313,7 +326,7 @@ bool spmv_peer_supported() { return spmv_variant() == 5; }
 
 int launch_spmv_peer(const heat_matrix *A, const double *x, double *y, CgGate gate, DotOut dot, SpmvPeer peer,
                      int grid, cudaStream_t st) {
-    auto kern = sell_spmv_tma_kernel<true, 8, 2, 8, true>;
+    auto kern = sell_spmv_tma_kernel<1, 8, 2, 8, true>;
     const size_t smem = TmaSmem<8, 2>::total(8);
     static bool configured = false;
     if (!configured) {
@@ -334,25 +347,32 @@ int launch_spmv(const heat_matrix *A, const double *x, double *y, const int32_t 
     if (n_list <= 0 && dot.out == nullptr) return 0;
     const int v = spmv_variant();
     const bool d = dot.out != nullptr;
+    if (d && dot.with_yy) {      // x.y and y.y in one pass (power method): default TMA config or direct loads
+        if (v != 0) return launch_tma<2, 8, 2, 8>(A, x, y, slice_list, n_list, gate, dot, grid, st);
+        sell_spmv_kernel<2><<<grid, kBlock, 0, st>>>(A->slice_ptr.p, A->sell_col.p, A->sell_val.p, x, y,
+                                                    A->n_owned, slice_list, n_list, gate, dot);
+        HEAT_LAUNCHED();
+        return 0;
+    }
     switch (v) {
-        case 1: return d ? launch_tma<true, 16, 2, 8>(A, x, y, slice_list, n_list, gate, dot, grid, st)
-                         : launch_tma<false, 16, 2, 8>(A, x, y, slice_list, n_list, gate, dot, grid, st);
-        case 2: return d ? launch_tma<true, 8, 3, 12>(A, x, y, slice_list, n_list, gate, dot, grid, st)
-                         : launch_tma<false, 8, 3, 12>(A, x, y, slice_list, n_list, gate, dot, grid, st);
-        case 3: return d ? launch_tma<true, 8, 2, 16>(A, x, y, slice_list, n_list, gate, dot, grid, st)
-                         : launch_tma<false, 8, 2, 16>(A, x, y, slice_list, n_list, gate, dot, grid, st);
-        case 4: return d ? launch_tma<true, 4, 3, 24>(A, x, y, slice_list, n_list, gate, dot, grid, st)
-                         : launch_tma<false, 4, 3, 24>(A, x, y, slice_list, n_list, gate, dot, grid, st);
-        case 5: return d ? launch_tma<true, 8, 2, 8>(A, x, y, slice_list, n_list, gate, dot, grid, st)
-                         : launch_tma<false, 8, 2, 8>(A, x, y, slice_list, n_list, gate, dot, grid, st);
+        case 1: return d ? launch_tma<1, 16, 2, 8>(A, x, y, slice_list, n_list, gate, dot, grid, st)
+                         : launch_tma<0, 16, 2, 8>(A, x, y, slice_list, n_list, gate, dot, grid, st);
+        case 2: return d ? launch_tma<1, 8, 3, 12>(A, x, y, slice_list, n_list, gate, dot, grid, st)
+                         : launch_tma<0, 8, 3, 12>(A, x, y, slice_list, n_list, gate, dot, grid, st);
+        case 3: return d ? launch_tma<1, 8, 2, 16>(A, x, y, slice_list, n_list, gate, dot, grid, st)
+                         : launch_tma<0, 8, 2, 16>(A, x, y, slice_list, n_list, gate, dot, grid, st);
+        case 4: return d ? launch_tma<1, 4, 3, 24>(A, x, y, slice_list, n_list, gate, dot, grid, st)
+                         : launch_tma<0, 4, 3, 24>(A, x, y, slice_list, n_list, gate, dot, grid, st);
+        case 5: return d ? launch_tma<1, 8, 2, 8>(A, x, y, slice_list, n_list, gate, dot, grid, st)
+                         : launch_tma<0, 8, 2, 8>(A, x, y, slice_list, n_list, gate, dot, grid, st);
         default: break;
     }
     if (d)
-        sell_spmv_kernel<true><<<grid, kBlock, 0, st>>>(A->slice_ptr.p, A->sell_col.p, A->sell_val.p, x, y,
-                                                       A->n_owned, slice_list, n_list, gate, dot);
+        sell_spmv_kernel<1><<<grid, kBlock, 0, st>>>(A->slice_ptr.p, A->sell_col.p, A->sell_val.p, x, y,
+                                                    A->n_owned, slice_list, n_list, gate, dot);
     else
-        sell_spmv_kernel<false><<<grid, kBlock, 0, st>>>(A->slice_ptr.p, A->sell_col.p, A->sell_val.p, x, y,
-                                                        A->n_owned, slice_list, n_list, gate, dot);
+        sell_spmv_kernel<0><<<grid, kBlock, 0, st>>>(A->slice_ptr.p, A->sell_col.p, A->sell_val.p, x, y,
+                                                    A->n_owned, slice_list, n_list, gate, dot);
     HEAT_LAUNCHED();
     return 0;
 }

@@ -50,6 +50,12 @@ class MatrixInfo(C.Structure):
                 ("assemble_ms", C.c_double), ("peer_path", C.c_int32), ("reserved", C.c_int32)]
 
 
+class PowerInfo(C.Structure):
+    _fields_ = [("lambda_", C.c_double), ("residual", C.c_double), ("iters", C.c_int), ("converged", C.c_int),
+                ("solve_ms", C.c_double), ("report_buf", C.POINTER(C.c_double)), ("report_capacity", C.c_int),
+                ("report_count", C.c_int)]
+
+
 class PlanSizes(C.Structure):
     _fields_ = [("n_owned", C.c_int64), ("n_ghost", C.c_int64), ("n_neighbors", C.c_int32), ("n_send", C.c_int64)]
 
@@ -57,8 +63,8 @@ class PlanSizes(C.Structure):
 # every symbol include/heat_b200.h declares (tests check the .so exports all of them)
 ABI_SYMBOLS = [
     "heat_last_error", "heat_version", "heat_device_count", "heat_kernel_launches", "heat_ctx_create", "heat_ctx_set_stream", "heat_open",
-    "heat_create", "heat_close", "heat_mesh_set", "heat_mesh_cube", "heat_comm_unique_id", "heat_comm_init",
-    "heat_comm_rank", "heat_assemble", "heat_solve_opts_default", "heat_solve", "heat_solve_host", "heat_spmv",
+    "heat_create", "heat_close", "heat_mesh_set", "heat_mesh_cube", "heat_mesh_nodeset_ids", "heat_comm_unique_id", "heat_comm_init",
+    "heat_comm_rank", "heat_assemble", "heat_get_matrix", "heat_node_owners", "heat_matrix_owned_nodeset", "heat_power_method", "heat_solve_opts_default", "heat_solve", "heat_solve_host", "heat_spmv",
     "heat_cg_iterations", "heat_decompose", "heat_write_solution", "heat_nodal_field", "heat_decompose_partition",
     "heat_matrix_get_info", "heat_matrix_export_csr", "heat_matrix_export_maps", "heat_matrix_export_plan",
     "heat_matrix_export_red2orig", "heat_matrix_free", "heat_vector_create", "heat_vector_size",
@@ -88,10 +94,15 @@ def lib():
     L.heat_close.argtypes = [vp]
     L.heat_mesh_set.argtypes = [vp, C.c_int64, C.c_int, dp, dp, dp, C.c_int64, C.c_int, i32p, C.c_int, i64p, i64p, i64p]
     L.heat_mesh_cube.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.heat_mesh_nodeset_ids.argtypes = [vp, C.POINTER(C.c_int), i64p]
     L.heat_comm_unique_id.argtypes = [C.c_char_p]
     L.heat_comm_init.argtypes = [vp, C.c_int, C.c_int, C.c_char_p]
     L.heat_comm_rank.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.heat_assemble.argtypes = [vp, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    L.heat_get_matrix.argtypes = [vp, C.c_int, C.POINTER(vp)]
+    L.heat_node_owners.argtypes = [C.c_int64, C.c_int64, C.c_int, i32p, i64p, C.c_int, i32p]
+    L.heat_matrix_owned_nodeset.argtypes = [vp, C.c_int64, i64p, i64p]
+    L.heat_power_method.argtypes = [vp, vp, C.c_int, C.c_double, C.c_uint64, C.POINTER(PowerInfo)]
     L.heat_solve_opts_default.argtypes = [C.POINTER(SolveOpts)]
     L.heat_solve_opts_default.restype = None
     L.heat_solve.argtypes = [vp, vp, vp, vp, C.POINTER(SolveOpts), C.POINTER(SolveInfo)]
@@ -246,10 +257,28 @@ class Matrix:
         _check(lib().heat_vector_fill_hash(self.io.h, self.h, v.h, seed))
         return v
 
+    def owned_nodeset(self, set_id: int) -> np.ndarray:
+        """getMatrix's nodeSetMap[set_id] (ExodusIO.hpp:1447-1466): owned nodes of that nodeset, 0-based."""
+        cnt = C.c_int64(0)
+        _check(lib().heat_matrix_owned_nodeset(self.h, set_id, C.byref(cnt), None))
+        out = np.empty(max(cnt.value, 1), dtype=np.int64)
+        _check(lib().heat_matrix_owned_nodeset(self.h, set_id, C.byref(cnt), _ptr(out, C.c_int64)))
+        return out[: cnt.value]
+
     def free(self):
         if self.h:
             lib().heat_matrix_free(self.h)
             self.h = None
+
+
+@dataclass
+class PowerResult:
+    lambda_: float
+    residual: float
+    iters: int
+    converged: bool
+    solve_ms: float
+    reports: np.ndarray = None      # rows {iteration, lambda, residual}: what the reference prints every 50 iterations
 
 
 @dataclass
@@ -320,11 +349,35 @@ class IO:
     def mesh_cube(self, nx: int, ny: int, nz: int, explicit_mesh: bool = False):
         _check(lib().heat_mesh_cube(self.h, nx, ny, nz, int(explicit_mesh)))
 
+    def nodeset_ids(self) -> np.ndarray:
+        cnt = C.c_int(0)
+        _check(lib().heat_mesh_nodeset_ids(self.h, C.byref(cnt), None))
+        ids = np.zeros(max(cnt.value, 1), dtype=np.int64)
+        _check(lib().heat_mesh_nodeset_ids(self.h, C.byref(cnt), _ptr(ids, C.c_int64)))
+        return ids[: cnt.value]
+
     def assemble(self, op_mode: int = OP_GRAPH_LAPLACIAN, partitioner: int = PART_METIS_KWAY):   # ExodusIO.hpp:128
         """-> (A, X, B) like `assemble(&A, &X, &B)`; X is zero (the reference randomises it unseeded)."""
         a, x, b = C.c_void_p(), C.c_void_p(), C.c_void_p()
         _check(lib().heat_assemble(self.h, op_mode, partitioner, C.byref(a), C.byref(x), C.byref(b)))
         return Matrix(self, a), Vector(self, x), Vector(self, b)
+
+    def getMatrix(self, op_mode: int = OP_GRAPH_LAPLACIAN) -> Matrix:      # ExodusIO.hpp:733
+        """-> the whole-mesh Laplacian, rows distributed by element partition + ownership rule;
+        the reference's second output (nodeSetMap) is `Matrix.owned_nodeset(id)`."""
+        a = C.c_void_p()
+        _check(lib().heat_get_matrix(self.h, op_mode, C.byref(a)))
+        return Matrix(self, a)
+
+    def power_method(self, A: Matrix, niters: int = 500, tolerance: float = 1.0e-2, seed: int = 12345) -> PowerResult:
+        """PowerMethod::run (ExodusMatrixTest.cpp:56-129; defaults 500 / 1e-2 from :163)."""
+        info = PowerInfo()
+        cap = niters // 50 + 2
+        rep = np.zeros(3 * cap)
+        info.report_buf, info.report_capacity = _ptr(rep, C.c_double), cap
+        _check(lib().heat_power_method(self.h, A.h, niters, tolerance, seed, C.byref(info)))
+        return PowerResult(info.lambda_, info.residual, info.iters, bool(info.converged), info.solve_ms,
+                           rep[: 3 * info.report_count].reshape(-1, 3))
 
     def decompose(self, partitions: int) -> bool:                          # ExodusIO.hpp:1496
         _check(lib().heat_decompose(self.h, partitions))
@@ -390,6 +443,16 @@ def partition_rows(row_ptr, col, partitioner: int, nranks: int) -> np.ndarray:
     part = np.zeros(max(n, 1), dtype=np.int32)
     _check(lib().heat_partition_rows(n, _ptr(row_ptr, C.c_int64), _ptr(col, C.c_int32), partitioner, nranks, _ptr(part, C.c_int32)))
     return part[:n]
+
+
+def node_owners(conn, num_nodes: int, epart, nparts: int) -> np.ndarray:
+    """Node-ownership rule of IO::getMatrix (ExodusIO.hpp:1191-1295) from an element partition."""
+    conn = np.ascontiguousarray(conn, dtype=np.int32)
+    epart = np.ascontiguousarray(epart, dtype=np.int64)
+    out = np.zeros(max(num_nodes, 1), dtype=np.int32)
+    _check(lib().heat_node_owners(num_nodes, conn.shape[0], conn.shape[1], _ptr(conn, C.c_int32), _ptr(epart, C.c_int64),
+                                  nparts, _ptr(out, C.c_int32)))
+    return out[:num_nodes]
 
 
 def plan_build(row_ptr, col, part, nranks: int, rank: int) -> dict:

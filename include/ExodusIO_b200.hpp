@@ -11,8 +11,11 @@
 #include <algorithm>
 #include <cstdio>
 #include <iostream>
+#include <map>
 #include <memory>
+#include <set>
 #include <string>
+#include <vector>
 
 #include "heat_b200.h"
 
@@ -79,6 +82,33 @@ class IO {
                       << std::endl;
         }
         *A = a; *X = x; *B = b;
+        return true;
+    }
+    // ExodusIO.hpp:733 — Laplacian of the whole mesh (singular: nodesets are NOT applied), rows
+    // distributed by element partition + the node-ownership rule; nodeSetMap receives, per nodeset
+    // id, the nodes whose rows this rank owns (0-based here; the reference keeps Exodus' 1-based ids)
+    bool getMatrix(heat::Matrix *ret, std::map<int, std::set<int64_t>> &nodeSetMap, bool verbose = false) {
+        if (!ctx_) return false;
+        auto a = std::make_shared<heat::MatrixHandle>();
+        if (heat_get_matrix(ctx_, opt_.op_mode, &a->h)) { perror_("getMatrix"); return false; }
+        int nsets = 0;
+        if (heat_mesh_nodeset_ids(ctx_, &nsets, nullptr)) { perror_("getMatrix"); return false; }
+        std::vector<int64_t> ids((size_t)nsets);
+        if (nsets > 0) heat_mesh_nodeset_ids(ctx_, &nsets, ids.data());
+        for (int64_t id : ids) {
+            int64_t cnt = 0;
+            if (heat_matrix_owned_nodeset(a->h, id, &cnt, nullptr)) { perror_("getMatrix"); return false; }
+            std::vector<int64_t> nodes((size_t)cnt);
+            if (cnt > 0) heat_matrix_owned_nodeset(a->h, id, &cnt, nodes.data());
+            nodeSetMap[(int)id].insert(nodes.begin(), nodes.end());
+        }
+        if (verbose) {
+            heat_matrix_info mi;
+            heat_matrix_get_info(a->h, &mi);
+            std::cout << "Rank #" << mi.rank << ": " << mi.n_owned << " of " << mi.n_global << " rows, " << mi.n_ghost
+                      << " ghost columns, " << mi.nnz_local << " entries" << std::endl;
+        }
+        *ret = a;
         return true;
     }
     // ExodusIO.hpp:1496 — partition with METIS and write the mesh with one element block per partition

@@ -71,6 +71,8 @@ int  heat_mesh_set(heat_ctx *ctx, int64_t num_nodes, int num_dim, const double *
  * materialises coordinates + connectivity on the device and runs the general assembly kernels;
  * 0 uses the analytic-connectivity kernels (needed for 512^3 and for per-GPU slabs).            */
 int  heat_mesh_cube(heat_ctx *ctx, int nx, int ny, int nz, int explicit_mesh);
+/* ex_get_ids(EX_NODE_SET) (ExodusIO.hpp:172): nodeset ids, ascending; ids_out may be NULL        */
+int  heat_mesh_nodeset_ids(const heat_ctx *ctx, int *count, int64_t *ids_out);
 
 /* ---- multi-GPU plumbing (replaces MPI_COMM_WORLD; one process per GPU) ---------------------- */
 #define HEAT_COMM_ID_BYTES 128
@@ -84,6 +86,33 @@ int  heat_comm_rank(const heat_ctx *ctx, int *rank, int *nranks);
  * the device.  Collective over the ranks of heat_comm_init.                                      */
 int  heat_assemble(heat_ctx *ctx, int op_mode, int partitioner, heat_matrix **A, heat_vector **X,
                    heat_vector **B);
+
+/* ---- getMatrix  (IO::getMatrix, ExodusIO.hpp:733-1489) + power method (ExodusMatrixTest.cpp) -- *
+ * The graph Laplacian (or P1 stiffness) of the WHOLE mesh: one row per node, nodesets not applied
+ * (singular, as the reference says at :729-731).  Rows are distributed by ELEMENT partition
+ * (METIS_PartMeshDual, the serial counterpart of ParMETIS_V3_PartMeshKway at :919) followed by the
+ * reference's node-ownership rule (:1191-1295).  Collective; needs a mesh from heat_open/mesh_set. */
+int  heat_get_matrix(heat_ctx *ctx, int op_mode, heat_matrix **A);
+/* the rule alone (pure host): owner[v] = the part in whose elements node v has the most distinct
+ * neighbours, ties to the lowest part; epart[e] in [0, nparts).                                  */
+int  heat_node_owners(int64_t num_nodes, int64_t num_elem, int npe, const int32_t *conn_host,
+                      const int64_t *epart_host, int nparts, int32_t *owner_out);
+/* nodeSetMap of getMatrix (:1447-1466): nodes (0-based) of nodeset `set_id` whose rows this rank
+ * owns, ascending.  nodes_out may be NULL to query *count.                                       */
+int  heat_matrix_owned_nodeset(const heat_matrix *A, int64_t set_id, int64_t *count, int64_t *nodes_out);
+/* PowerMethod::run (ExodusMatrixTest.cpp:56-129): q = z/||z||, z = A q, lambda = q.z; the residual
+ * ||A q - lambda q||_2 is evaluated every 50 iterations and at the last one and compared with
+ * `tolerance`.  The reference starts from an unseeded random vector; here z0 is the counter-based
+ * U(-1,1) vector of heat_vector_fill_hash(seed).  iters = index of the iteration that converged
+ * (the reference's "Converged after <iter> iterations"), or niters.                              */
+typedef struct {
+    double lambda, residual; int iters, converged; double solve_ms;
+    /* optional (in): room for the reports the reference prints every 50 iterations (:103-111);
+     * report k holds {iteration, lambda, residual} in report_buf[3k..3k+2]; (out) report_count      */
+    double *report_buf; int report_capacity, report_count;
+} heat_power_info;
+int  heat_power_method(heat_ctx *ctx, heat_matrix *A, int niters, double tolerance, uint64_t seed,
+                       heat_power_info *info);
 
 /* ---- solve  (belosSolver, BelosMueLuSolver.cpp:87-139) --------------------------------------- *
  * Stops when ||r||_2/||r0||_2 <= tol (status test before each iteration, as Belos) or after

@@ -339,3 +339,34 @@ void oracle_scatter_field(int64_t N, const double *node_bc, int64_t n, const int
     for (int64_t g = 0; g < N; ++g) field[g] = isnan(node_bc[g]) ? 0.0 : node_bc[g];
     for (int64_t i = 0; i < n; ++i) field[red2orig[i]] = x[i];
 }
+
+/* PowerMethod::run, /root/reference/ExodusMatrixTest.cpp:56-129.  z holds the start vector on entry
+ * (the reference: z.randomize()).  Returns the loop index at which it stopped ("Converged after
+ * <iter> iterations", :116) or niters; *converged tells which. */
+int oracle_power_method(int64_t n, const int64_t *rp, const int32_t *col, const double *val, double *z,
+                        int niters, double tolerance, double *lambda_out, double *residual_out,
+                        int *converged) {
+    double *q = (double *)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
+    double lambda = 0.0, normz = 0.0, residual = 0.0;
+    const int reportFrequency = 50;                                   /* :91 */
+    int stopped = niters, conv = 0;
+    for (int iter = 0; iter < niters; ++iter) {
+        normz = sqrt(dot(n, z, z));                                   /* :97 */
+        const double inv = 1.0 / normz;
+#pragma omp parallel for schedule(static)
+        for (int64_t i = 0; i < n; ++i) q[i] = inv * z[i];            /* :98 q := z / normz */
+        oracle_spmv(n, rp, col, val, q, z);                           /* :99 z := A q       */
+        lambda = dot(n, q, z);                                        /* :100               */
+        if (iter % reportFrequency == 0 || iter + 1 == niters) {      /* :103-106           */
+            double s = 0.0;
+#pragma omp parallel for reduction(+ : s) schedule(static)
+            for (int64_t i = 0; i < n; ++i) { const double d = z[i] - lambda * q[i]; s += d * d; }
+            residual = sqrt(s);
+        }
+        if (residual < tolerance) { stopped = iter; conv = 1; break; }   /* :113-118 */
+        else if (iter + 1 == niters) break;                              /* :119-125 */
+    }
+    free(q);
+    *lambda_out = lambda; *residual_out = residual; *converged = conv;
+    return stopped;
+}

@@ -5,6 +5,8 @@
  *   IO::assemble           /root/reference/ExodusIO.hpp:128-723
  *   belosSolver (as CG)    /root/reference/BelosMueLuSolver.cpp:87-139
  *   IO::writeSolution      /root/reference/ExodusIO.hpp:1972-2070  (field scatter only)
+ *   PowerMethod::run       /root/reference/ExodusMatrixTest.cpp:56-129
+ *   (IO::getMatrix's ownership rule, ExodusIO.hpp:1089-1295, is restated in oracle.py)
  *
  * PARITY STATUS: "parity unpinned" against the reference binary.  The reference cannot be
  * compiled here (needs MPI, Trilinos, ParMETIS, SEACAS-Exodus; none present, no network) and
@@ -75,6 +77,11 @@ int oracle_pcg(int64_t n, const int64_t *row_ptr, const int32_t *col, const doub
  * node_bc (lowest-id rule, consistent with the RHS — see D2 in SURVEY.md).                    */
 void oracle_scatter_field(int64_t num_nodes, const double *node_bc, int64_t n,
                           const int64_t *red2orig, const double *x, double *field);
+
+/* PowerMethod::run (ExodusMatrixTest.cpp:56-129): z = start vector in, last A q out.            */
+int oracle_power_method(int64_t n, const int64_t *row_ptr, const int32_t *col, const double *val,
+                        double *z, int niters, double tolerance, double *lambda_out,
+                        double *residual_out, int *converged);
 
 int oracle_num_threads(void);
 

@@ -61,6 +61,8 @@ def lib():
         _lib.oracle_pcg.restype = C.c_int
         _lib.oracle_scatter_field.argtypes = [C.c_int64, dp, C.c_int64, lp, dp, dp]
         _lib.oracle_num_threads.restype = C.c_int
+        _lib.oracle_power_method.argtypes = [C.c_int64, lp, ip, dp, dp, C.c_int, C.c_double, dp, dp, C.POINTER(C.c_int)]
+        _lib.oracle_power_method.restype = C.c_int
     return _lib
 
 
@@ -323,6 +325,81 @@ def scatter_field(sys_: System, x: np.ndarray) -> np.ndarray:
     lib().oracle_scatter_field(N, _p(sys_.node_bc, C.c_double), sys_.n, _p(sys_.red2orig, C.c_int64),
                                _p(x, C.c_double), _p(f, C.c_double))
     return f
+
+
+def power_method(sys_: System, z0: np.ndarray, niters: int = 500, tolerance: float = 1.0e-2):
+    """PowerMethod::run (ExodusMatrixTest.cpp:56-129).  Returns (lambda, residual, stop_iter, converged)."""
+    z = np.array(z0, dtype=np.float64)
+    lam, res, conv = C.c_double(0.0), C.c_double(0.0), C.c_int(0)
+    it = lib().oracle_power_method(sys_.n, _p(sys_.row_ptr, C.c_int64), _p(sys_.col, C.c_int32), _p(sys_.val, C.c_double),
+                                   _p(z, C.c_double), niters, tolerance, C.byref(lam), C.byref(res), C.byref(conv))
+    return lam.value, res.value, int(it), bool(conv.value)
+
+
+def hash_vector(gids, seed: int) -> np.ndarray:
+    """numpy twin of the product's counter-based U(-1,1) vector keyed on the global row id
+    (splitmix64(g ^ 0x9E3779B97F4A7C15*seed))."""
+    M = (1 << 64) - 1
+    out = np.empty(len(gids))
+    for k, g in enumerate(np.asarray(gids, dtype=np.int64).tolist()):
+        z = ((g ^ ((0x9E3779B97F4A7C15 * seed) & M)) + 0x9E3779B97F4A7C15) & M
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & M
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & M
+        z ^= z >> 31
+        out[k] = float(z >> 11) * (1.0 / 9007199254740992.0) * 2.0 - 1.0
+    return out
+
+
+def get_matrix(mesh: Mesh, mode: int = GRAPH_LAPLACIAN) -> System:
+    """The matrix IO::getMatrix ends up with (ExodusIO.hpp:1379-1425): off-diagonals -1 for every
+    pair of nodes sharing an element, diagonal = (entries in the row) - 1; nodesets are NOT applied
+    (:729-731) — i.e. IO::assemble's operator with no Dirichlet node."""
+    return assemble(mesh, mode, node_bc=np.full(mesh.num_nodes, np.nan))
+
+
+def get_matrix_owners(conn: np.ndarray, epart: np.ndarray, nparts: int, num_nodes: int) -> np.ndarray:
+    """Node ownership of IO::getMatrix, restated rank by rank as the reference computes it
+    (ExodusIO.hpp:1080-1295, with std::map/std::set semantics; pure Python — small meshes only):
+      adjacents (:1089-1097), ghostedNodeMap = pairwise intersections of the ranks' node lists
+      (:1113-1135), nodeToFreq (:1163-1168), and the keep/remove decision (:1247-1281): a rank drops a
+      node if another sharer has a higher frequency, or an equal one and a lower rank.
+    Nodes in no element belong to nobody in the reference; they are given to rank 0 here."""
+    conn = np.asarray(conn)
+    adj = [dict() for _ in range(nparts)]                    # rank -> node -> set(neighbours)
+    for e, nodes in enumerate(conn.tolist()):
+        a = adj[int(epart[e])]
+        for j in nodes:
+            for k in nodes:
+                if j != k:
+                    a.setdefault(j, set()).add(k)
+    node_lists = [sorted({int(v) for e in np.flatnonzero(np.asarray(epart) == r) for v in conn[e]}) for r in range(nparts)]
+    freq = []
+    for r in range(nparts):                                   # nodeToFreq[id] = rows of `adjacents` containing id
+        f = {}
+        for row in adj[r].values():
+            for v in row:
+                f[v] = f.get(v, 0) + 1
+        freq.append(f)
+    owner = np.zeros(num_nodes, dtype=np.int32)
+    claimed = np.zeros(num_nodes, dtype=np.int32)
+    sets = [set(l) for l in node_lists]
+    for r in range(nparts):
+        for v in node_lists[r]:
+            mine = freq[r].get(v, 0)
+            keep = True
+            for i in range(nparts):
+                if i == r or v not in sets[i]:
+                    continue
+                theirs = freq[i].get(v, 0)
+                if mine < theirs or (mine == theirs and i < r):
+                    keep = False
+            if keep:
+                owner[v] = r
+                claimed[v] += 1
+    used = np.zeros(num_nodes, dtype=bool)
+    used[np.unique(conn)] = True
+    assert np.all(claimed[used] == 1), "ownership rule must give every used node exactly one owner (map->isOneToOne, :1375)"
+    return owner
 
 
 def num_threads() -> int:

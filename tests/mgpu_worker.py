@@ -48,7 +48,8 @@ def slab_part(ref, nx, ny, nz, P):
     return (np.searchsorted(np.array(bounds), k, side="right") - 1).astype(np.int32)
 
 
-def check_system(io, A, X, B, ref, part, rank, world, tag, log):
+def check_rows(io, A, ref, part, rank, world, tag):
+    """maps, local rows and SpMV-with-halo of this rank against the global oracle system"""
     mi = A.info
     owned, ghost, owner = A.maps()
     plan = hb.plan_build(ref.row_ptr, ref.col, part, world, rank)
@@ -69,7 +70,6 @@ def check_system(io, A, X, B, ref, part, rank, world, tag, log):
     sel = np.concatenate([np.arange(ref.row_ptr[g], ref.row_ptr[g + 1]) for g in owned]) if len(owned) else np.zeros(0, int)
     np.testing.assert_array_equal(l2g[col], ref.col[sel], err_msg=f"{tag}: columns")
     np.testing.assert_array_equal(val, ref.val[sel], err_msg=f"{tag}: values")
-    np.testing.assert_array_equal(B.numpy(), ref.b[owned], err_msg=f"{tag}: rhs")
     np.testing.assert_array_equal(A.red2orig(), ref.red2orig[owned])
     # SpMV with halo exchange: bit-exact
     xv, yv = A.hash_vector(4242), A.new_vector()
@@ -77,6 +77,12 @@ def check_system(io, A, X, B, ref, part, rank, world, tag, log):
     np.testing.assert_array_equal(xv.numpy(), xg[owned], err_msg=f"{tag}: hash vector")
     io.spmv(A, xv, yv)
     np.testing.assert_array_equal(yv.numpy(), O.spmv(ref, xg)[owned], err_msg=f"{tag}: spmv")
+    return owned, ghost, nbr
+
+
+def check_system(io, A, X, B, ref, part, rank, world, tag, log):
+    owned, ghost, nbr = check_rows(io, A, ref, part, rank, world, tag)
+    np.testing.assert_array_equal(B.numpy(), ref.b[owned], err_msg=f"{tag}: rhs")
     # PCG
     x_ref, it_ref, _, _ = O.pcg(ref, tol=1e-10, max_iters=3000)
     for solver in (hb.SOLVER_CG, hb.SOLVER_CG_SINGLE_REDUCE):
@@ -167,6 +173,30 @@ def main():
                         assert nc.dimensions["num_el_blk"] == max(2, world)
                         nc.close()
                 io.close()
+
+    # ---- 3. IO::getMatrix (ExodusIO.hpp:733): element partition + node-ownership rule, whole-mesh
+    #         Laplacian, and the power method of ExodusMatrixTest.cpp on it ----
+    for name, ncommon in (("bolted_bracket", 3), ("mitchell_tri", 2)):
+        path = os.path.join(MESHES, name + ".exo")
+        mesh = O.read_exodus(path)
+        ref = O.get_matrix(mesh)
+        _, epart, _ = O.metis_part_mesh_dual(mesh.conn, mesh.num_nodes, ncommon, world)
+        owners = O.get_matrix_owners(mesh.conn, epart, world, mesh.num_nodes)
+        io = fresh_io()
+        io.open(path, True)
+        A = io.getMatrix()
+        owned, ghost, nbr = check_rows(io, A, ref, owners, rank, world, f"getMatrix {name}")
+        for sid, nodes in mesh.nodesets.items():
+            mine = np.unique(nodes)
+            np.testing.assert_array_equal(A.owned_nodeset(sid), mine[owners[mine] == rank])
+        z0 = O.hash_vector(np.arange(ref.n), 12345)
+        for niters, tol in ((500, 1e-2), (30, 0.0)):
+            lam, res, it, conv = O.power_method(ref, z0, niters, tol)
+            pr = io.power_method(A, niters, tol, 12345)
+            assert (pr.iters, pr.converged) == (it, conv) and abs(pr.lambda_ - lam) <= 1e-10 * abs(lam), (name, pr, lam, it)
+        log.append(f"getMatrix {name}: owned={len(owned)} ghosts={len(ghost)} nbrs={len(nbr)} lambda={pr.lambda_:.12g} (oracle {lam:.12g})")
+        A.free()
+        io.close()
 
     dist.barrier()
     if rank == 0:

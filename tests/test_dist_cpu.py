@@ -17,6 +17,9 @@ import torch.multiprocessing as mp
 from conftest import ROOT, mesh_path
 
 
+GETMATRIX = 2
+
+
 def _worker(rank, world, port, name, partitioner, q):
     try:
         for p in (os.path.join(ROOT, "oracle"), os.path.join(ROOT, "domain-decomposed-pde-solver_b200")):
@@ -25,8 +28,14 @@ def _worker(rank, world, port, name, partitioner, q):
         import oracle as O
         os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
         dist.init_process_group("gloo", rank=rank, world_size=world)
-        ref = O.assemble(O.read_exodus(mesh_path(name)), O.GRAPH_LAPLACIAN)
-        part = hb.partition_rows(ref.row_ptr, ref.col, partitioner, world)
+        mesh = O.read_exodus(mesh_path(name))
+        if partitioner == GETMATRIX:        # IO::getMatrix: whole-mesh Laplacian, rows by element partition + ownership rule
+            ref = O.get_matrix(mesh)
+            _, epart, _ = O.metis_part_mesh_dual(mesh.conn, mesh.num_nodes, {4: 3, 3: 2}[mesh.conn.shape[1]], world)
+            part = hb.node_owners(mesh.conn, mesh.num_nodes, epart, world)
+        else:
+            ref = O.assemble(mesh, O.GRAPH_LAPLACIAN)
+            part = hb.partition_rows(ref.row_ptr, ref.col, partitioner, world)
         pl = hb.plan_build(ref.row_ptr, ref.col, part, world, rank)
         owned, ghost = pl["owned"], pl["ghost"]
         g2l = {int(g): i for i, g in enumerate(np.concatenate([owned, ghost]))}
@@ -67,6 +76,21 @@ def _worker(rank, world, port, name, partitioner, q):
         y = spmv(x)
         np.testing.assert_allclose(y, (ref.csr() @ xg)[owned], rtol=0, atol=1e-12)
         np.testing.assert_array_equal(x[n_own:], xg[ghost])     # ghosts landed in ghost order
+        if partitioner == GETMATRIX:
+            # distributed power method (ExodusMatrixTest.cpp:56-129), 30 iterations, vs the serial oracle
+            z0 = O.hash_vector(np.arange(ref.n), 12345)
+            z = z0[owned].copy()
+            qv = np.zeros(n_own + len(ghost))
+            lam = 0.0
+            for _ in range(30):
+                normz = np.sqrt(allsum(z @ z)[0])
+                qv[:n_own] = z / normz
+                z = spmv(qv)
+                lam = allsum(qv[:n_own] @ z)[0]
+            lam_ref, _, it_ref, _ = O.power_method(ref, z0, 30, 0.0)
+            q.put((rank, 30, it_ref, abs(lam - lam_ref) / abs(lam_ref), None))
+            dist.destroy_process_group()
+            return
         # Chronopoulos-Gear PCG, one all-reduce per iteration
         dinv = 1.0 / ref.csr().diagonal()[owned]
         b = ref.b[owned]
@@ -96,7 +120,8 @@ def _worker(rank, world, port, name, partitioner, q):
         q.put((rank, -1, -1, 1.0, traceback.format_exc()))
 
 
-@pytest.mark.parametrize("name,partitioner", [("bolted_bracket", 1), ("bolted_bracket", 0), ("mitchell_tri", 1)])
+@pytest.mark.parametrize("name,partitioner", [("bolted_bracket", 1), ("bolted_bracket", 0), ("mitchell_tri", 1),
+                                              ("bolted_bracket", GETMATRIX)])
 def test_plan_drives_distributed_pcg_gloo(name, partitioner):
     world = 2
     ctx = mp.get_context("spawn")

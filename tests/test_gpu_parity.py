@@ -384,3 +384,66 @@ def test_cli_driver_end_to_end(hb, oracle, tmp_path):
     assert np.abs(f - (550.0 - 90.0 * xs)).max() < 1e-5
     assert nc.dimensions["num_el_blk"] == 4
     nc.close()
+
+
+@pytest.mark.parametrize("name", ["bolted_bracket", "mitchell_tri", "2blocks", "rectangle-tris"])
+def test_get_matrix_and_power_method(hb, io, oracle, name):
+    """IO::getMatrix + PowerMethod::run (ExodusIO.hpp:733, ExodusMatrixTest.cpp:56-129) on one GPU:
+    the whole-mesh Laplacian bit-exact, lambda within 1e-10 relative, same stop iteration."""
+    mesh = oracle.read_exodus(mesh_path(name))
+    ref = oracle.get_matrix(mesh)
+    io.open(mesh_path(name), True)
+    A = io.getMatrix()
+    rp, col, val = A.csr()
+    assert np.array_equal(rp, ref.row_ptr) and np.array_equal(col, ref.col) and np.array_equal(val, ref.val)
+    np.testing.assert_array_equal(A.red2orig(), np.arange(mesh.num_nodes))
+    for sid, nodes in mesh.nodesets.items():
+        np.testing.assert_array_equal(A.owned_nodeset(sid), np.unique(nodes))
+    np.testing.assert_array_equal(io.nodeset_ids(), sorted(mesh.nodesets))
+    z0 = oracle.hash_vector(np.arange(ref.n), 12345)
+    for niters, tol in ((500, 1e-2), (7, 0.0), (120, 1e-9)):
+        lam, res, it, conv = oracle.power_method(ref, z0, niters, tol)
+        pr = io.power_method(A, niters, tol, 12345)
+        assert (pr.iters, pr.converged) == (it, conv), (pr, it, conv)
+        assert abs(pr.lambda_ - lam) <= 1e-10 * abs(lam), (pr, lam)
+        assert abs(pr.residual - res) <= 1e-6 * max(res, 1e-12) + 1e-9, (pr, res)
+    # P1 stiffness of the whole mesh (Neumann problem): rows sum to ~0
+    if mesh.conn.shape[1] in (3, 4):
+        K = io.getMatrix(hb.OP_P1_FEM)
+        refK = oracle.get_matrix(mesh, oracle.P1_FEM)
+        assert np.array_equal(K.csr()[2], refK.val)
+        K.free()
+    A.free()
+
+
+def test_power_method_full_size_256(hb):
+    """size-independent property at BASELINE configs[2] size: for the P1 operator of the Kuhn cube
+    (h x 7-point stencil) Gershgorin bounds lambda_max by 12 h, and the Rayleigh quotient grows
+    monotonically with the iteration count."""
+    io = hb.IO(0)
+    io.mesh_cube(256, 256, 256)
+    A, X, B = io.assemble(hb.OP_P1_FEM, hb.PART_SLAB)
+    h = 10.0 / 255.0
+    lam = [io.power_method(A, k, 0.0, 3).lambda_ for k in (5, 20, 60)]
+    assert lam[0] < lam[1] < lam[2] <= 12.0 * h * (1 + 1e-12)
+    assert lam[2] > 0.8 * 12.0 * h
+    for v in (X, B):
+        v.free()
+    A.free()
+    io.close()
+
+
+def test_matrix_test_cli(hb, oracle):
+    """bin/heat_matrix_test: the reference's ExodusMatrixTest call order and progress lines."""
+    import re
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "domain-decomposed-pde-solver_b200", "bin", "heat_matrix_test")
+    p = subprocess.run([exe, f"--input={mesh_path('bolted_bracket')}", "--verbose"], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr
+    ref = oracle.get_matrix(oracle.read_exodus(mesh_path("bolted_bracket")))
+    lam, res, it, conv = oracle.power_method(ref, oracle.hash_vector(np.arange(ref.n), 12345), 500, 1e-2)
+    assert f"Converged after {it} iterations" in p.stdout, p.stdout
+    assert "Iteration 0:" in p.stdout and "- ||A*q - lambda*q||_2 = " in p.stdout
+    got = float(re.search(r"Lambda = ([-0-9.e+]+)", p.stdout).group(1))
+    assert abs(got - lam) <= 1e-5 * lam          # printed with 6 significant digits

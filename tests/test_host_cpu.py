@@ -176,6 +176,39 @@ def test_partition_and_plan_bit_exact(hb, oracle, name, P):
         assert total_send == sum(len(hb.plan_build(s.row_ptr, s.col, prt, P, r)["ghost"]) for r in range(P))
 
 
+@pytest.mark.parametrize("name", ["bolted_bracket", "mitchell_tri", "2blocks", "rectangle-tris"])
+@pytest.mark.parametrize("P", [2, 4, 8])
+def test_get_matrix_node_ownership_rule(hb, oracle, name, P):
+    """IO::getMatrix's node ownership (ExodusIO.hpp:1191-1295) from the METIS element partition: the
+    host routine against the rank-by-rank restatement in the oracle."""
+    mesh = oracle.read_exodus(mesh_path(name))
+    if mesh.conn.shape[0] < 2 * P:
+        pytest.skip("fewer elements than 2 x parts")
+    ncommon = {4: 3, 3: 2, 8: 4}[mesh.conn.shape[1]]
+    _, epart, _ = oracle.metis_part_mesh_dual(mesh.conn, mesh.num_nodes, ncommon, P)
+    exp = oracle.get_matrix_owners(mesh.conn, epart, P, mesh.num_nodes)
+    got = hb.node_owners(mesh.conn, mesh.num_nodes, epart, P)
+    np.testing.assert_array_equal(got, exp)
+    # a node touched by ONE part only belongs to that part
+    for v in range(0, mesh.num_nodes, max(1, mesh.num_nodes // 50)):
+        parts = {int(epart[e]) for e in np.flatnonzero((mesh.conn == v).any(1))}
+        if len(parts) == 1:
+            assert got[v] == parts.pop()
+    # the plan built from that ownership covers every row exactly once
+    ref = oracle.get_matrix(mesh)
+    assert sum(len(hb.plan_build(ref.row_ptr, ref.col, got, P, r)["owned"]) for r in range(P)) == mesh.num_nodes
+
+
+def test_node_owners_rejects_bad_input(hb):
+    conn = np.array([[0, 1, 2], [1, 2, 3]], dtype=np.int32)
+    with pytest.raises(hb.HeatError):
+        hb.node_owners(conn, 4, np.array([0, 2]), 2)          # part id out of range
+    with pytest.raises(hb.HeatError):
+        hb.node_owners(conn, 3, np.array([0, 1]), 2)          # node id out of range
+    # tie (node 1 and 2 have 2 neighbours in each part) -> lowest part; unused node 4 -> part 0
+    np.testing.assert_array_equal(hb.node_owners(conn, 5, np.array([1, 0]), 2), [1, 0, 0, 0, 0])
+
+
 def test_single_rank_plan_is_trivial(hb, oracle):
     s = oracle.assemble(oracle.read_exodus(mesh_path("rectangle-tris-boundary")), 0)
     p = hb.plan_build(s.row_ptr, s.col, np.zeros(s.n, dtype=np.int32), 1, 0)
@@ -185,5 +218,12 @@ def test_single_rank_plan_is_trivial(hb, oracle):
 def test_cli_driver_usage(hb):
     import subprocess
     exe = os.path.join(ROOT, "domain-decomposed-pde-solver_b200", "bin", "heat_solver")
+    p = subprocess.run([exe], capture_output=True, text=True)
+    assert p.returncode != 0 and "No input file was provided; use the '--input' parameter!" in p.stderr
+
+
+def test_matrix_test_cli_usage(hb):
+    import subprocess
+    exe = os.path.join(ROOT, "domain-decomposed-pde-solver_b200", "bin", "heat_matrix_test")
     p = subprocess.run([exe], capture_output=True, text=True)
     assert p.returncode != 0 and "No input file was provided; use the '--input' parameter!" in p.stderr

@@ -166,3 +166,34 @@ def test_metis_known_answers(oracle, golden):
         obj, epart, npart = oracle.metis_part_mesh_dual(mm.conn, mm.num_nodes, ncommon, int(nparts))
         assert obj == rec["objval"]
         assert np.bincount(epart, minlength=int(nparts)).tolist() == rec["epart_hist"]
+
+
+def test_get_matrix_is_the_whole_mesh_laplacian(oracle):
+    """IO::getMatrix (ExodusIO.hpp:1379-1425): -1 off-diagonals, diagonal = row entries - 1, nodesets
+    not applied => every row sums to zero (singular, as the reference says at :729-731)."""
+    mesh = oracle.read_exodus(mesh_path("bolted_bracket"))
+    s = oracle.get_matrix(mesh)
+    A = s.csr()
+    assert s.n == mesh.num_nodes and np.array_equal(s.red2orig, np.arange(s.n))
+    assert abs(A - A.T).sum() == 0 and np.abs(np.asarray(A.sum(1))).max() == 0
+    np.testing.assert_array_equal(A.diagonal(), np.diff(s.row_ptr) - 1)
+    assert np.all(s.b == 0)
+
+
+def test_power_method_oracle(oracle):
+    """PowerMethod::run (ExodusMatrixTest.cpp:56-129, 500 iterations / 1e-2 at :163) against scipy's
+    largest eigenvalue; the stop index is a multiple of the report frequency 50."""
+    import scipy.sparse.linalg as spl
+    s = oracle.get_matrix(oracle.read_exodus(mesh_path("bolted_bracket")))
+    z0 = oracle.hash_vector(np.arange(s.n), 12345)
+    lam, res, it, conv = oracle.power_method(s, z0, 500, 1e-2)
+    lmax = spl.eigsh(s.csr(), k=1, which="LA", return_eigenvectors=False)[0]
+    assert conv and it % 50 == 0 and res < 1e-2
+    assert 0 < lmax - lam <= 1e-3 * lmax                      # Rayleigh quotient from below
+    lam2, res2, it2, conv2 = oracle.power_method(s, z0, 7, 0.0)
+    assert (it2, conv2) == (7, False) and lam2 < lam
+
+
+def test_hash_vector_twin(oracle):
+    v = oracle.hash_vector(np.arange(1000), 12345)
+    assert v.min() >= -1 and v.max() < 1 and abs(v.mean()) < 0.1 and len(np.unique(v)) == 1000
