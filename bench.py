@@ -241,7 +241,7 @@ def run_ours(args):
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-            ent = json.load(f).get(f"sell_spmv_tma_kernel|nx={nx}|gpus={world}")
+            ent = json.load(f).get(f"sell_spmv_tma_kernel|nx={nx}|gpus={world}|colbytes={mi.col_index_bytes}")
             traffic = ent["traffic_bytes"] if ent else None
     except OSError:
         pass
@@ -276,8 +276,12 @@ def run_ours(args):
                           f"CPU assembly {t_asm:.1f} s")}
 
     if rank == 0:
+        metric = METRIC
+        if args.workload == "weak" or args.prec != "jacobi" or nx != 512:
+            metric = (f"CG iters/s ({args.prec}-PCG fp64, {nx}x{ny}x{nz}-node P1-tet heat, {n_full / 1e6:.1f}M DOF"
+                      + (", weak scaling 64Mi nodes/GPU" if args.workload == "weak" else "") + ")")
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak" if args.workload == "weak" else "strong",
             "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
@@ -286,11 +290,13 @@ def run_ours(args):
                        "comm": "peer-memory" if mi.nranks > 1 and A.info.peer_path else ("nccl" if mi.nranks > 1 else "none"),
                        "n_dof": n_full, "nnz": nnz_full, "iters_per_step": ips, "solver": args.solver,
                        "l2_policy": "inputs (>=38 GB per iteration sweep) far exceed the 126 MB L2; no flush",
-                       "assemble_ms": mi.assemble_ms, "sell_padding": mi.sell_padded_nnz / max(mi.nnz_local, 1) - 1.0},
+                       "assemble_ms": mi.assemble_ms, "sell_padding": mi.sell_padded_nnz / max(mi.nnz_local, 1) - 1.0,
+                       "spmv_col_index_bytes": mi.col_index_bytes},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 16 * n_own * world, "d2h_bytes_per_step": 8 * n_own * world,
                     "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps, "check_max_abs_x": res_check},
             "gpu_launches": launch_mark["l1"] - launch_mark["l0"],     # counted by the library (heat_kernel_launches), rank 0
-            "roofline": {"bound": "hbm", "kernel": "sell_spmv_tma_kernel (fp64 SELL-64 SpMV, TMA-staged)", "achieved": per_gpu_gbs, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": "sell_spmv_tma_kernel (fp64 SELL-64 SpMV, TMA-staged"
+                                                          + (", byte-indexed columns)" if mi.col_index_bytes == 1 else ")"), "achieved": per_gpu_gbs, "peak": peak,
                          "unit": "GB/s", "frac": per_gpu_gbs / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": spmv_bytes(n_full, nnz_full) / world, "ms_per_launch": ms_spmv,
                          "launches_timed": n_spmv},
@@ -320,7 +326,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--nx", type=int, default=512, help="nodes per cube edge (BASELINE.json configs[3]: 512)")
-    ap.add_argument("--iters-per-step", type=int, default=50)
+    ap.add_argument("--iters-per-step", type=int, default=100,
+                    help="CG iterations per solver call (a 512^3 solve to 1e-10 needs thousands: SURVEY.md Appendix E)")
     ap.add_argument("--solver", default="cg", choices=["cg", "cg1"])
     ap.add_argument("--operator", default="p1", choices=["p1", "graph"])
     ap.add_argument("--workload", default="strong", choices=["strong", "weak"],

@@ -278,6 +278,8 @@ extern "C" int heat_close(heat_ctx *ctx) {
     exo_close(ctx->write_file); ctx->write_file = nullptr;
     comm_destroy(ctx);
     if (ctx->comm_stream) cudaStreamDestroy(ctx->comm_stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
     if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
@@ -444,6 +446,29 @@ extern "C" int heat_solve(heat_ctx *ctx, heat_matrix *A, heat_vector *X, const h
     return solve_device(ctx, A, X->d.p, B->d.p, *opts, info);
 }
 
+// belosSolver's per-iteration output (BelosMueLuSolver.cpp:113-133: io.writeSolution(X, i) after every
+// pass of the loop) inside ONE Krylov run: the device loop is polled every `write_every` iterations and
+// the iterate it holds at that moment is written as the next time step.
+extern "C" int heat_solve_trajectory(heat_ctx *ctx, heat_matrix *A, heat_vector *X, const heat_vector *B,
+                                     const heat_solve_opts *opts, int write_every, int first_timestep,
+                                     heat_solve_info *info, int *frames_written) {
+    if (!ctx || !A || !X || !B || !opts) HEAT_FAIL(2, "heat_solve_trajectory: null argument");
+    if (X->n_owned != A->n_owned || B->n_owned != A->n_owned) HEAT_FAIL(2, "heat_solve_trajectory: vector/matrix size mismatch");
+    if (write_every < 1 || first_timestep < 0) HEAT_FAIL(2, "heat_solve_trajectory: write_every >= 1 and first_timestep >= 0 needed");
+    heat_solve_opts o = *opts;
+    o.check_every = write_every;
+    int frames = 0, last_iters = -1;
+    const std::function<int(int)> hook = [&](int iters_done) -> int {
+        if (iters_done == last_iters) return 0;            // the loop stopped exactly on a poll boundary
+        last_iters = iters_done;
+        return heat_write_solution(ctx, X, first_timestep + frames++);
+    };
+    HEAT_TRY(solve_device(ctx, A, X->d.p, B->d.p, o, info, &hook));
+    if (frames == 0) HEAT_TRY(heat_write_solution(ctx, X, first_timestep + frames++));     // max_iters == 0
+    if (frames_written) *frames_written = frames;
+    return 0;
+}
+
 extern "C" int heat_cg_iterations(heat_ctx *ctx, heat_matrix *A, heat_vector *X, const heat_vector *B,
                                   const heat_solve_opts *opts, int iters, heat_solve_info *info) {
     if (!opts) HEAT_FAIL(2, "heat_cg_iterations: null opts");
@@ -453,18 +478,32 @@ extern "C" int heat_cg_iterations(heat_ctx *ctx, heat_matrix *A, heat_vector *X,
     return heat_solve(ctx, A, X, B, &o, info);
 }
 
+// End-to-end entry point: host buffers in, host buffer out.  The device staging buffers live with the
+// matrix (no cudaMalloc per call); x0 goes up on the compute stream, b on a second stream so that its
+// transfer overlaps the r0 = b - A x0 set-up SpMV (solve_device waits for it right after that SpMV).
 extern "C" int heat_solve_host(heat_ctx *ctx, heat_matrix *A, const double *b_host, double *x_host,
                                const heat_solve_opts *opts, heat_solve_info *info) {
     if (!ctx || !A || !b_host || !x_host || !opts) HEAT_FAIL(2, "heat_solve_host: null argument");
+    HEAT_NEED_GPU(ctx, "heat_solve_host");
     HEAT_CUDA(cudaSetDevice(ctx->device));
     const size_t nv = (size_t)(A->n_owned + A->n_ghost), nb = sizeof(double) * (size_t)A->n_owned;
-    DevBuf<double> x, b;
-    HEAT_TRY(x.alloc(nv)); HEAT_TRY(b.alloc((size_t)A->n_owned));
-    HEAT_CUDA(cudaMemcpyAsync(x.p, x_host, nb, cudaMemcpyHostToDevice, ctx->stream));
-    HEAT_CUDA(cudaMemcpyAsync(b.p, b_host, nb, cudaMemcpyHostToDevice, ctx->stream));
-    int rc = solve_device(ctx, A, x.p, b.p, *opts, info);
+    if (!A->h_x.p) HEAT_TRY(A->h_x.alloc(nv));
+    if (!A->h_b.p) HEAT_TRY(A->h_b.alloc((size_t)A->n_owned));
+    if (!ctx->copy_stream) {
+        HEAT_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        HEAT_CUDA(cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming));
+    }
+    // the previous user of h_b (an earlier solve on ctx->stream) must be done before it is overwritten
+    HEAT_CUDA(cudaEventRecord(ctx->ev_copy, ctx->stream));
+    HEAT_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_copy, 0));
+    HEAT_CUDA(cudaMemcpyAsync(A->h_b.p, b_host, nb, cudaMemcpyHostToDevice, ctx->copy_stream));
+    HEAT_CUDA(cudaEventRecord(ctx->ev_copy, ctx->copy_stream));
+    HEAT_CUDA(cudaMemcpyAsync(A->h_x.p, x_host, nb, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->wait_before_rhs = ctx->ev_copy;
+    int rc = solve_device(ctx, A, A->h_x.p, A->h_b.p, *opts, info);
+    ctx->wait_before_rhs = nullptr;
     if (rc) return rc;
-    HEAT_CUDA(cudaMemcpyAsync(x_host, x.p, nb, cudaMemcpyDeviceToHost, ctx->stream));
+    HEAT_CUDA(cudaMemcpyAsync(x_host, A->h_x.p, nb, cudaMemcpyDeviceToHost, ctx->stream));
     HEAT_CUDA(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
@@ -492,6 +531,7 @@ extern "C" int heat_matrix_get_info(const heat_matrix *A, heat_matrix_info *info
     info->n_boundary_slices = A->n_bnd_slices; info->n_slices = A->n_slices;
     info->assemble_ms = A->assemble_ms;
     info->peer_path = A->peer ? 1 : 0;
+    info->col_index_bytes = A->sell_idx8.p ? 1 : 4;
     return 0;
 }
 

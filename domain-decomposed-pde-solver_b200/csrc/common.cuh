@@ -80,6 +80,7 @@ struct DevBuf {
 
 constexpr int kSellRowsPerLane = 2;                      // R
 constexpr int kSellChunk = 32 * kSellRowsPerLane;        // C: rows per SELL slice (one warp)
+constexpr int kSellDictCap = 64;                         // most distinct col-row offsets a slice may have to be byte-indexed
 constexpr int kMaxPartials = 4096;                       // per-launch block partials capacity
 
 // scalar slots of the CG state (device doubles)
@@ -130,6 +131,11 @@ struct heat_matrix {
     heat::DevBuf<int64_t> slice_ptr;     // [n_slices+1] entry offsets
     heat::DevBuf<int32_t> sell_col;
     heat::DevBuf<double> sell_val;
+    // byte-indexed column stream (built when EVERY slice has <= kSellDictCap distinct col-row offsets):
+    // col = row + sell_tab[slice][sell_idx8[entry]]; 1 byte per entry instead of 4
+    heat::DevBuf<uint8_t> sell_idx8;
+    heat::DevBuf<int32_t> sell_tab;
+    int sell_tpad = 0;
     heat::DevBuf<int32_t> slices_interior, slices_boundary;   // slice id lists (multi-GPU overlap)
     heat::DevBuf<int32_t> slices_all;                         // interior list followed by boundary list
     int64_t n_int_slices = 0, n_bnd_slices = 0;
@@ -144,6 +150,7 @@ struct heat_matrix {
     HaloPlan halo;
     // solver workspace (lazily allocated)
     heat::DevBuf<double> w_r, w_p, w_p2, w_ap, w_s, w_u, w_t, w_w;
+    heat::DevBuf<double> h_x, h_b;       // staging of heat_solve_host (x with ghosts, b)
     PeerMatrixState *peer = nullptr;     // non-null once the peer-memory halo path is set up
     heat::DevBuf<double> partials;       // [2 * kMaxPartials * 4]
     heat::DevBuf<double> scal;           // [S_COUNT]
@@ -171,6 +178,9 @@ struct heat_ctx {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     cudaStream_t comm_stream = nullptr;
+    cudaStream_t copy_stream = nullptr;  // heat_solve_host: b goes up beside the set-up SpMV
+    cudaEvent_t ev_copy = nullptr;
+    cudaEvent_t wait_before_rhs = nullptr;   // if set, solve_device waits for it before it first reads b
     cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_halo = nullptr, ev_pack = nullptr;
     int rank = 0, nranks = 1;
     void *nccl_comm = nullptr;           // ncclComm_t

@@ -290,13 +290,19 @@ int nc_read(const std::string &path, NcFile &out) {
     return 0;
 }
 
-int nc_write(const std::string &path, const NcFile &f) {
-    // always CDF-2 (64-bit offset), like every file under the reference's data/
+// file layout of a CDF-2 image of `f`: header bytes, fixed-size variables, then the record section
+namespace {
+struct NcLayout {
+    std::vector<int64_t> vsize, begin;
+    int64_t rec_start = 0, recsize = 0;
+    std::vector<uint8_t> header;
+};
+void nc_layout(const NcFile &f, NcLayout &L) {
     auto padded = [](int64_t b) { return (b + 3) & ~(int64_t)3; };
-    std::vector<int64_t> vsize(f.vars.size()), begin(f.vars.size());
+    L.vsize.assign(f.vars.size(), 0); L.begin.assign(f.vars.size(), 0);
     int nrecvars = 0;
     for (size_t i = 0; i < f.vars.size(); ++i) {
-        vsize[i] = padded(f.var_elems_per_record(f.vars[i]) * nc_type_size(f.vars[i].type));
+        L.vsize[i] = padded(f.var_elems_per_record(f.vars[i]) * nc_type_size(f.vars[i].type));
         nrecvars += f.vars[i].is_record;
     }
     auto header = [&](Writer &w) {
@@ -318,37 +324,43 @@ int nc_write(const std::string &path, const NcFile &f) {
                 for (int id : v.dimids) w.u32((uint32_t)id);
                 write_atts(w, v.atts);
                 w.u32((uint32_t)v.type);
-                w.u32((uint32_t)(vsize[i] > 0xFFFFFFFFll ? 0xFFFFFFFFu : (uint32_t)vsize[i]));
-                w.u64((uint64_t)begin[i]);
+                w.u32((uint32_t)(L.vsize[i] > 0xFFFFFFFFll ? 0xFFFFFFFFu : (uint32_t)L.vsize[i]));
+                w.u64((uint64_t)L.begin[i]);
             }
         }
     };
     Writer probe;
-    std::fill(begin.begin(), begin.end(), 0);
-    header(probe);
+    header(probe);                                       // offsets are fixed-width: size is final
     int64_t off = (int64_t)probe.b.size();
     for (size_t i = 0; i < f.vars.size(); ++i)
-        if (!f.vars[i].is_record) { begin[i] = off; off += vsize[i]; }
-    int64_t recsize = 0;
-    const int64_t rec_start = off;
+        if (!f.vars[i].is_record) { L.begin[i] = off; off += L.vsize[i]; }
+    L.rec_start = off; L.recsize = 0;
     for (size_t i = 0; i < f.vars.size(); ++i)
-        if (f.vars[i].is_record) { begin[i] = off; off += vsize[i]; recsize += vsize[i]; }
-    if (nrecvars == 1)
+        if (f.vars[i].is_record) { L.begin[i] = off; off += L.vsize[i]; L.recsize += L.vsize[i]; }
+    if (nrecvars == 1)                                   // a lone record variable is not padded
         for (size_t i = 0; i < f.vars.size(); ++i)
-            if (f.vars[i].is_record) recsize = f.var_elems_per_record(f.vars[i]) * nc_type_size(f.vars[i].type);
+            if (f.vars[i].is_record) L.recsize = f.var_elems_per_record(f.vars[i]) * nc_type_size(f.vars[i].type);
     Writer w;
     header(w);
-    std::vector<uint8_t> &b = w.b;
-    b.resize((size_t)(rec_start + recsize * f.numrecs), 0);
+    L.header.swap(w.b);
+}
+}  // namespace
+
+int nc_write(const std::string &path, const NcFile &f) {
+    // always CDF-2 (64-bit offset), like every file under the reference's data/
+    NcLayout L;
+    nc_layout(f, L);
+    std::vector<uint8_t> b(L.header);
+    b.resize((size_t)(L.rec_start + L.recsize * f.numrecs), 0);
     for (size_t i = 0; i < f.vars.size(); ++i) {
         const NcVar &v = f.vars[i];
         const int64_t per = f.var_elems_per_record(v) * nc_type_size(v.type);
         if (!v.is_record) {
-            memcpy(b.data() + begin[i], v.raw.data(), std::min<size_t>(v.raw.size(), (size_t)per));
+            memcpy(b.data() + L.begin[i], v.raw.data(), std::min<size_t>(v.raw.size(), (size_t)per));
         } else {
             for (int64_t r = 0; r < f.numrecs; ++r) {
                 if ((size_t)((r + 1) * per) > v.raw.size()) break;
-                memcpy(b.data() + begin[i] + r * recsize, v.raw.data() + r * per, (size_t)per);
+                memcpy(b.data() + L.begin[i] + r * L.recsize, v.raw.data() + r * per, (size_t)per);
             }
         }
     }
@@ -357,6 +369,32 @@ int nc_write(const std::string &path, const NcFile &f) {
     size_t put = fwrite(b.data(), 1, b.size(), fp);
     fclose(fp);
     if (put != b.size()) HEAT_FAIL(64, "short write on '%s'", path.c_str());
+    return 0;
+}
+
+// Rewrites records [r0, r1) of every record variable and the record count IN PLACE.  The file on disk
+// must have been written by nc_write() from the same dimension / variable set (the header has the same
+// size and offsets; only numrecs changes), which is what a sequence of ex_put_var calls amounts to.
+int nc_update_records(const std::string &path, const NcFile &f, int64_t r0, int64_t r1) {
+    NcLayout L;
+    nc_layout(f, L);
+    FILE *fp = fopen(path.c_str(), "r+b");
+    if (!fp) HEAT_FAIL(64, "ex_put_var: cannot reopen '%s'", path.c_str());
+    bool ok = fseek(fp, 0, SEEK_SET) == 0 && fwrite(L.header.data(), 1, 8, fp) == 8;      // magic + numrecs
+    std::vector<uint8_t> rec((size_t)L.recsize);
+    for (int64_t r = r0; ok && r < r1 && r < f.numrecs; ++r) {
+        std::fill(rec.begin(), rec.end(), 0);
+        for (size_t i = 0; i < f.vars.size(); ++i) {
+            const NcVar &v = f.vars[i];
+            if (!v.is_record) continue;
+            const int64_t per = f.var_elems_per_record(v) * nc_type_size(v.type);
+            if ((size_t)((r + 1) * per) <= v.raw.size())
+                memcpy(rec.data() + (L.begin[i] - L.rec_start), v.raw.data() + r * per, (size_t)per);
+        }
+        ok = fseek(fp, (long)(L.rec_start + r * L.recsize), SEEK_SET) == 0 && fwrite(rec.data(), 1, rec.size(), fp) == rec.size();
+    }
+    fclose(fp);
+    if (!ok) HEAT_FAIL(64, "short write on '%s'", path.c_str());
     return 0;
 }
 
@@ -606,7 +644,9 @@ extern "C" int heat_write_solution(heat_ctx *ctx, const heat_vector *X, int time
     NcFile &nc = wf.nc;
     if (nc.dim_id("num_nodes") < 0) HEAT_FAIL(4, "heat_write_solution: output mesh not written (call heat_decompose)");
     const int64_t N = m.num_nodes;
+    bool layout_changed = false;
     if (!ctx->printed_time_zero) {                              // :2034-2040
+        layout_changed = true;
         nc.add_dim("num_nod_var", 1);
         if (nc.dim_id("len_name") < 0) nc.add_dim("len_name", 33);
         const int64_t len_name = nc.dim_len("len_name", 33);
@@ -635,5 +675,8 @@ extern "C" int heat_write_solution(heat_ctx *ctx, const heat_vector *X, int time
     swap_copy(tw->raw.data() + (step - 1) * 8, &t, 1, 8);
     swap_copy(vv->raw.data() + (step - 1) * N * 8, field.data(), (size_t)N, 8);
     wf.steps_written = nc.numrecs;
-    return nc_write(wf.path, nc);
+    // the first result call lays the file out again (new dimension + variables: ex_put_variable_param);
+    // later calls only touch the record they write, like ex_put_var (:2056)
+    if (layout_changed) return nc_write(wf.path, nc);
+    return nc_update_records(wf.path, nc, step - 1, step);
 }

@@ -55,6 +55,7 @@ int nc_type_size(int type);
 // 0 on success; message via heat::set_error
 int nc_read(const std::string &path, NcFile &out);
 int nc_write(const std::string &path, const NcFile &f);
+int nc_update_records(const std::string &path, const NcFile &f, int64_t r0, int64_t r1);   // in place, same layout
 
 struct ExoFile {
     std::string path;

@@ -22,6 +22,12 @@ struct DotOut {               // where a fused dot product is reduced to
     bool with_yy = false;     // SpMV only: also reduce sum_i y_i^2 into out[1]
 };
 
+struct SellDict {             // byte-indexed column stream of the SELL matrix (sell.cu); idx8 == nullptr: not built
+    const uint8_t *idx8;      // [sell_padded] index into the slice's offset table
+    const int32_t *tab;       // [n_slices][tpad] distinct (col - row) offsets of each slice
+    int tpad;                 // table stride, a multiple of 4 entries (16 bytes: one TMA granule)
+};
+
 struct SpmvPeer {             // peer-memory mode of the SpMV (single launch over interior+boundary slices)
     bool on = false;
     int64_t n_interior = 0;   // leading entries of the slice list that never touch a ghost column

@@ -1,6 +1,8 @@
 // sell.cu — local CSR -> SELL-C (C = 64, 2 rows per lane) conversion, diagonal extraction and the
 // interior / boundary slice split used to overlap the halo exchange with the interior SpMV.
 // (Role of Tpetra::CrsMatrix::fillComplete's local-matrix + Import set-up, ExodusIO.hpp:609.)
+#include <cstdlib>
+
 #include <cub/cub.cuh>
 
 #include "device_utils.cuh"
@@ -23,7 +25,9 @@ __global__ void sell_width_kernel(const int64_t *__restrict__ row_ptr, int64_t n
     slice_entries[s] = w * kSellChunk;
 }
 
-// one warp per slice: lane owns rows 2*lane, 2*lane+1; padding = (value 0, column = own row)
+// one warp per slice: lane owns rows 2*lane, 2*lane+1; padding = (value 0, column = own row).  Rows past
+// the end of the matrix (tail of the last slice) point 64 rows back — a valid column at a CONSTANT
+// col-row offset, so the tail does not add 60 distinct offsets to the last slice's table (sell_dict_kernel)
 __global__ void __launch_bounds__(kBlock)
 sell_fill_kernel(const int64_t *__restrict__ row_ptr, const int32_t *__restrict__ col,
                  const double *__restrict__ val, int64_t n_rows, int64_t n_owned_cols, int64_t n_slices,
@@ -38,7 +42,8 @@ sell_fill_kernel(const int64_t *__restrict__ row_ptr, const int32_t *__restrict_
     int64_t b0 = 0, l0 = 0, b1 = 0, l1 = 0;
     if (row0 < n_rows) { b0 = row_ptr[row0]; l0 = row_ptr[row0 + 1] - b0; }
     if (row1 < n_rows) { b1 = row_ptr[row1]; l1 = row_ptr[row1 + 1] - b1; }
-    const int32_t pad0 = row0 < n_rows ? (int32_t)row0 : 0, pad1 = row1 < n_rows ? (int32_t)row1 : 0;
+    const int32_t pad0 = row0 < n_rows ? (int32_t)row0 : (row0 >= kSellChunk ? (int32_t)(row0 - kSellChunk) : 0);
+    const int32_t pad1 = row1 < n_rows ? (int32_t)row1 : (row1 >= kSellChunk ? (int32_t)(row1 - kSellChunk) : 0);
     int ghost = 0;
     for (int k = 0; k < w; ++k) {
         int32_t c0 = pad0, c1 = pad1;
@@ -52,6 +57,91 @@ sell_fill_kernel(const int64_t *__restrict__ row_ptr, const int32_t *__restrict_
     }
     ghost = __any_sync(0xffffffffu, ghost);
     if (lane == 0 && slice_is_boundary) slice_is_boundary[s] = ghost;
+}
+
+// Byte-indexed column stream.  One warp per slice collects the distinct (col - row) offsets of the
+// slice's 64 x w entries (first-seen order: k ascending, then lane, then the lane's first row) in a
+// shared-memory table.  On a structured mesh a slice has as many distinct offsets as the stencil has
+// directions (15 on the Kuhn cube, a few more where ghost columns start), so the 4-byte column id of
+// every entry shrinks to a 1-byte table index: 12 -> 9 bytes per stored entry in the SpMV stream.
+// WRITE == false only measures the table length of every slice (the matrix is byte-indexed only if ALL
+// slices fit kSellDictCap); WRITE == true stores indices and tables (stride tpad).
+template <bool WRITE>
+__global__ void __launch_bounds__(kBlock)
+sell_dict_kernel(const int64_t *__restrict__ slice_ptr, const int32_t *__restrict__ scol, int64_t n_slices,
+                 int tpad, uint8_t *__restrict__ idx8, int32_t *__restrict__ tabs, int *__restrict__ max_len) {
+    __shared__ int32_t tab_s[kWarpsPerBlock][kSellDictCap];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t s = (int64_t)blockIdx.x * kWarpsPerBlock + warp;
+    if (s >= n_slices) return;
+    int32_t *tab = tab_s[warp];
+    const int64_t base = slice_ptr[s];
+    const int w = (int)((slice_ptr[s + 1] - base) >> 6);
+    const int row0 = (int)(s * kSellChunk) + 2 * lane;
+    int T = 0;                                         // warp-uniform table length
+    bool overflow = false;
+    for (int k = 0; k < w && !overflow; ++k) {
+        const int2 c = *reinterpret_cast<const int2 *>(scol + base + (int64_t)k * kSellChunk + 2 * lane);
+        const int off[2] = {c.x - row0, c.y - (row0 + 1)};
+        int id[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            int found = -1;
+            for (int t = 0; t < T; ++t)
+                if (tab[t] == off[h]) { found = t; break; }
+            unsigned miss = __ballot_sync(0xffffffffu, found < 0);
+            while (miss && !overflow) {
+                const int v = __shfl_sync(0xffffffffu, off[h], __ffs(miss) - 1);
+                if (T >= kSellDictCap) { overflow = true; break; }
+                if (lane == 0) tab[T] = v;
+                __syncwarp();
+                if (found < 0 && off[h] == v) found = T;
+                ++T;
+                miss = __ballot_sync(0xffffffffu, found < 0);
+            }
+            id[h] = found;
+        }
+        if (WRITE && !overflow)
+            *reinterpret_cast<uchar2 *>(idx8 + base + (int64_t)k * kSellChunk + 2 * lane) =
+                make_uchar2((unsigned char)id[0], (unsigned char)id[1]);
+    }
+    if (overflow) T = kSellDictCap + 1;
+    if (!WRITE) {
+        if (lane == 0) atomicMax(max_len, T);
+    } else {
+        __syncwarp();
+        for (int t = lane; t < tpad; t += 32) tabs[s * tpad + t] = t < T ? tab[t] : 0;
+    }
+}
+
+static bool want_byte_index() {
+    const char *e = getenv("HEAT_SPMV_CIDX");          // 0: keep int32 columns only
+    return !(e && atoi(e) == 0);
+}
+
+// builds A->sell_idx8 / sell_tab when every slice qualifies; leaves them empty otherwise
+static int sell_build_dict(heat_matrix *A, cudaStream_t st) {
+    const int64_t ns = A->n_slices;
+    A->sell_tpad = 0;
+    A->sell_idx8.release(); A->sell_tab.release();
+    if (ns == 0 || A->sell_padded == 0 || !want_byte_index()) return 0;
+    DevBuf<int> d_max;
+    HEAT_TRY(d_max.alloc(1));
+    HEAT_CUDA(cudaMemsetAsync(d_max.p, 0, sizeof(int), st));
+    const unsigned grid = (unsigned)((ns + kWarpsPerBlock - 1) / kWarpsPerBlock);
+    sell_dict_kernel<false><<<grid, kBlock, 0, st>>>(A->slice_ptr.p, A->sell_col.p, ns, 0, nullptr, nullptr, d_max.p);
+    HEAT_LAUNCHED();
+    int h_max = 0;
+    HEAT_CUDA(cudaMemcpyAsync(&h_max, d_max.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    HEAT_CUDA(cudaStreamSynchronize(st));
+    if (h_max > kSellDictCap) return 0;                // some slice has too many distinct offsets: int32 columns
+    const int tpad = h_max < 4 ? 4 : (h_max + 3) & ~3; // 16-byte granules for the TMA copy of a table
+    HEAT_TRY(A->sell_idx8.alloc((size_t)A->sell_padded));
+    HEAT_TRY(A->sell_tab.alloc((size_t)ns * (size_t)tpad));
+    sell_dict_kernel<true><<<grid, kBlock, 0, st>>>(A->slice_ptr.p, A->sell_col.p, ns, tpad, A->sell_idx8.p, A->sell_tab.p, nullptr);
+    HEAT_LAUNCHED();
+    A->sell_tpad = tpad;
+    return 0;
 }
 
 __global__ void extract_diag_kernel(const int64_t *__restrict__ row_ptr, const int32_t *__restrict__ col,
@@ -131,6 +221,7 @@ int sell_from_csr(heat_matrix *A, cudaStream_t st) {
             HEAT_CUDA(cudaStreamSynchronize(st));
         }
     }
+    HEAT_TRY(sell_build_dict(A, st));
     HEAT_TRY(launch_extract_diag(A, st));
     return 0;
 }

@@ -172,7 +172,7 @@ int power_method_device(heat_ctx *ctx, heat_matrix *A, int niters, double tol, u
 }
 
 int solve_device(heat_ctx *ctx, heat_matrix *A, double *x, const double *b, const heat_solve_opts &o,
-                 heat_solve_info *info) {
+                 heat_solve_info *info, const std::function<int(int)> *on_poll) {
     HEAT_CUDA(cudaSetDevice(ctx->device));
     const bool single = o.solver == HEAT_SOLVER_CG_SINGLE_REDUCE;
     const bool cheb = o.prec == HEAT_PREC_CHEBYSHEV;
@@ -218,6 +218,7 @@ int solve_device(heat_ctx *ctx, heat_matrix *A, double *x, const double *b, cons
     HEAT_CUDA(cudaEventRecord(ctx->ev_a, st));
     // ---- r0 = b - A x0 ; z0 ; p0 (or u0, w0) ; H[0] ----
     HEAT_TRY(spmv_halo(ctx, A, x, ap, nogate, nullptr));
+    if (ctx->wait_before_rhs) HEAT_CUDA(cudaStreamWaitEvent(st, ctx->wait_before_rhs, 0));   // b still in flight (heat_solve_host)
     if (single) {
         double *u = A->w_u.p, *s = A->w_s.p, *w = ap;
         HEAT_TRY(launch_cg_init(n, b, ap, dinv, r, u, H, A->partials.p, I + I_COUNTER2, vgrid, st));
@@ -294,6 +295,7 @@ int solve_device(heat_ctx *ctx, heat_matrix *A, double *x, const double *b, cons
         HEAT_CUDA(cudaMemcpyAsync(hI, I, sizeof(int) * 2, cudaMemcpyDeviceToHost, st));
         HEAT_CUDA(cudaStreamSynchronize(st));
         h_iters = hI[I_ITERS]; h_status = hI[I_STATUS];
+        if (on_poll && h_status == 0) HEAT_TRY((*on_poll)(h_iters));      // x holds iterate h_iters (trajectory output)
         if (h_iters < launched) break;              // the stopping test fired (or breakdown): frozen
     }
     HEAT_CUDA(cudaEventRecord(ctx->ev_b, st));

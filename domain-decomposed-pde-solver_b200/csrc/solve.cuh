@@ -1,5 +1,7 @@
 // solve.cuh — host drivers (definitions in solve.cu).
 #pragma once
+#include <functional>
+
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -8,6 +10,8 @@ int sm_count(int device);
 int spmv_halo(heat_ctx *ctx, heat_matrix *A, double *x, double *y, CgGate gate, double *dot_out, bool with_yy = false);
 int power_method_device(heat_ctx *ctx, heat_matrix *A, int niters, double tol, uint64_t seed, heat_power_info *info);
 int ensure_workspace(heat_matrix *A, bool single_reduce, bool cheb);
+// on_poll (optional) is called with the iteration count after every host poll (every check_every
+// iterations and when the stopping test fired), while x holds exactly that iterate
 int solve_device(heat_ctx *ctx, heat_matrix *A, double *x, const double *b, const heat_solve_opts &o,
-                 heat_solve_info *info);
+                 heat_solve_info *info, const std::function<int(int)> *on_poll = nullptr);
 }  // namespace heat

@@ -121,26 +121,31 @@ __device__ __forceinline__ uint64_t l2_evict_first_policy() {
     return p;
 }
 
-template <int KC, int NSTAGE>
+// C8: the column stream is one byte per entry (index into the slice's table of distinct col-row
+// offsets, sell.cu) instead of an int32; each warp also keeps NSTAGE table buffers (the issue cursor
+// runs at most NSTAGE chunks, hence at most NSTAGE slices, ahead of the consume cursor).
+template <int KC, int NSTAGE, bool C8 = false>
 struct TmaSmem {
     static constexpr int kValBytes = KC * kSellChunk * 8;
-    static constexpr int kColBytes = KC * kSellChunk * 4;
+    static constexpr int kColBytes = KC * kSellChunk * (C8 ? 1 : 4);
     static constexpr int kStageBytes = kValBytes + kColBytes;
-    static constexpr int kWarpBytes = NSTAGE * kStageBytes;
+    static constexpr int kTabBytes = C8 ? kSellDictCap * 4 : 0;
+    static constexpr int kWarpBytes = NSTAGE * (kStageBytes + kTabBytes);
     static constexpr size_t total(int nwarps) { return (size_t)nwarps * kWarpBytes + (size_t)nwarps * NSTAGE * 8; }
 };
 
-template <int DOT, int KC, int NSTAGE, int NWARPS, bool PEER = false>
+template <int DOT, int KC, int NSTAGE, int NWARPS, bool PEER = false, bool C8 = false>
 __global__ void __launch_bounds__(NWARPS * 32, (NWARPS <= 8 && KC <= 8) ? 2 : 1)
 sell_spmv_tma_kernel(const int64_t *__restrict__ slice_ptr, const int32_t *__restrict__ col,
                      const double *__restrict__ val, const double *__restrict__ x, double *__restrict__ y,
                      int64_t n_rows, const int32_t *__restrict__ slice_list, int64_t n_list, CgGate gate,
-                     DotOut dot, SpmvPeer peer) {
+                     DotOut dot, SpmvPeer peer, SellDict dict) {
     if (gate_done(gate)) return;
-    using L = TmaSmem<KC, NSTAGE>;
+    using L = TmaSmem<KC, NSTAGE, C8>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char *my = smem_raw + (size_t)warp * L::kWarpBytes;
+    unsigned char *my_tabs = my + NSTAGE * L::kStageBytes;           // C8: NSTAGE offset tables of this warp
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)NWARPS * L::kWarpBytes) + warp * NSTAGE;
     if (lane == 0) {
 #pragma unroll
@@ -168,24 +173,30 @@ sell_spmv_tma_kernel(const int64_t *__restrict__ slice_ptr, const int32_t *__res
 
     // issue cursor (runs NSTAGE chunks ahead of the consume cursor)
     int64_t ti = first;
-    int ki = 0;
+    int ki = 0, si = 0;                                              // si: ordinal of the slice being issued
     Meta mi = load_meta(ti), mi_next = load_meta(ti + W);
     auto issue = [&](int stage) {
         const int kc = (mi.w - ki) < KC ? (mi.w - ki) : KC;
         if (lane == 0) {
             if (kc > 0) {
                 unsigned char *dst = my + stage * L::kStageBytes;
-                const uint32_t vb = (uint32_t)kc * kSellChunk * 8, cb = (uint32_t)kc * kSellChunk * 4;
-                mbar_arrive_expect_tx(bars + stage, vb + cb);
+                const uint32_t vb = (uint32_t)kc * kSellChunk * 8, cb = (uint32_t)kc * kSellChunk * (C8 ? 1 : 4);
+                const uint32_t tb = (C8 && ki == 0) ? (uint32_t)dict.tpad * 4 : 0;   // first chunk brings the table
+                mbar_arrive_expect_tx(bars + stage, vb + cb + tb);
                 tma_load_1d(dst, val + mi.base + (int64_t)ki * kSellChunk, vb, bars + stage, policy);
-                tma_load_1d(dst + L::kValBytes, col + mi.base + (int64_t)ki * kSellChunk, cb, bars + stage, policy);
+                if (C8) {
+                    tma_load_1d(dst + L::kValBytes, dict.idx8 + mi.base + (int64_t)ki * kSellChunk, cb, bars + stage, policy);
+                    if (tb) tma_load_1d(my_tabs + (si % NSTAGE) * L::kTabBytes, dict.tab + mi.s * dict.tpad, tb, bars + stage, policy);
+                } else {
+                    tma_load_1d(dst + L::kValBytes, col + mi.base + (int64_t)ki * kSellChunk, cb, bars + stage, policy);
+                }
             } else {
                 mbar_arrive(bars + stage);                              // empty slice: complete the phase
             }
         }
         ki += KC;
         if (ki >= mi.w) {
-            ti += W; ki = 0;
+            ti += W; ki = 0; ++si;
             mi = mi_next;
             mi_next = load_meta(ti + W);
         }
@@ -196,7 +207,7 @@ sell_spmv_tma_kernel(const int64_t *__restrict__ slice_ptr, const int32_t *__res
 
     // consume cursor
     int64_t tc = first;
-    int kc0 = 0;
+    int kc0 = 0, sc = 0;                                             // sc: ordinal of the slice being consumed
     Meta mc = load_meta(tc), mc_next = load_meta(tc + W);
     int stage = 0;
     uint32_t parity = 0;
@@ -207,6 +218,17 @@ sell_spmv_tma_kernel(const int64_t *__restrict__ slice_ptr, const int32_t *__res
         const int kc = (mc.w - kc0) < KC ? (mc.w - kc0) : KC;
         const double *vs = reinterpret_cast<const double *>(my + stage * L::kStageBytes) + 2 * lane;
         const int32_t *cs = reinterpret_cast<const int32_t *>(my + stage * L::kStageBytes + L::kValBytes) + 2 * lane;
+        const unsigned char *is = my + stage * L::kStageBytes + L::kValBytes + 2 * lane;
+        const int32_t *tb = reinterpret_cast<const int32_t *>(my_tabs + (sc % NSTAGE) * L::kTabBytes);
+        const int row0 = (int)(mc.s * kSellChunk) + 2 * lane;
+        // the two column ids of this lane at entry k of the staged chunk
+        auto cols_at = [&](int k) -> int2 {
+            if (C8) {
+                const uchar2 ix = *reinterpret_cast<const uchar2 *>(is + k * kSellChunk);
+                return make_int2(row0 + tb[ix.x], row0 + 1 + tb[ix.y]);
+            }
+            return *reinterpret_cast<const int2 *>(cs + k * kSellChunk);
+        };
         if (PEER && tc >= peer.n_interior) {
             // boundary slice: its ghost columns are written by the neighbours' GPUs (peer stores).
             // Wait once per warp for their epoch flags, then gather through L2 (coherent), not L1.
@@ -218,7 +240,7 @@ sell_spmv_tma_kernel(const int64_t *__restrict__ slice_ptr, const int32_t *__res
 #pragma unroll 4
             for (int k = 0; k < kc; ++k) {
                 const double2 v = *reinterpret_cast<const double2 *>(vs + k * kSellChunk);
-                const int2 c = *reinterpret_cast<const int2 *>(cs + k * kSellChunk);
+                const int2 c = cols_at(k);
                 acc0 = fma(v.x, __ldcg(x + c.x), acc0);
                 acc1 = fma(v.y, __ldcg(x + c.y), acc1);
             }
@@ -226,7 +248,7 @@ sell_spmv_tma_kernel(const int64_t *__restrict__ slice_ptr, const int32_t *__res
 #pragma unroll
             for (int k = 0; k < KC; ++k) {
                 const double2 v = *reinterpret_cast<const double2 *>(vs + k * kSellChunk);
-                const int2 c = *reinterpret_cast<const int2 *>(cs + k * kSellChunk);
+                const int2 c = cols_at(k);
                 acc0 = fma(v.x, __ldg(x + c.x), acc0);
                 acc1 = fma(v.y, __ldg(x + c.y), acc1);
             }
@@ -234,7 +256,7 @@ sell_spmv_tma_kernel(const int64_t *__restrict__ slice_ptr, const int32_t *__res
 #pragma unroll 4
             for (int k = 0; k < kc; ++k) {
                 const double2 v = *reinterpret_cast<const double2 *>(vs + k * kSellChunk);
-                const int2 c = *reinterpret_cast<const int2 *>(cs + k * kSellChunk);
+                const int2 c = cols_at(k);
                 acc0 = fma(v.x, __ldg(x + c.x), acc0);
                 acc1 = fma(v.y, __ldg(x + c.y), acc1);
             }
@@ -254,7 +276,7 @@ sell_spmv_tma_kernel(const int64_t *__restrict__ slice_ptr, const int32_t *__res
                 if (DOT == 2) ysum += acc0 * acc0;
             }
             acc0 = 0.0; acc1 = 0.0;
-            tc += W; kc0 = 0;
+            tc += W; kc0 = 0; ++sc;
             mc = mc_next;
             mc_next = load_meta(tc + W);
         }
@@ -305,18 +327,20 @@ int spmv_grid(int64_t n_list, int sm_count) {
     return grid_for(blocks, sm_count, v == 5 ? 2 : 1);    // persistent: one (or two) CTA per SM
 }
 
-template <int DOT, int KC, int NSTAGE, int NWARPS>
+static SellDict dict_of(const heat_matrix *A) { return SellDict{A->sell_idx8.p, A->sell_tab.p, A->sell_tpad}; }
+
+template <int DOT, int KC, int NSTAGE, int NWARPS, bool C8 = false>
 static int launch_tma(const heat_matrix *A, const double *x, double *y, const int32_t *slice_list, int64_t n_list,
                       CgGate gate, DotOut dot, int grid, cudaStream_t st) {
-    auto kern = sell_spmv_tma_kernel<DOT, KC, NSTAGE, NWARPS>;
-    const size_t smem = TmaSmem<KC, NSTAGE>::total(NWARPS);
+    auto kern = sell_spmv_tma_kernel<DOT, KC, NSTAGE, NWARPS, false, C8>;
+    const size_t smem = TmaSmem<KC, NSTAGE, C8>::total(NWARPS);
     static bool configured = false;
     if (!configured) {
         HEAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
     kern<<<grid, NWARPS * 32, smem, st>>>(A->slice_ptr.p, A->sell_col.p, A->sell_val.p, x, y, A->n_owned, slice_list,
-                                         n_list, gate, dot, SpmvPeer());
+                                         n_list, gate, dot, SpmvPeer(), dict_of(A));
     HEAT_LAUNCHED();
     return 0;
 }
@@ -324,10 +348,11 @@ static int launch_tma(const heat_matrix *A, const double *x, double *y, const in
 // peer-memory mode: ONE launch over [interior slices | boundary slices]; needs the default TMA config
 bool spmv_peer_supported() { return spmv_variant() == 5; }
 
-int launch_spmv_peer(const heat_matrix *A, const double *x, double *y, CgGate gate, DotOut dot, SpmvPeer peer,
-                     int grid, cudaStream_t st) {
-    auto kern = sell_spmv_tma_kernel<1, 8, 2, 8, true>;
-    const size_t smem = TmaSmem<8, 2>::total(8);
+template <bool C8>
+static int launch_spmv_peer_t(const heat_matrix *A, const double *x, double *y, CgGate gate, DotOut dot, SpmvPeer peer,
+                              int grid, cudaStream_t st) {
+    auto kern = sell_spmv_tma_kernel<1, 8, 2, 8, true, C8>;
+    const size_t smem = TmaSmem<8, 2, C8>::total(8);
     static bool configured = false;
     if (!configured) {
         HEAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -337,9 +362,14 @@ int launch_spmv_peer(const heat_matrix *A, const double *x, double *y, CgGate ga
     const int64_t n_list = have_list ? A->n_int_slices + A->n_bnd_slices : A->n_slices;
     if (!have_list) peer.n_interior = n_list;
     kern<<<grid, 8 * 32, smem, st>>>(A->slice_ptr.p, A->sell_col.p, A->sell_val.p, x, y, A->n_owned,
-                                    have_list ? A->slices_all.p : nullptr, n_list, gate, dot, peer);
+                                    have_list ? A->slices_all.p : nullptr, n_list, gate, dot, peer, dict_of(A));
     HEAT_LAUNCHED();
     return 0;
+}
+int launch_spmv_peer(const heat_matrix *A, const double *x, double *y, CgGate gate, DotOut dot, SpmvPeer peer,
+                     int grid, cudaStream_t st) {
+    return A->sell_idx8.p ? launch_spmv_peer_t<true>(A, x, y, gate, dot, peer, grid, st)
+                          : launch_spmv_peer_t<false>(A, x, y, gate, dot, peer, grid, st);
 }
 
 int launch_spmv(const heat_matrix *A, const double *x, double *y, const int32_t *slice_list,
@@ -347,6 +377,11 @@ int launch_spmv(const heat_matrix *A, const double *x, double *y, const int32_t 
     if (n_list <= 0 && dot.out == nullptr) return 0;
     const int v = spmv_variant();
     const bool d = dot.out != nullptr;
+    if (A->sell_idx8.p && v == 5) {      // byte-indexed column stream (sell.cu: every slice has a small offset table)
+        if (d && dot.with_yy) return launch_tma<2, 8, 2, 8, true>(A, x, y, slice_list, n_list, gate, dot, grid, st);
+        return d ? launch_tma<1, 8, 2, 8, true>(A, x, y, slice_list, n_list, gate, dot, grid, st)
+                 : launch_tma<0, 8, 2, 8, true>(A, x, y, slice_list, n_list, gate, dot, grid, st);
+    }
     if (d && dot.with_yy) {      // x.y and y.y in one pass (power method): default TMA config or direct loads
         if (v != 0) return launch_tma<2, 8, 2, 8>(A, x, y, slice_list, n_list, gate, dot, grid, st);
         sell_spmv_kernel<2><<<grid, kBlock, 0, st>>>(A->slice_ptr.p, A->sell_col.p, A->sell_val.p, x, y,

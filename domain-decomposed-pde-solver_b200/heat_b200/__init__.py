@@ -47,7 +47,7 @@ class MatrixInfo(C.Structure):
                 ("max_row_len", C.c_int32), ("npe", C.c_int32), ("num_dim", C.c_int32), ("num_node_sets", C.c_int32),
                 ("rank", C.c_int32), ("nranks", C.c_int32), ("n_neighbors", C.c_int32), ("sell_chunk", C.c_int32),
                 ("sell_padded_nnz", C.c_int64), ("n_boundary_slices", C.c_int64), ("n_slices", C.c_int64),
-                ("assemble_ms", C.c_double), ("peer_path", C.c_int32), ("reserved", C.c_int32)]
+                ("assemble_ms", C.c_double), ("peer_path", C.c_int32), ("col_index_bytes", C.c_int32)]
 
 
 class PowerInfo(C.Structure):
@@ -64,7 +64,7 @@ class PlanSizes(C.Structure):
 ABI_SYMBOLS = [
     "heat_last_error", "heat_version", "heat_device_count", "heat_kernel_launches", "heat_ctx_create", "heat_ctx_set_stream", "heat_open",
     "heat_create", "heat_close", "heat_mesh_set", "heat_mesh_cube", "heat_mesh_nodeset_ids", "heat_comm_unique_id", "heat_comm_init",
-    "heat_comm_rank", "heat_assemble", "heat_get_matrix", "heat_node_owners", "heat_matrix_owned_nodeset", "heat_power_method", "heat_solve_opts_default", "heat_solve", "heat_solve_host", "heat_spmv",
+    "heat_comm_rank", "heat_assemble", "heat_get_matrix", "heat_node_owners", "heat_matrix_owned_nodeset", "heat_power_method", "heat_solve_opts_default", "heat_solve", "heat_solve_trajectory", "heat_solve_host", "heat_spmv",
     "heat_cg_iterations", "heat_decompose", "heat_write_solution", "heat_nodal_field", "heat_decompose_partition",
     "heat_matrix_get_info", "heat_matrix_export_csr", "heat_matrix_export_maps", "heat_matrix_export_plan",
     "heat_matrix_export_red2orig", "heat_matrix_free", "heat_vector_create", "heat_vector_size",
@@ -106,6 +106,8 @@ def lib():
     L.heat_solve_opts_default.argtypes = [C.POINTER(SolveOpts)]
     L.heat_solve_opts_default.restype = None
     L.heat_solve.argtypes = [vp, vp, vp, vp, C.POINTER(SolveOpts), C.POINTER(SolveInfo)]
+    L.heat_solve_trajectory.argtypes = [vp, vp, vp, vp, C.POINTER(SolveOpts), C.c_int, C.c_int, C.POINTER(SolveInfo),
+                                        C.POINTER(C.c_int)]
     L.heat_solve_host.argtypes = [vp, vp, vp, vp, C.POINTER(SolveOpts), C.POINTER(SolveInfo)]
     L.heat_spmv.argtypes = [vp, vp, vp, vp]
     L.heat_cg_iterations.argtypes = [vp, vp, vp, vp, C.POINTER(SolveOpts), C.c_int, C.POINTER(SolveInfo)]
@@ -414,6 +416,14 @@ class IO:
         o, info = self.solve_opts(**kw), SolveInfo()
         _check(lib().heat_solve(self.h, A.h, X.h, B.h, C.byref(o), C.byref(info)))
         return SolveResult(info.iters, bool(info.converged), info.achieved_tol, info.r0_norm, info.solve_ms)
+
+    def solve_trajectory(self, A: Matrix, X: Vector, B: Vector, write_every: int = 1, first_timestep: int = 0, **kw):
+        """belosSolver with its per-iteration writeSolution (BelosMueLuSolver.cpp:113-133) in one Krylov
+        run -> (SolveResult, frames written)."""
+        o, info, frames = self.solve_opts(**kw), SolveInfo(), C.c_int(0)
+        _check(lib().heat_solve_trajectory(self.h, A.h, X.h, B.h, C.byref(o), write_every, first_timestep,
+                                           C.byref(info), C.byref(frames)))
+        return SolveResult(info.iters, bool(info.converged), info.achieved_tol, info.r0_norm, info.solve_ms), frames.value
 
     def solve_host(self, A: Matrix, b_host, x_host, **kw) -> SolveResult:
         """b_host / x_host: numpy arrays or pinned torch CPU tensors (x_host: x0 in, solution out)."""

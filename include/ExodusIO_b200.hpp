@@ -137,7 +137,7 @@ class IO {
 
 // Solves A x = b (BelosMueLuSolver.cpp:87-139).  The reference runs Belos GMRES(1)+ILUT restarted in a
 // loop and writes the field after every iteration; here the Krylov loop is device-resident PCG and
-// the field is written every `write_every` iterations (and at the end).
+// the field is written every `write_every` iterations (and at the end) without restarting it.
 inline void belosSolver(const heat::Matrix A, const heat::Vector X, const heat::Vector B, size_t numIterations,
                         double tolerance, ExodusIO::IO &io, bool verbose) {
     const heat::Options &opt = io.options();
@@ -149,28 +149,23 @@ inline void belosSolver(const heat::Matrix A, const heat::Vector X, const heat::
     heat_comm_rank(io.ctx(), &rank, &nranks);
     size_t iterations = 0;
     heat_solve_info info{};
-    const size_t chunk = opt.write_every > 0 ? (size_t)opt.write_every : numIterations;
-    int frame = 0;
     bool converged = false;
-    if (opt.write_every > 0 && chunk < numIterations) {
-        // trajectory mode: restart CG every `chunk` iterations from the current X (loses the Krylov
-        // space at each restart, like the reference's reset()/setProblem() loop at :131-132)
-        while (iterations < numIterations) {
-            o.max_iters = (int)std::min(chunk, numIterations - iterations);
-            const double r0_first = info.r0_norm;
-            if (heat_solve(io.ctx(), A->h, X->h, B->h, &o, &info)) { std::cerr << heat_last_error() << std::endl; return; }
-            (void)r0_first;
-            iterations += (size_t)info.iters;
-            io.writeSolution(X, frame++, verbose);
-            if (info.converged || info.iters == 0) { converged = info.converged != 0; break; }
+    o.max_iters = (int)numIterations;
+    if (opt.write_every > 0) {
+        // trajectory mode (the reference writes after EVERY pass of its loop, :114-117): one Krylov run,
+        // the iterate is written every write_every iterations as time steps 0, 1, 2, ...
+        int frames = 0;
+        if (heat_solve_trajectory(io.ctx(), A->h, X->h, B->h, &o, opt.write_every, 0, &info, &frames)) {
+            std::cerr << heat_last_error() << std::endl;
+            return;
         }
+        if (verbose && rank == 0) std::cout << "Wrote " << frames << " time steps." << std::endl;
     } else {
-        o.max_iters = (int)numIterations;
         if (heat_solve(io.ctx(), A->h, X->h, B->h, &o, &info)) { std::cerr << heat_last_error() << std::endl; return; }
-        iterations = (size_t)info.iters;
-        converged = info.converged != 0;
         io.writeSolution(X, 0, verbose);
     }
+    iterations = (size_t)info.iters;
+    converged = info.converged != 0;
     if (rank == 0) {
         if (converged)
             std::cout << "The Belos solve took " << iterations << " iteration(s) to reach a relative residual tolerance of "

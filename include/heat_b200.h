@@ -137,6 +137,13 @@ typedef struct {
 void heat_solve_opts_default(heat_solve_opts *o);
 int  heat_solve(heat_ctx *ctx, heat_matrix *A, heat_vector *X, const heat_vector *B,
                 const heat_solve_opts *opts, heat_solve_info *info);
+/* Same solve with the reference's per-iteration field output (BelosMueLuSolver.cpp:113-133 calls
+ * io.writeSolution(X, i) after every pass): ONE Krylov run; every `write_every` iterations, and at
+ * the end, the current iterate is written as time step first_timestep, first_timestep+1, ...
+ * through heat_write_solution (collective; needs heat_create + heat_decompose on rank 0).         */
+int  heat_solve_trajectory(heat_ctx *ctx, heat_matrix *A, heat_vector *X, const heat_vector *B,
+                           const heat_solve_opts *opts, int write_every, int first_timestep,
+                           heat_solve_info *info, int *frames_written);
 /* Same, through host buffers (the end-to-end path): b_host[n_owned] is copied in, x_host holds
  * x0 on entry and the solution on exit.                                                          */
 int  heat_solve_host(heat_ctx *ctx, heat_matrix *A, const double *b_host, double *x_host,
@@ -166,7 +173,8 @@ typedef struct {
     int64_t sell_padded_nnz, n_boundary_slices, n_slices;
     double  assemble_ms;      /* device time of pattern+values+SELL (CUDA events)                 */
     int32_t peer_path;        /* 1 once the NVLink peer-memory halo/all-reduce path is set up      */
-    int32_t reserved;
+    int32_t col_index_bytes;  /* bytes per stored entry of the SpMV column stream: 4 (int32 ids), or 1
+                                 (index into the slice's table of distinct col-row offsets)        */
 } heat_matrix_info;
 int  heat_matrix_get_info(const heat_matrix *A, heat_matrix_info *info);
 /* local CSR: row_ptr[n_owned+1] (int64), col[nnz_local] LOCAL column ids (int32), val.           */

@@ -281,6 +281,49 @@ def test_write_solution_round_trip(hb, io, oracle, tmp_path):
     nc.close()
 
 
+def test_solve_trajectory_writes_every_k_iterations(hb, io, oracle, tmp_path):
+    """belosSolver's per-iteration writeSolution (BelosMueLuSolver.cpp:113-133) in ONE Krylov run: frame k
+    is the oracle's iterate after 25(k+1) iterations, the last frame is the converged solution, and the
+    run is bit-identical to a plain solve (no restart)."""
+    from scipy.io import netcdf_file
+    io.open(mesh_path("tet-cube-heat"), True)
+    A, X, B = io.assemble(hb.OP_P1_FEM)
+    ref = oracle.assemble(oracle.read_exodus(mesh_path("tet-cube-heat")), oracle.P1_FEM)
+    out = str(tmp_path / "trajectory.exo")
+    io.create(out)
+    io.decompose(2)
+    res, frames = io.solve_trajectory(A, X, B, write_every=25, max_iters=1000, tol=RES_TOL)
+    x_ref, it_ref, *_ = oracle.pcg(ref, tol=RES_TOL, max_iters=1000)
+    assert res.converged and abs(res.iters - it_ref) <= ITER_SLACK
+    assert frames == -(-res.iters // 25)
+    nc = netcdf_file(out, "r", mmap=False)
+    vals = np.array(nc.variables["vals_nod_var1"].data)
+    np.testing.assert_array_equal(np.array(nc.variables["time_whole"].data), np.arange(frames, dtype=np.float64))
+    nc.close()
+    assert vals.shape == (frames, ref.node_bc.shape[0])
+    np.testing.assert_array_equal(vals[-1], oracle.scatter_field(ref, X.numpy()))
+    scale = np.abs(x_ref).max()
+    for k in (0, 2, frames - 2):
+        xk = oracle.pcg(ref, tol=0.0, max_iters=25 * (k + 1))[0]
+        assert np.abs(vals[k] - oracle.scatter_field(ref, xk)).max() <= SOL_RTOL * scale, k
+    err = [np.abs(vals[k] - vals[-1]).max() for k in range(frames)]
+    assert err[0] > err[frames // 2] > err[-2] > 0
+    x_traj = X.numpy().copy()
+    X.fill(0.0)
+    io.solve(A, X, B, max_iters=1000, tol=RES_TOL)
+    np.testing.assert_array_equal(X.numpy(), x_traj)                 # same Krylov run, no restart
+    # exactly on a poll boundary: no duplicate frame; max_iters == 0: one frame (x0)
+    X.fill(0.0)
+    _, fr = io.solve_trajectory(A, X, B, write_every=10, first_timestep=frames, max_iters=30, tol=0.0)
+    assert fr == 3
+    X.fill(0.0)
+    _, fr0 = io.solve_trajectory(A, X, B, write_every=5, first_timestep=frames + 3, max_iters=0, tol=0.0)
+    assert fr0 == 1
+    nc = netcdf_file(out, "r", mmap=False)
+    assert nc.variables["vals_nod_var1"].data.shape[0] == frames + 4
+    nc.close()
+
+
 # ---- edge cases ------------------------------------------------------------------------------------
 def test_mesh_without_nodesets_is_the_full_laplacian(hb, io, oracle):
     """2blocks.exo: two TETRA4 blocks, no nodesets -> every node is a DOF, B = 0, A singular (A.1 = 0);
@@ -358,12 +401,41 @@ def test_spmv_variants_bit_identical(hb, oracle):
             "print(hashlib.sha1(y.numpy().tobytes()).hexdigest(), hashlib.sha1(X.numpy().tobytes()).hexdigest())")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     outs = set()
-    for v in range(6):
-        env = dict(os.environ, HEAT_SPMV_VARIANT=str(v))
+    for v, cidx in [(v, "1") for v in range(6)] + [(5, "0")]:      # (5, "1") is the byte-indexed default
+        env = dict(os.environ, HEAT_SPMV_VARIANT=str(v), HEAT_SPMV_CIDX=cidx)
         p = subprocess.run([sys.executable, "-c", code % root], capture_output=True, text=True, env=env, timeout=300)
         assert p.returncode == 0, p.stderr[-2000:]
         outs.add(p.stdout.strip().split()[0])
     assert len(outs) == 1, outs
+
+
+def test_byte_indexed_column_stream(hb, oracle):
+    """The SpMV column stream shrinks to one byte per entry when every 64-row slice has at most 64
+    distinct col-row offsets (structured meshes); otherwise the int32 stream is kept.  Either way the
+    SpMV is bit-exact against the oracle."""
+    for dims in ((40, 33, 29), (5, 5, 5), (66, 3, 2), (3, 2, 2)):
+        io = hb.IO(0)
+        io.mesh_cube(*dims)
+        for mode in (0, 1):
+            A, X, B = io.assemble(mode)
+            # (3,2,2): 4 rows in one 64-row slice, the 60 tail rows all point at column 0 -> int32 stream
+            assert A.info.col_index_bytes == (4 if dims == (3, 2, 2) else 1), dims
+            ref = oracle.assemble(oracle.cube_mesh(*dims), mode)
+            x, y = A.hash_vector(11), A.new_vector()
+            io.spmv(A, x, y)
+            np.testing.assert_array_equal(y.numpy(), oracle.spmv(ref, x.numpy()))
+            pr = io.power_method(A, 3, 0.0, 5)                       # fused x.y / y.y variant of the same kernel
+            lam = oracle.power_method(ref, oracle.hash_vector(np.arange(ref.n), 5), 3, 0.0)[0]
+            assert abs(pr.lambda_ - lam) <= 1e-12 * abs(lam)
+            for v in (x, y, X, B):
+                v.free()
+            A.free()
+        io.close()
+    io = hb.IO(0)
+    io.open(mesh_path("tet-cube-heat"), True)                         # unstructured numbering: hundreds of offsets per slice
+    A, X, B = io.assemble(0)
+    assert A.info.col_index_bytes == 4
+    io.close()
 
 
 def test_cli_driver_end_to_end(hb, oracle, tmp_path):
