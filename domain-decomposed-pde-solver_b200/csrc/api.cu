@@ -437,6 +437,7 @@ extern "C" void heat_solve_opts_default(heat_solve_opts *o) {
     o->solver = HEAT_SOLVER_CG; o->prec = HEAT_PREC_JACOBI;
     o->max_iters = 300; o->tol = 1e-14;                  // BelosMueLuSolver.cpp:149-151
     o->cheb_degree = 1; o->cheb_lambda_max = 0.0; o->cheb_ratio = 30.0; o->check_every = 32;
+    o->gmres_restart = 300;                               // Belos "Num Blocks" default
 }
 
 extern "C" int heat_solve(heat_ctx *ctx, heat_matrix *A, heat_vector *X, const heat_vector *B,
@@ -593,8 +594,15 @@ extern "C" int heat_matrix_export_red2orig(const heat_matrix *A, int64_t *out) {
 }
 
 extern "C" int heat_matrix_free(heat_matrix *A) {
-    if (A) { cudaSetDevice(A->ctx->device); cudaStreamSynchronize(A->ctx->stream); peer_matrix_teardown(A); delete A; }
+    if (A) { cudaSetDevice(A->ctx->device); cudaStreamSynchronize(A->ctx->stream); peer_matrix_teardown(A); ilu_free(A); delete A; }
     return 0;
+}
+
+// L and U of HEAT_PREC_ILU0 on the pattern of the local CSR (parity hook)
+extern "C" int heat_matrix_export_ilu0(const heat_matrix *A, double *lu_host, int *n_levels_lower, int *n_levels_upper) {
+    if (!A) HEAT_FAIL(2, "null matrix");
+    HEAT_CUDA(cudaSetDevice(A->ctx->device));
+    return ilu_export(A, lu_host, n_levels_lower, n_levels_upper);
 }
 
 // ---- vectors -----------------------------------------------------------------------------------------

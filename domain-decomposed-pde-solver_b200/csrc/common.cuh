@@ -98,6 +98,7 @@ enum { I_ITERS = 0, I_STATUS = 1, I_COUNTER = 2, I_COUNTER2 = 3, I_COUNT = 8 };
 
 }  // namespace heat
 
+namespace heat { struct IluState; }   // ilu.cu: ILU(0) factors + level schedules of one matrix
 struct PeerMatrixState;    // comm.cu: CUDA-IPC mappings + push plans of one matrix (peer-memory halo path)
 
 struct heat_vector {
@@ -152,6 +153,7 @@ struct heat_matrix {
     heat::DevBuf<double> w_r, w_p, w_p2, w_ap, w_s, w_u, w_t, w_w;
     heat::DevBuf<double> h_x, h_b;       // staging of heat_solve_host (x with ghosts, b)
     PeerMatrixState *peer = nullptr;     // non-null once the peer-memory halo path is set up
+    heat::IluState *ilu = nullptr;       // non-null once HEAT_PREC_ILU0 has been set up
     heat::DevBuf<double> partials;       // [2 * kMaxPartials * 4]
     heat::DevBuf<double> scal;           // [S_COUNT]
     heat::DevBuf<int> iscal;             // [I_COUNT]

@@ -71,8 +71,8 @@ int ensure_workspace(heat_matrix *A, bool single_reduce, bool cheb) {
 struct ChebCoef { double inv_theta, delta, s1; };
 
 // z = p_k(D^-1 A) D^-1 r, Ifpack2 recurrences, zero starting solution
-static int cheb_apply(heat_ctx *ctx, heat_matrix *A, const heat_solve_opts &o, double lmax, const double *r,
-                      double *z, CgGate gate, int grid) {
+int cheb_apply(heat_ctx *ctx, heat_matrix *A, const heat_solve_opts &o, double lmax, const double *r,
+               double *z, CgGate gate, int grid) {
     const double ratio = o.cheb_ratio > 0 ? o.cheb_ratio : 30.0;
     const double alpha = lmax / ratio, beta = 1.1 * lmax;
     const double delta = 2.0 / (beta - alpha), theta = 0.5 * (beta + alpha), s1 = theta * delta;
@@ -90,7 +90,7 @@ static int cheb_apply(heat_ctx *ctx, heat_matrix *A, const heat_solve_opts &o, d
 
 // lambda_max(D^-1 A) by 10 power iterations from a fixed pseudo-random start (Ifpack2 default is a
 // random start; a counter-based start keeps the solve reproducible and GPU-count invariant)
-static int estimate_lambda_max(heat_ctx *ctx, heat_matrix *A, double *lmax_out) {
+int estimate_lambda_max(heat_ctx *ctx, heat_matrix *A, double *lmax_out) {
     const int grid = vec_grid(A->n_owned, sm_count(ctx->device));
     double *x = A->w_u.p;
     HEAT_TRY(launch_fill_hash(A->n_owned, x, A->owned_contiguous ? nullptr : A->d_owned_gids.p, A->gid0, 777, ctx->stream));
@@ -175,12 +175,19 @@ int solve_device(heat_ctx *ctx, heat_matrix *A, double *x, const double *b, cons
                  heat_solve_info *info, const std::function<int(int)> *on_poll) {
     HEAT_CUDA(cudaSetDevice(ctx->device));
     const bool single = o.solver == HEAT_SOLVER_CG_SINGLE_REDUCE;
-    const bool cheb = o.prec == HEAT_PREC_CHEBYSHEV;
-    if (o.solver != HEAT_SOLVER_CG && !single) HEAT_FAIL(2, "heat_solve: unknown solver %d", o.solver);
+    const bool is_cheb = o.prec == HEAT_PREC_CHEBYSHEV, is_ilu = o.prec == HEAT_PREC_ILU0;
+    const bool cheb = is_cheb || is_ilu;            // "general" preconditioner: z = M^-1 r is a separate step
+    if (o.solver != HEAT_SOLVER_CG && !single && o.solver != HEAT_SOLVER_GMRES) HEAT_FAIL(2, "heat_solve: unknown solver %d", o.solver);
     if (o.prec != HEAT_PREC_NONE && o.prec != HEAT_PREC_JACOBI && !cheb) HEAT_FAIL(2, "heat_solve: unknown preconditioner %d", o.prec);
-    if (cheb && single) HEAT_FAIL(2, "heat_solve: Chebyshev is implemented for HEAT_SOLVER_CG only");
+    if (cheb && single) HEAT_FAIL(2, "heat_solve: Chebyshev / ILU(0) are implemented for HEAT_SOLVER_CG and HEAT_SOLVER_GMRES only");
     if (o.max_iters < 0 || !(o.tol >= 0.0)) HEAT_FAIL(2, "heat_solve: bad max_iters/tol");
+    if (o.solver == HEAT_SOLVER_GMRES) return gmres_device(ctx, A, x, b, o, info, on_poll);
     HEAT_TRY(ensure_workspace(A, single, cheb));
+    if (is_ilu) HEAT_TRY(ilu0_setup(ctx, A));
+    // z = M^-1 r for the general preconditioners (ILU(0) of a symmetric matrix is L D L^T: a valid CG preconditioner)
+    auto gen_prec = [&](double lmax_, const double *r_, double *z_, CgGate gate_, int grid_) -> int {
+        return is_ilu ? ilu_apply(ctx, A, r_, z_) : cheb_apply(ctx, A, o, lmax_, r_, z_, gate_, grid_);
+    };
     // peer-memory path (peer.cuh): classical CG with the fused Jacobi/identity preconditioner
     if (!single && !cheb && ctx->nranks > 1 && ctx->peer_enabled && !A->peer) HEAT_TRY(peer_matrix_setup(ctx, A));
     const bool peer = !single && !cheb && ctx->nranks > 1 && A->peer != nullptr;
@@ -213,7 +220,7 @@ int solve_device(heat_ctx *ctx, heat_matrix *A, double *x, const double *b, cons
     CgGate nogate{nullptr, nullptr, nullptr, 0};
 
     double lmax = o.cheb_lambda_max;
-    if (cheb && !(lmax > 0.0)) HEAT_TRY(estimate_lambda_max(ctx, A, &lmax));
+    if (is_cheb && !(lmax > 0.0)) HEAT_TRY(estimate_lambda_max(ctx, A, &lmax));
 
     HEAT_CUDA(cudaEventRecord(ctx->ev_a, st));
     // ---- r0 = b - A x0 ; z0 ; p0 (or u0, w0) ; H[0] ----
@@ -237,7 +244,7 @@ int solve_device(heat_ctx *ctx, heat_matrix *A, double *x, const double *b, cons
     } else {
         double *z = A->w_u.p;
         HEAT_TRY(launch_cg_init(n, b, ap, A->dinv.p, r, z, H, A->partials.p, I + I_COUNTER2, vgrid, st));   // r (z overwritten below)
-        HEAT_TRY(cheb_apply(ctx, A, o, lmax, r, z, nogate, vgrid));
+        HEAT_TRY(gen_prec(lmax, r, z, nogate, vgrid));
         HEAT_TRY(launch_dot2(n, r, z, r, r, &H[0].rz, &H[0].rr, A->partials.p, I + I_COUNTER2, vgrid, st));
         HEAT_TRY(comm_allreduce_sum(ctx, &H[0].rz, 3));
         HEAT_TRY(launch_axpby(n, 1.0, z, 0.0, p, vgrid, st));
@@ -284,7 +291,7 @@ int solve_device(heat_ctx *ctx, heat_matrix *A, double *x, const double *b, cons
                 HEAT_TRY(spmv_halo(ctx, A, p, ap, gate, S + S_PAP0));
                 HEAT_TRY(comm_allreduce_sum(ctx, S + S_PAP0, 1));
                 HEAT_TRY(launch_cg_xr_plain(n, x, r, p, ap, gate, S, I, vgrid, st));
-                HEAT_TRY(cheb_apply(ctx, A, o, lmax, r, z, gate, vgrid));
+                HEAT_TRY(gen_prec(lmax, r, z, gate, vgrid));
                 HEAT_TRY(launch_cg_dots(n, r, z, gate, H, I, A->partials.p, I + I_COUNTER2, vgrid, st));
                 HEAT_TRY(comm_allreduce_sum(ctx, &H[it + 1].rz, 3));
                 HEAT_TRY(launch_cg_p_plain(n, p, z, gate, vgrid, st));

@@ -14,4 +14,15 @@ int ensure_workspace(heat_matrix *A, bool single_reduce, bool cheb);
 // iterations and when the stopping test fired), while x holds exactly that iterate
 int solve_device(heat_ctx *ctx, heat_matrix *A, double *x, const double *b, const heat_solve_opts &o,
                  heat_solve_info *info, const std::function<int(int)> *on_poll = nullptr);
+int cheb_apply(heat_ctx *ctx, heat_matrix *A, const heat_solve_opts &o, double lmax, const double *r,
+               double *z, CgGate gate, int grid);
+int estimate_lambda_max(heat_ctx *ctx, heat_matrix *A, double *lmax_out);
+// gmres.cu
+int gmres_device(heat_ctx *ctx, heat_matrix *A, double *x, const double *b, const heat_solve_opts &o,
+                 heat_solve_info *info, const std::function<int(int)> *on_poll);
+// ilu.cu
+int ilu0_setup(heat_ctx *ctx, heat_matrix *A);
+int ilu_apply(heat_ctx *ctx, heat_matrix *A, const double *v, double *z);
+int ilu_export(const heat_matrix *A, double *lu_host, int *n_levels_lower, int *n_levels_upper);
+void ilu_free(heat_matrix *A);
 }  // namespace heat

@@ -20,8 +20,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libheat_b200.so")
 
 OP_GRAPH_LAPLACIAN, OP_P1_FEM = 0, 1
-SOLVER_CG, SOLVER_CG_SINGLE_REDUCE = 0, 1
-PREC_NONE, PREC_JACOBI, PREC_CHEBYSHEV = 0, 1, 2
+SOLVER_CG, SOLVER_CG_SINGLE_REDUCE, SOLVER_GMRES = 0, 1, 2
+PREC_NONE, PREC_JACOBI, PREC_CHEBYSHEV, PREC_ILU0 = 0, 1, 2, 3
 PART_CONTIGUOUS, PART_METIS_KWAY, PART_SLAB = 0, 1, 2
 COMM_ID_BYTES = 128
 
@@ -33,7 +33,7 @@ class HeatError(RuntimeError):
 class SolveOpts(C.Structure):
     _fields_ = [("solver", C.c_int), ("prec", C.c_int), ("max_iters", C.c_int), ("tol", C.c_double),
                 ("cheb_degree", C.c_int), ("cheb_lambda_max", C.c_double), ("cheb_ratio", C.c_double),
-                ("check_every", C.c_int)]
+                ("check_every", C.c_int), ("gmres_restart", C.c_int)]
 
 
 class SolveInfo(C.Structure):
@@ -67,7 +67,7 @@ ABI_SYMBOLS = [
     "heat_comm_rank", "heat_assemble", "heat_get_matrix", "heat_node_owners", "heat_matrix_owned_nodeset", "heat_power_method", "heat_solve_opts_default", "heat_solve", "heat_solve_trajectory", "heat_solve_host", "heat_spmv",
     "heat_cg_iterations", "heat_decompose", "heat_write_solution", "heat_nodal_field", "heat_decompose_partition",
     "heat_matrix_get_info", "heat_matrix_export_csr", "heat_matrix_export_maps", "heat_matrix_export_plan",
-    "heat_matrix_export_red2orig", "heat_matrix_free", "heat_vector_create", "heat_vector_size",
+    "heat_matrix_export_red2orig", "heat_matrix_export_ilu0", "heat_matrix_free", "heat_vector_create", "heat_vector_size",
     "heat_vector_device_ptr", "heat_vector_set", "heat_vector_get", "heat_vector_fill", "heat_vector_fill_hash",
     "heat_vector_free", "heat_plan_build", "heat_partition_rows",
 ]
@@ -120,6 +120,7 @@ def lib():
     L.heat_matrix_export_maps.argtypes = [vp, i64p, i64p, i32p]
     L.heat_matrix_export_plan.argtypes = [vp, i32p, i64p, i32p, i64p]
     L.heat_matrix_export_red2orig.argtypes = [vp, i64p]
+    L.heat_matrix_export_ilu0.argtypes = [vp, dp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.heat_matrix_free.argtypes = [vp]
     L.heat_vector_create.argtypes = [vp, vp, C.POINTER(vp)]
     L.heat_vector_size.argtypes = [vp]
@@ -258,6 +259,13 @@ class Matrix:
         v = self.new_vector()
         _check(lib().heat_vector_fill_hash(self.io.h, self.h, v.h, seed))
         return v
+
+    def ilu0(self):
+        """(lu values on the CSR pattern, forward levels, backward levels) of HEAT_PREC_ILU0."""
+        lu = np.empty(max(self.info.nnz_local, 1), dtype=np.float64)
+        nl, nu = C.c_int(0), C.c_int(0)
+        _check(lib().heat_matrix_export_ilu0(self.h, _ptr(lu, C.c_double), C.byref(nl), C.byref(nu)))
+        return lu[: self.info.nnz_local], nl.value, nu.value
 
     def owned_nodeset(self, set_id: int) -> np.ndarray:
         """getMatrix's nodeSetMap[set_id] (ExodusIO.hpp:1447-1466): owned nodes of that nodeset, 0-based."""

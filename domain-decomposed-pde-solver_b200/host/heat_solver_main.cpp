@@ -2,8 +2,9 @@
 // same flags (--input --solution --iterations --tolerance --verbose/--no-verbose --outputPrefix
 // --reportAfterIterations) and the same call order
 //     io.open -> io.assemble -> (rank 0) io.create + io.decompose(max(2, ranks)) -> belosSolver
-// plus the knobs the reference hard-codes: --operator graph|p1, --solver cg|cg1, --prec
-// none|jacobi|chebyshev, --partitions N, --write-every K, --device D.
+// plus the knobs the reference hard-codes: --operator graph|p1, --solver cg|cg1|gmres, --prec
+// none|jacobi|chebyshev|ilu0, --gmres-restart M, --reference-loop (GMRES + ILU with one iteration per
+// solve() call, as the reference is written), --partitions N, --write-every K, --device D.
 // Single process, single GPU (multi-GPU runs are driven by one process per GPU through the C ABI;
 // see INTEGRATION.md).
 #include <cstdlib>
@@ -42,9 +43,15 @@ int main(int argc, char *argv[]) {
         else if (flag_value(a, "cheb-degree", v)) opt.cheb_degree = std::atoi(v.c_str());
         else if (flag_value(a, "cheb-lambda-max", v)) opt.cheb_lambda_max = std::strtod(v.c_str(), nullptr);
         else if (flag_value(a, "operator", v)) opt.op_mode = (v == "p1") ? HEAT_OP_P1_FEM : HEAT_OP_GRAPH_LAPLACIAN;
-        else if (flag_value(a, "solver", v)) opt.solver = (v == "cg1") ? HEAT_SOLVER_CG_SINGLE_REDUCE : HEAT_SOLVER_CG;
+        else if (flag_value(a, "solver", v))
+            opt.solver = (v == "cg1") ? HEAT_SOLVER_CG_SINGLE_REDUCE : (v == "gmres") ? HEAT_SOLVER_GMRES : HEAT_SOLVER_CG;
         else if (flag_value(a, "prec", v))
-            opt.prec = (v == "none") ? HEAT_PREC_NONE : (v == "chebyshev") ? HEAT_PREC_CHEBYSHEV : HEAT_PREC_JACOBI;
+            opt.prec = (v == "none") ? HEAT_PREC_NONE : (v == "chebyshev") ? HEAT_PREC_CHEBYSHEV
+                     : (v == "ilu0" || v == "ilut") ? HEAT_PREC_ILU0 : HEAT_PREC_JACOBI;
+        else if (flag_value(a, "gmres-restart", v)) opt.gmres_restart = std::atoi(v.c_str());
+        else if (a == "--reference-loop") {      // the reference as shipped: GMRES(1) + ILU, one iteration per solve()
+            opt.solver = HEAT_SOLVER_GMRES; opt.prec = HEAT_PREC_ILU0; opt.literal_loop = true;
+        }
         else if (a == "--verbose") verbose = true;
         else if (a == "--no-verbose") verbose = false;
         else if (a == "--dump") dump = true;

@@ -41,6 +41,9 @@ struct Options {                 // knobs the reference hard-codes (ExodusIO.hpp
     int cheb_degree = 3;
     double cheb_lambda_max = 0.0;
     int write_every = 0;         // 0: write the final field only; k: every k iterations (the reference: 1)
+    int gmres_restart = 300;     // HEAT_SOLVER_GMRES: Belos "Num Blocks"
+    bool literal_loop = false;   // reproduce the reference's loop literally: numIterations solves with
+                                 // "Maximum Iterations" = 1, field written after each (BelosMueLuSolver.cpp:102,113-133)
 };
 
 }  // namespace heat
@@ -145,12 +148,29 @@ inline void belosSolver(const heat::Matrix A, const heat::Vector X, const heat::
     heat_solve_opts_default(&o);
     o.solver = opt.solver; o.prec = opt.prec; o.tol = tolerance;
     o.cheb_degree = opt.cheb_degree; o.cheb_lambda_max = opt.cheb_lambda_max;
+    o.gmres_restart = opt.gmres_restart;
     int rank = 0, nranks = 1;
     heat_comm_rank(io.ctx(), &rank, &nranks);
     size_t iterations = 0;
     heat_solve_info info{};
     bool converged = false;
     o.max_iters = (int)numIterations;
+    if (opt.literal_loop) {
+        // the reference's loop as written: every pass is a fresh solve() limited to ONE iteration, starting
+        // from the current X, with its own initial residual as the reference of the relative test (so the
+        // test can only fire if one iteration gains `tolerance`), and the field is written after each pass
+        o.max_iters = 1;
+        for (size_t i = 0; i < numIterations; ++i) {
+            if (heat_solve(io.ctx(), A->h, X->h, B->h, &o, &info)) { std::cerr << heat_last_error() << std::endl; return; }
+            io.writeSolution(X, (int)i, verbose);
+            ++iterations;
+            if (info.converged || info.achieved_tol <= tolerance) { converged = info.converged != 0; break; }
+        }
+        if (rank == 0)        // the reference prints this line unconditionally after the loop (D8)
+            std::cout << "The Belos solve took " << iterations << " iteration(s), but did not converge. Achieved tolerance = "
+                      << info.achieved_tol << "." << std::endl;
+        return;
+    }
     if (opt.write_every > 0) {
         // trajectory mode (the reference writes after EVERY pass of its loop, :114-117): one Krylov run,
         // the iterate is written every write_every iterations as time steps 0, 1, 2, ...

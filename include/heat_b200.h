@@ -36,9 +36,13 @@ enum { HEAT_OP_GRAPH_LAPLACIAN = 0,      /* reference-exact, ExodusIO.hpp:116-12
        HEAT_OP_P1_FEM = 1 };             /* north-star P1 stiffness, same pattern                */
 /* Krylov solver (reference: Belos "GMRES", BelosMueLuSolver.cpp:106; north-star: CG)            */
 enum { HEAT_SOLVER_CG = 0,               /* classical Belos-style PCG, 2 reductions / iteration  */
-       HEAT_SOLVER_CG_SINGLE_REDUCE = 1  /* Chronopoulos-Gear PCG, 1 reduction / iteration       */ };
-/* preconditioner (reference: Ifpack2 "ILUT", BelosMueLuSolver.cpp:93; north-star: below)        */
-enum { HEAT_PREC_NONE = 0, HEAT_PREC_JACOBI = 1, HEAT_PREC_CHEBYSHEV = 2 };
+       HEAT_SOLVER_CG_SINGLE_REDUCE = 1, /* Chronopoulos-Gear PCG, 1 reduction / iteration       */
+       HEAT_SOLVER_GMRES = 2 };          /* restarted GMRES(m), RIGHT preconditioned: the literal
+                                            reference solver (BelosMueLuSolver.cpp:102-109)      */
+/* preconditioner (reference: Ifpack2 "ILUT", BelosMueLuSolver.cpp:93; north-star: Jacobi/Chebyshev) */
+enum { HEAT_PREC_NONE = 0, HEAT_PREC_JACOBI = 1, HEAT_PREC_CHEBYSHEV = 2,
+       HEAT_PREC_ILU0 = 3 };             /* ILU(0) of the rank-local block (stands in for Ifpack2
+                                            ILUT with its default list; CG or GMRES)             */
 /* partitioner used by heat_assemble when nranks > 1                                             */
 enum { HEAT_PART_CONTIGUOUS = 0,         /* Tpetra uniform contiguous map, ExodusIO.hpp:252      */
        HEAT_PART_METIS_KWAY = 1,         /* METIS k-way on the matrix row graph (role of Zoltan2
@@ -126,6 +130,7 @@ typedef struct {
     double cheb_lambda_max;   /* "chebyshev: max eigenvalue"; <=0 => 10 power iterations          */
     double cheb_ratio;        /* "chebyshev: ratio eigenvalue" (default 30)                       */
     int    check_every;       /* host convergence poll period in iterations (0 => 32)             */
+    int    gmres_restart;     /* GMRES: Belos "Num Blocks" = iterations per restart cycle (300)    */
 } heat_solve_opts;
 typedef struct {
     int    iters;
@@ -189,6 +194,10 @@ int  heat_matrix_export_plan(const heat_matrix *A, int32_t *nbr_rank_host, int64
                              int32_t *send_idx_host, int64_t *recv_ptr_host);
 /* reduced global id -> 0-based original node (globalIDMap, ExodusIO.hpp:572-576) of owned rows   */
 int  heat_matrix_export_red2orig(const heat_matrix *A, int64_t *red2orig_host);
+/* ILU(0) factors (after a solve with HEAT_PREC_ILU0): lu_host[nnz_local] on the pattern of
+ * heat_matrix_export_csr — strictly lower part = L (unit diagonal), the rest = U; ghost-column
+ * entries keep the values of A.  Also the number of dependency levels of the two sweeps.        */
+int  heat_matrix_export_ilu0(const heat_matrix *A, double *lu_host, int *n_levels_lower, int *n_levels_upper);
 int  heat_matrix_free(heat_matrix *A);
 
 int  heat_vector_create(heat_ctx *ctx, const heat_matrix *A, heat_vector **out);

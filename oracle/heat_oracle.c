@@ -277,9 +277,17 @@ static void cheb_apply(int64_t n, const int64_t *rp, const int32_t *col, const d
     }
 }
 
+int oracle_ilu0(int64_t n, const int64_t *rp, const int32_t *col, const double *val, double *lu);
+void oracle_ilu0_apply(int64_t n, const int64_t *rp, const int32_t *col, const double *lu, const double *v, double *z);
+
 int oracle_pcg(int64_t n, const int64_t *rp, const int32_t *col, const double *val,
                const double *b, double *x, int prec, int cheb_degree, double lmax, double ratio,
                int max_iters, double tol, double *achieved_tol, double *res_hist) {
+    double *lu = NULL;                 /* prec == 3: ILU(0) (= L D L^T for a symmetric matrix) */
+    if (prec == 3) {
+        lu = (double *)malloc(sizeof(double) * (size_t)(rp[n] > 0 ? rp[n] : 1));
+        if (oracle_ilu0(n, rp, col, val, lu)) { free(lu); return -1; }
+    }
     double *r = (double *)malloc(sizeof(double) * (size_t)n), *z = (double *)malloc(sizeof(double) * (size_t)n);
     double *p = (double *)malloc(sizeof(double) * (size_t)n), *Ap = (double *)malloc(sizeof(double) * (size_t)n);
     double *dinv = (double *)malloc(sizeof(double) * (size_t)n);
@@ -298,6 +306,7 @@ int oracle_pcg(int64_t n, const int64_t *rp, const int32_t *col, const double *v
 #pragma omp parallel for schedule(static)
     for (int64_t i = 0; i < n; ++i) r[i] = b[i] - Ap[i];
     if (prec == ORACLE_PREC_CHEBYSHEV) cheb_apply(n, rp, col, val, dinv, r, z, w, t, cheb_degree, lmax, ratio);
+    else if (prec == 3) oracle_ilu0_apply(n, rp, col, lu, r, z);
     else {
 #pragma omp parallel for schedule(static)
         for (int64_t i = 0; i < n; ++i) z[i] = dinv[i] * r[i];
@@ -316,6 +325,7 @@ int oracle_pcg(int64_t n, const int64_t *rp, const int32_t *col, const double *v
 #pragma omp parallel for schedule(static)
         for (int64_t i = 0; i < n; ++i) { x[i] += alpha * p[i]; r[i] -= alpha * Ap[i]; }
         if (prec == ORACLE_PREC_CHEBYSHEV) cheb_apply(n, rp, col, val, dinv, r, z, w, t, cheb_degree, lmax, ratio);
+        else if (prec == 3) oracle_ilu0_apply(n, rp, col, lu, r, z);
         else {
 #pragma omp parallel for schedule(static)
             for (int64_t i = 0; i < n; ++i) z[i] = dinv[i] * r[i];
@@ -330,7 +340,7 @@ int oracle_pcg(int64_t n, const int64_t *rp, const int32_t *col, const double *v
         if (res_hist) res_hist[it] = sqrt(rr / rr0);
     }
     if (achieved_tol) *achieved_tol = (rr0 > 0.0) ? sqrt(rr / rr0) : 0.0;
-    free(r); free(z); free(p); free(Ap); free(dinv); free(w); free(t);
+    free(r); free(z); free(p); free(Ap); free(dinv); free(w); free(t); free(lu);
     return status < 0 ? -1 : it;
 }
 
@@ -369,4 +379,156 @@ int oracle_power_method(int64_t n, const int64_t *rp, const int32_t *col, const 
     free(q);
     *lambda_out = lambda; *residual_out = residual; *converged = conv;
     return stopped;
+}
+
+/* ILU(0) in the textbook IKJ order on the CSR pattern (columns ascending in every row): the stand-in for
+ * the reference's Ifpack2 "ILUT" with an empty parameter list (BelosMueLuSolver.cpp:93-96).  Strictly
+ * lower entries of lu = L (unit diagonal), the rest = U.  Returns -1 if a row has no diagonal entry. */
+int oracle_ilu0(int64_t n, const int64_t *rp, const int32_t *col, const double *val, double *lu) {
+    int64_t *dpos = (int64_t *)malloc(sizeof(int64_t) * (size_t)(n > 0 ? n : 1));
+    memcpy(lu, val, sizeof(double) * (size_t)rp[n]);
+    for (int64_t i = 0; i < n; ++i) {
+        dpos[i] = -1;
+        for (int64_t q = rp[i]; q < rp[i + 1]; ++q)
+            if (col[q] == i) dpos[i] = q;
+        if (dpos[i] < 0) { free(dpos); return -1; }
+    }
+    for (int64_t i = 0; i < n; ++i) {
+        for (int64_t q = rp[i]; q < rp[i + 1]; ++q) {
+            const int32_t k = col[q];
+            if (k >= i) continue;
+            const double lik = lu[q] / lu[dpos[k]];
+            lu[q] = lik;
+            for (int64_t s = rp[k]; s < rp[k + 1]; ++s) {
+                const int32_t j = col[s];
+                if (j <= k) continue;
+                for (int64_t p = rp[i]; p < rp[i + 1]; ++p)
+                    if (col[p] == j) { lu[p] = lu[p] - lik * lu[s]; break; }
+            }
+        }
+    }
+    free(dpos);
+    return 0;
+}
+
+/* z = U^-1 L^-1 v */
+void oracle_ilu0_apply(int64_t n, const int64_t *rp, const int32_t *col, const double *lu, const double *v, double *z) {
+    for (int64_t i = 0; i < n; ++i) {
+        double s = v[i];
+        for (int64_t q = rp[i]; q < rp[i + 1]; ++q)
+            if (col[q] < i) s = s - lu[q] * z[col[q]];
+        z[i] = s;
+    }
+    for (int64_t i = n - 1; i >= 0; --i) {
+        double s = z[i], d = 1.0;
+        for (int64_t q = rp[i]; q < rp[i + 1]; ++q) {
+            if (col[q] > i) s = s - lu[q] * z[col[q]];
+            else if (col[q] == i) d = lu[q];
+        }
+        z[i] = s / d;
+    }
+}
+
+/* Belos pseudo-block GMRES restated: restarted GMRES(m) with a RIGHT preconditioner
+ * (BelosMueLuSolver.cpp:102-109), two passes of classical Gram-Schmidt (ICGS), Givens rotations, the
+ * implicit residual |g_{j+1}| / ||r_0|| tested after every iteration and the explicit one at a restart.
+ * prec: ORACLE_PREC_* or 3 = ILU(0).  Returns the number of inner iterations. */
+int oracle_gmres(int64_t n, const int64_t *rp, const int32_t *col, const double *val, const double *b, double *x,
+                 int prec, int cheb_degree, double lmax, double ratio, int restart, int max_iters, double tol,
+                 double *achieved_tol, int *converged) {
+    int m = restart > 0 ? restart : 300;
+    if (max_iters > 0 && m > max_iters) m = max_iters;
+    if (m < 1) m = 1;
+    const size_t N = (size_t)(n > 0 ? n : 1);
+    double *V = (double *)malloc(sizeof(double) * N * (size_t)(m + 1));
+    double *H = (double *)calloc((size_t)(m + 1) * (size_t)m, sizeof(double));
+    double *cs = (double *)malloc(sizeof(double) * (size_t)m), *sn = (double *)malloc(sizeof(double) * (size_t)m);
+    double *g = (double *)malloc(sizeof(double) * (size_t)(m + 1)), *y = (double *)malloc(sizeof(double) * (size_t)m);
+    double *r = (double *)malloc(sizeof(double) * N), *w = (double *)malloc(sizeof(double) * N);
+    double *z = (double *)malloc(sizeof(double) * N), *u = (double *)malloc(sizeof(double) * N);
+    double *dinv = (double *)malloc(sizeof(double) * N), *cw = (double *)malloc(sizeof(double) * N), *ct = (double *)malloc(sizeof(double) * N);
+    double *lu = NULL, *h1 = (double *)malloc(sizeof(double) * (size_t)(m + 1));
+    for (int64_t i = 0; i < n; ++i) {
+        double d = 1.0;
+        for (int64_t q = rp[i]; q < rp[i + 1]; ++q)
+            if (col[q] == i) d = val[q];
+        dinv[i] = 1.0 / d;
+    }
+    if (prec == 3) { lu = (double *)malloc(sizeof(double) * (size_t)(rp[n] > 0 ? rp[n] : 1)); oracle_ilu0(n, rp, col, val, lu); }
+#define PREC_APPLY(in, out)                                                                         \
+    do {                                                                                            \
+        if (prec == ORACLE_PREC_CHEBYSHEV) cheb_apply(n, rp, col, val, dinv, (in), (out), cw, ct, cheb_degree, lmax, ratio); \
+        else if (prec == 3) oracle_ilu0_apply(n, rp, col, lu, (in), (out));                         \
+        else for (int64_t i_ = 0; i_ < n; ++i_) (out)[i_] = (prec == ORACLE_PREC_JACOBI) ? dinv[i_] * (in)[i_] : (in)[i_]; \
+    } while (0)
+    double r0norm = -1.0, resid = 0.0;
+    int iters = 0, conv = 0;
+    while (1) {
+        oracle_spmv(n, rp, col, val, x, w);
+        for (int64_t i = 0; i < n; ++i) r[i] = b[i] - w[i];
+        const double beta = sqrt(dot(n, r, r));
+        if (r0norm < 0.0) r0norm = beta;
+        resid = beta;
+        if (!(beta > tol * r0norm) || iters >= max_iters) { conv = !(beta > tol * r0norm); break; }
+        for (int64_t i = 0; i < n; ++i) V[i] = r[i] * (1.0 / beta);
+        memset(g, 0, sizeof(double) * (size_t)(m + 1));
+        g[0] = beta;
+        int k = 0, stagnated = 0;
+        for (int j = 0; j < m && iters < max_iters; ++j) {
+            PREC_APPLY(V + (size_t)j * N, z);
+            oracle_spmv(n, rp, col, val, z, w);
+            double *Hj = H + (size_t)j * (size_t)(m + 1);
+            for (int t = 0; t <= j; ++t) Hj[t] = 0.0;
+            for (int pass = 0; pass < 2; ++pass) {
+                for (int t = 0; t <= j; ++t) h1[t] = dot(n, V + (size_t)t * N, w);
+                for (int64_t i = 0; i < n; ++i) {
+                    double s = w[i];
+                    for (int t = 0; t <= j; ++t) s = fma(-h1[t], V[(size_t)t * N + (size_t)i], s);
+                    w[i] = s;
+                }
+                for (int t = 0; t <= j; ++t) Hj[t] += h1[t];
+            }
+            const double nrm2 = dot(n, w, w), hnext = sqrt(nrm2);
+            Hj[j + 1] = hnext;
+            for (int t = 0; t < j; ++t) {
+                const double a = cs[t] * Hj[t] + sn[t] * Hj[t + 1];
+                Hj[t + 1] = -sn[t] * Hj[t] + cs[t] * Hj[t + 1];
+                Hj[t] = a;
+            }
+            const double den = hypot(Hj[j], Hj[j + 1]);
+            if (!(den > 0.0)) { stagnated = 1; break; }
+            cs[j] = Hj[j] / den; sn[j] = Hj[j + 1] / den;
+            Hj[j] = den; Hj[j + 1] = 0.0;
+            g[j + 1] = -sn[j] * g[j];
+            g[j] = cs[j] * g[j];
+            ++iters; k = j + 1;
+            resid = fabs(g[j + 1]);
+            if (!(resid > tol * r0norm) || !(hnext > 0.0)) break;
+            const double inv = 1.0 / sqrt(nrm2);
+            for (int64_t i = 0; i < n; ++i) V[(size_t)(j + 1) * N + (size_t)i] = inv * w[i];
+        }
+        if (k > 0) {
+            for (int i = k - 1; i >= 0; --i) {
+                double s = g[i];
+                for (int t = i + 1; t < k; ++t) s -= H[(size_t)t * (size_t)(m + 1) + (size_t)i] * y[t];
+                y[i] = s / H[(size_t)i * (size_t)(m + 1) + (size_t)i];
+            }
+            for (int64_t i = 0; i < n; ++i) {
+                double s = 0.0;
+                for (int t = 0; t < k; ++t) s = fma(y[t], V[(size_t)t * N + (size_t)i], s);
+                u[i] = s;
+            }
+            PREC_APPLY(u, z);
+            for (int64_t i = 0; i < n; ++i) x[i] = fma(1.0, z[i], 1.0 * x[i]);
+        }
+        if (stagnated || k == 0) break;
+        if (!(resid > tol * r0norm)) { conv = 1; break; }
+        if (iters >= max_iters) break;
+    }
+#undef PREC_APPLY
+    if (achieved_tol) *achieved_tol = r0norm > 0.0 ? resid / r0norm : 0.0;
+    if (converged) *converged = conv;
+    free(V); free(H); free(cs); free(sn); free(g); free(y); free(r); free(w); free(z); free(u);
+    free(dinv); free(cw); free(ct); free(lu); free(h1);
+    return iters;
 }

@@ -83,6 +83,16 @@ int oracle_power_method(int64_t n, const int64_t *row_ptr, const int32_t *col, c
                         double *z, int niters, double tolerance, double *lambda_out,
                         double *residual_out, int *converged);
 
+/* ILU(0) (IKJ order) on the CSR pattern + its triangular solves; restarted right-preconditioned
+ * GMRES(m): the literal reference solver (BelosMueLuSolver.cpp:93-109) with ILU(0) for Ifpack2 ILUT. */
+enum { ORACLE_PREC_ILU0 = 3 };
+int  oracle_ilu0(int64_t n, const int64_t *row_ptr, const int32_t *col, const double *val, double *lu);
+void oracle_ilu0_apply(int64_t n, const int64_t *row_ptr, const int32_t *col, const double *lu,
+                       const double *v, double *z);
+int  oracle_gmres(int64_t n, const int64_t *row_ptr, const int32_t *col, const double *val, const double *b,
+                  double *x, int prec, int cheb_degree, double cheb_lambda_max, double cheb_ratio, int restart,
+                  int max_iters, double tol, double *achieved_tol, int *converged);
+
 int oracle_num_threads(void);
 
 #ifdef __cplusplus

@@ -22,7 +22,7 @@ _LIB = os.path.join(_HERE, "_build", "libheat_oracle.so")
 _METIS = os.path.join(_HERE, "_build", "libmetis_oracle.so")
 
 GRAPH_LAPLACIAN, P1_FEM = 0, 1
-PREC_NONE, PREC_JACOBI, PREC_CHEBYSHEV = 0, 1, 2
+PREC_NONE, PREC_JACOBI, PREC_CHEBYSHEV, PREC_ILU0 = 0, 1, 2, 3
 
 
 def build(force: bool = False) -> None:
@@ -61,6 +61,12 @@ def lib():
         _lib.oracle_pcg.restype = C.c_int
         _lib.oracle_scatter_field.argtypes = [C.c_int64, dp, C.c_int64, lp, dp, dp]
         _lib.oracle_num_threads.restype = C.c_int
+        _lib.oracle_ilu0.argtypes = [C.c_int64, lp, ip, dp, dp]
+        _lib.oracle_ilu0.restype = C.c_int
+        _lib.oracle_ilu0_apply.argtypes = [C.c_int64, lp, ip, dp, dp, dp]
+        _lib.oracle_gmres.argtypes = [C.c_int64, lp, ip, dp, dp, dp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int,
+                                      C.c_int, C.c_double, dp, C.POINTER(C.c_int)]
+        _lib.oracle_gmres.restype = C.c_int
         _lib.oracle_power_method.argtypes = [C.c_int64, lp, ip, dp, dp, C.c_int, C.c_double, dp, dp, C.POINTER(C.c_int)]
         _lib.oracle_power_method.restype = C.c_int
     return _lib
@@ -325,6 +331,36 @@ def scatter_field(sys_: System, x: np.ndarray) -> np.ndarray:
     lib().oracle_scatter_field(N, _p(sys_.node_bc, C.c_double), sys_.n, _p(sys_.red2orig, C.c_int64),
                                _p(x, C.c_double), _p(f, C.c_double))
     return f
+
+
+def ilu0(sys_: System) -> np.ndarray:
+    """ILU(0) factors on the CSR pattern (IKJ order): strictly lower = L (unit diagonal), rest = U."""
+    lu = np.empty(max(sys_.nnz, 1))
+    rc = lib().oracle_ilu0(sys_.n, _p(sys_.row_ptr, C.c_int64), _p(sys_.col, C.c_int32), _p(sys_.val, C.c_double), _p(lu, C.c_double))
+    if rc:
+        raise RuntimeError("oracle_ilu0: missing diagonal")
+    return lu[: sys_.nnz]
+
+
+def ilu0_apply(sys_: System, lu: np.ndarray, v: np.ndarray) -> np.ndarray:
+    v = np.ascontiguousarray(v, dtype=np.float64)
+    lu = np.ascontiguousarray(lu, dtype=np.float64)
+    z = np.empty(sys_.n)
+    lib().oracle_ilu0_apply(sys_.n, _p(sys_.row_ptr, C.c_int64), _p(sys_.col, C.c_int32), _p(lu, C.c_double), _p(v, C.c_double), _p(z, C.c_double))
+    return z
+
+
+def gmres(sys_: System, x0: np.ndarray | None = None, prec: int = PREC_ILU0, restart: int = 300, max_iters: int = 300,
+          tol: float = 1e-8, cheb_degree: int = 1, cheb_lambda_max: float = 2.0, cheb_ratio: float = 30.0):
+    """Right-preconditioned restarted GMRES (Belos "GMRES" + setRightPrec, BelosMueLuSolver.cpp:102-109).
+    Returns (x, inner iterations, achieved_tol, converged)."""
+    x = np.zeros(sys_.n) if x0 is None else np.array(x0, dtype=np.float64)
+    b = np.ascontiguousarray(sys_.b)
+    ach, conv = C.c_double(0.0), C.c_int(0)
+    it = lib().oracle_gmres(sys_.n, _p(sys_.row_ptr, C.c_int64), _p(sys_.col, C.c_int32), _p(sys_.val, C.c_double),
+                            _p(b, C.c_double), _p(x, C.c_double), prec, cheb_degree, cheb_lambda_max, cheb_ratio, restart,
+                            max_iters, tol, C.byref(ach), C.byref(conv))
+    return x, int(it), ach.value, bool(conv.value)
 
 
 def power_method(sys_: System, z0: np.ndarray, niters: int = 500, tolerance: float = 1.0e-2):

@@ -99,6 +99,17 @@ def check_system(io, A, X, B, ref, part, rank, world, tag, log):
     res = io.solve(A, X, B, prec=hb.PREC_CHEBYSHEV, cheb_degree=3, cheb_lambda_max=2.5, max_iters=3000, tol=1e-10)
     xc, itc, *_ = O.pcg(ref, tol=1e-10, prec=O.PREC_CHEBYSHEV, cheb_degree=3, cheb_lambda_max=2.5, max_iters=3000)
     assert res.converged and abs(res.iters - itc) <= 2 and np.abs(X.numpy() - xc[owned]).max() <= 1e-8 * np.abs(xc).max(), (tag, res, itc)
+    # GMRES(20) + Jacobi (distributed Gram-Schmidt: all-reduced multi-dots) == the serial oracle;
+    # GMRES + ILU(0) of the rank-local block converges to the same solution (iteration count depends on the split)
+    X.fill(0.0)
+    res = io.solve(A, X, B, solver=hb.SOLVER_GMRES, prec=hb.PREC_JACOBI, gmres_restart=20, max_iters=5000, tol=1e-10)
+    xg, itg, _, convg = O.gmres(ref, prec=O.PREC_JACOBI, restart=20, max_iters=5000, tol=1e-10)
+    assert res.converged and convg and abs(res.iters - itg) <= max(2, itg // 100), (tag, res, itg)
+    assert np.abs(X.numpy() - xg[owned]).max() <= 1e-8 * np.abs(xg).max(), tag
+    X.fill(0.0)
+    res = io.solve(A, X, B, solver=hb.SOLVER_GMRES, prec=hb.PREC_ILU0, gmres_restart=50, max_iters=5000, tol=1e-10)
+    assert res.converged and np.abs(X.numpy() - x_ref[owned]).max() <= 1e-8 * np.abs(x_ref).max(), (tag, res)
+    log.append(f"{tag} gmres(20)+jacobi iters={itg}, gmres(50)+block-ilu0 iters={res.iters}")
     return x_ref
 
 

@@ -197,3 +197,47 @@ def test_power_method_oracle(oracle):
 def test_hash_vector_twin(oracle):
     v = oracle.hash_vector(np.arange(1000), 12345)
     assert v.min() >= -1 and v.max() < 1 and abs(v.mean()) < 0.1 and len(np.unique(v)) == 1000
+
+
+@pytest.mark.parametrize("name,mode", [("bolted_bracket", 0), ("tet-cube-heat", 1), ("mitchell_tri", 1)])
+def test_ilu0_oracle_reproduces_A_on_its_pattern(oracle, name, mode):
+    """Defining property of ILU(0): (L U)_ij = A_ij wherever A has an entry."""
+    import scipy.sparse as sp
+    s = oracle.assemble(oracle.read_exodus(mesh_path(name)), mode)
+    lu = oracle.ilu0(s)
+    rows = np.repeat(np.arange(s.n), np.diff(s.row_ptr))
+    L = sp.csr_matrix((np.where(s.col < rows, lu, 0.0), s.col, s.row_ptr), shape=(s.n, s.n)) + sp.identity(s.n)
+    U = sp.csr_matrix((np.where(s.col >= rows, lu, 0.0), s.col, s.row_ptr), shape=(s.n, s.n))
+    A = s.csr()
+    patt = A.copy()
+    patt.data[:] = 1.0
+    assert abs((L @ U).multiply(patt) - A).max() <= 1e-12 * abs(A).max()
+    # the two triangular solves invert L U
+    v = oracle.hash_vector(np.arange(s.n), 3)
+    z = oracle.ilu0_apply(s, lu, v)
+    assert np.abs(L @ (U @ z) - v).max() <= 1e-10
+
+
+@pytest.mark.parametrize("prec,restart", [(3, 300), (3, 1), (1, 30), (0, 50), (2, 20)])
+def test_gmres_oracle_matches_direct_solve(oracle, golden, prec, restart):
+    """Right-preconditioned restarted GMRES (the reference's literal Krylov method, BelosMueLuSolver.cpp:102-109)
+    against the golden direct-solve statistics; restart = 1 is the reference's one-iteration-per-solve loop."""
+    s = oracle.assemble(oracle.read_exodus(mesh_path("bolted_bracket")), 0)
+    x, it, ach, conv = oracle.gmres(s, prec=prec, restart=restart, max_iters=3000, tol=1e-10, cheb_degree=3)
+    g = golden["bolted_bracket"]["graph"]
+    assert conv and ach <= 1e-10
+    assert abs(x.mean() - g["x_mean"]) <= 1e-7 * abs(g["x_mean"]) and abs(np.linalg.norm(x) - g["x_norm2"]) <= 1e-7 * g["x_norm2"]
+    if restart == 1:          # GMRES(1) = minimal-residual iteration: the residual never grows
+        res = []
+        xk = np.zeros(s.n)
+        for _ in range(5):
+            xk = oracle.gmres(s, x0=xk, prec=prec, restart=1, max_iters=1, tol=0.0)[0]
+            res.append(np.linalg.norm(s.b - s.csr() @ xk))
+        assert all(b <= a for a, b in zip(res, res[1:]))
+
+
+def test_pcg_with_ilu0_oracle(oracle):
+    s = oracle.assemble(oracle.read_exodus(mesh_path("tet-cube-heat")), oracle.P1_FEM)
+    x, it, *_ = oracle.pcg(s, prec=oracle.PREC_ILU0, tol=1e-10, max_iters=1000)
+    xj, itj, *_ = oracle.pcg(s, tol=1e-10, max_iters=1000)
+    assert it < itj / 2 and np.abs(x - xj).max() <= 1e-8 * np.abs(xj).max()
