@@ -73,30 +73,27 @@ int main(int argc, char *argv[]) {
         std::cerr << "Process #" << rank << ": Failed to getMatrix!!" << std::endl;
         return EXIT_FAILURE;
     }
+    std::ofstream output;
     if (dump) {
-        // the reference's only observability format: "row: [(col,val),...]" per rank (BelosMueLuSolver.cpp:37-84)
-        std::ofstream output(outputPrefix + std::to_string(rank) + ".out");
-        heat_matrix_info mi;
-        heat_matrix_get_info(A->h, &mi);
-        std::vector<int64_t> rp((size_t)mi.n_owned + 1);
-        std::vector<int32_t> col((size_t)mi.nnz_local);
-        std::vector<double> val((size_t)mi.nnz_local), b((size_t)mi.n_owned);
-        heat_matrix_export_csr(A->h, rp.data(), col.data(), val.data());
-        heat_vector_get(io.ctx(), B->h, b.data(), mi.n_owned);
-        output << "[Laplacian: A]" << std::endl;
-        for (int64_t r = 0; r < mi.n_owned; ++r) {
-            output << r << ": [";
-            for (int64_t q = rp[(size_t)r]; q < rp[(size_t)r + 1]; ++q)
-                output << (q > rp[(size_t)r] ? "," : "") << "(" << col[(size_t)q] << "," << val[(size_t)q] << ")";
-            output << "]" << std::endl;
+        // the reference's only observability format (BelosMueLuSolver.cpp:37-84, :169-215): "<prefix><rank>.out"
+        output.open(outputPrefix + std::to_string(rank) + ".out");
+        if (!output.good()) {
+            std::cerr << "Process #" << rank << ": Failed to open output file '" << outputPrefix << rank << ".out'" << std::endl;
+            return EXIT_FAILURE;
         }
+        output << "[Laplacian: A]" << std::endl;
+        heat::printCrsMatrix(A, output);
         output << "[RHS: B]" << std::endl;
-        for (int64_t r = 0; r < mi.n_owned; ++r) output << r << ": " << b[(size_t)r] << std::endl;
+        heat::printMultiVector(io.ctx(), A, B, output);
     }
     if (!io.create(solution)) {
         std::cerr << "Process #" << rank << ": Failed to create output file '" << solution << "'" << std::endl;
     }
     io.decompose(partitions > 0 ? partitions : std::max(2, ranks), verbose);      // :209
     belosSolver(A, X, B, numIterations, tolerance, io, verbose);
+    if (dump) {
+        output << "[Solution: X]" << std::endl;
+        heat::printMultiVector(io.ctx(), A, X, output);
+    }
     return 0;
 }

@@ -9,6 +9,8 @@
 // One IO per process == per GPU (the reference: one IO per MPI rank).
 #pragma once
 #include <algorithm>
+#include <chrono>
+#include <cstdint>
 #include <cstdio>
 #include <iostream>
 #include <map>
@@ -137,6 +139,46 @@ class IO {
 };
 
 }  // namespace ExodusIO
+
+// The reference's debug dump (BelosMueLuSolver.cpp:28-84): one line per owned row with GLOBAL ids,
+// "row: [(col,val),(col,val),...] ~timestamp~" for a matrix and "row: [val] ~timestamp~" for a vector,
+// columns sorted ascending; the per-rank files "<prefix><rank>.out" with their "[Section]" headers are
+// merged by the reference's mpi_output_combiner.py, which orders lines by the microsecond timestamp.
+namespace heat {
+inline uint64_t getTime() {
+    return (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::system_clock::now().time_since_epoch()).count();
+}
+inline void printCrsMatrix(const Matrix &A, std::ostream &output) {
+    heat_matrix_info mi;
+    heat_matrix_get_info(A->h, &mi);
+    std::vector<int64_t> rp((size_t)mi.n_owned + 1), owned((size_t)mi.n_owned + 1), ghost((size_t)mi.n_ghost + 1);
+    std::vector<int32_t> col((size_t)mi.nnz_local + 1), owner((size_t)mi.n_ghost + 1);
+    std::vector<double> val((size_t)mi.nnz_local + 1);
+    heat_matrix_export_csr(A->h, rp.data(), col.data(), val.data());
+    heat_matrix_export_maps(A->h, owned.data(), ghost.data(), owner.data());
+    std::vector<std::pair<int64_t, double>> entries;
+    for (int64_t r = 0; r < mi.n_owned; ++r) {
+        entries.clear();
+        for (int64_t q = rp[(size_t)r]; q < rp[(size_t)r + 1]; ++q) {
+            const int32_t c = col[(size_t)q];
+            entries.emplace_back(c < mi.n_owned ? owned[(size_t)c] : ghost[(size_t)(c - mi.n_owned)], val[(size_t)q]);
+        }
+        std::sort(entries.begin(), entries.end());
+        output << owned[(size_t)r] << ": [";
+        for (size_t i = 0; i < entries.size(); ++i) output << (i ? "," : "") << "(" << entries[i].first << "," << entries[i].second << ")";
+        output << "] ~" << getTime() << "~" << std::endl;
+    }
+}
+inline void printMultiVector(heat_ctx *ctx, const Matrix &A, const Vector &X, std::ostream &output) {
+    heat_matrix_info mi;
+    heat_matrix_get_info(A->h, &mi);
+    std::vector<int64_t> owned((size_t)mi.n_owned + 1);
+    std::vector<double> x((size_t)mi.n_owned + 1);
+    heat_matrix_export_maps(A->h, owned.data(), nullptr, nullptr);
+    heat_vector_get(ctx, X->h, x.data(), mi.n_owned);
+    for (int64_t r = 0; r < mi.n_owned; ++r) output << owned[(size_t)r] << ": [" << x[(size_t)r] << "] ~" << getTime() << "~" << std::endl;
+}
+}  // namespace heat
 
 // Solves A x = b (BelosMueLuSolver.cpp:87-139).  The reference runs Belos GMRES(1)+ILUT restarted in a
 // loop and writes the field after every iteration; here the Krylov loop is device-resident PCG and

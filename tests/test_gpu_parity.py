@@ -595,3 +595,34 @@ def test_reference_loop_cli(hb, oracle, tmp_path):
     A = ref.csr()
     res = [np.linalg.norm(ref.b - A @ v[ref.red2orig]) for v in vals[::10]]
     assert all(b < a for a, b in zip(res, res[1:]))
+
+
+def test_cli_dump_matches_reference_format(hb, oracle, tmp_path):
+    """heat_solver --dump writes "<prefix><rank>.out" in the format the reference's mpi_output_combiner.py
+    consumes (BelosMueLuSolver.cpp:37-84): "[Section]" headers, then "row: [(col,val),...] ~usec~" /
+    "row: [val] ~usec~" lines with global ids and ascending columns."""
+    import re
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "domain-decomposed-pde-solver_b200", "bin", "heat_solver")
+    prefix = str(tmp_path / "mpi-proc-")
+    p = subprocess.run([exe, f"--input={mesh_path('rectangle-tris-boundary')}", f"--solution={tmp_path / 's.exo'}",
+                        f"--outputPrefix={prefix}", "--dump", "--tolerance=1e-12"], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr
+    lines = open(prefix + "0.out").read().splitlines(keepends=True)
+    sections, cur, stamps = {}, None, []
+    for l in lines:
+        if re.match(r"\[.*\]", l):                         # the combiner's section test
+            cur = l.strip()[1:-1]
+            sections[cur] = []
+            continue
+        m = re.search(r"~([0-9]*)~\n", l)                   # the combiner's timestamp extraction
+        assert m, l
+        stamps.append(int(m.group(1)))
+        sections[cur].append(re.sub(r"~[0-9]*~", "", l).strip())
+    assert list(sections) == ["Laplacian: A", "RHS: B", "Solution: X"]
+    assert stamps == sorted(stamps)
+    assert sections["Laplacian: A"] == ["0: [(0,5),(2,-1)]", "1: [(1,4),(2,-1)]", "2: [(0,-1),(1,-1),(2,5)]"]
+    assert sections["RHS: B"] == ["0: [500]", "1: [450]", "2: [300]"]
+    x = [float(re.match(r"\d+: \[(.*)\]", l).group(1)) for l in sections["Solution: X"]]
+    np.testing.assert_allclose(x, [122.527472527, 140.659340659, 112.637362637], rtol=1e-5)
