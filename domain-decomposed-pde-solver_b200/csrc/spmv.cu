@@ -134,8 +134,9 @@ struct TmaSmem {
     static constexpr size_t total(int nwarps) { return (size_t)nwarps * kWarpBytes + (size_t)nwarps * NSTAGE * 8; }
 };
 
-template <int DOT, int KC, int NSTAGE, int NWARPS, bool PEER = false, bool C8 = false>
-__global__ void __launch_bounds__(NWARPS * 32, (NWARPS <= 8 && KC <= 8) ? 2 : 1)
+template <int DOT, int KC, int NSTAGE, int NWARPS, bool PEER = false, bool C8 = false,
+          int MINB = ((NWARPS <= 8 && KC <= 8) ? 2 : 1)>
+__global__ void __launch_bounds__(NWARPS * 32, MINB)
 sell_spmv_tma_kernel(const int64_t *__restrict__ slice_ptr, const int32_t *__restrict__ col,
                      const double *__restrict__ val, const double *__restrict__ x, double *__restrict__ y,
                      int64_t n_rows, const int32_t *__restrict__ slice_list, int64_t n_list, CgGate gate,
@@ -314,6 +315,21 @@ static int spmv_variant() {
     return v;
 }
 
+// shapes of the byte-indexed kernel (HEAT_SPMV_C8CFG, tools/bench_spmv.py), KC x stages x warps x CTAs/SM:
+// 0 = default 8x2x10x2 (its smaller stages leave room for 20 warps per SM: 2.94 ms at 512^3 against 3.11 ms
+// for the int32 kernel's 8x2x8x2 shape, 3.58 for 8x3x6x2, 3.46 for 4x4x8x2, 3.16 for 8x2x5x3, 3.08 for 4x3x10x2);
+// 1 = 8x2x8x2; 2 = 8x2x11x2; 3 = 6x2x12x2; 4 = 6x3x10x2; 5 = 4x3x10x2
+static int c8_cfg() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("HEAT_SPMV_C8CFG");
+        v = e ? atoi(e) : 0;
+        if (v < 0 || v > 5) v = 0;
+    }
+    return v;
+}
+constexpr int kC8Warps = 10;
+
 static int tma_warps(int variant) { return variant == 1 ? 8 : variant == 2 ? 12 : variant == 3 ? 16 : variant == 4 ? 24 : 8; }
 
 int spmv_grid(int64_t n_list, int sm_count) {
@@ -329,10 +345,10 @@ int spmv_grid(int64_t n_list, int sm_count) {
 
 static SellDict dict_of(const heat_matrix *A) { return SellDict{A->sell_idx8.p, A->sell_tab.p, A->sell_tpad}; }
 
-template <int DOT, int KC, int NSTAGE, int NWARPS, bool C8 = false>
+template <int DOT, int KC, int NSTAGE, int NWARPS, bool C8 = false, int MINB = ((NWARPS <= 8 && KC <= 8) ? 2 : 1)>
 static int launch_tma(const heat_matrix *A, const double *x, double *y, const int32_t *slice_list, int64_t n_list,
                       CgGate gate, DotOut dot, int grid, cudaStream_t st) {
-    auto kern = sell_spmv_tma_kernel<DOT, KC, NSTAGE, NWARPS, false, C8>;
+    auto kern = sell_spmv_tma_kernel<DOT, KC, NSTAGE, NWARPS, false, C8, MINB>;
     const size_t smem = TmaSmem<KC, NSTAGE, C8>::total(NWARPS);
     static bool configured = false;
     if (!configured) {
@@ -351,8 +367,9 @@ bool spmv_peer_supported() { return spmv_variant() == 5; }
 template <bool C8>
 static int launch_spmv_peer_t(const heat_matrix *A, const double *x, double *y, CgGate gate, DotOut dot, SpmvPeer peer,
                               int grid, cudaStream_t st) {
-    auto kern = sell_spmv_tma_kernel<1, 8, 2, 8, true, C8>;
-    const size_t smem = TmaSmem<8, 2, C8>::total(8);
+    constexpr int NW = C8 ? kC8Warps : 8;
+    auto kern = sell_spmv_tma_kernel<1, 8, 2, NW, true, C8, 2>;
+    const size_t smem = TmaSmem<8, 2, C8>::total(NW);
     static bool configured = false;
     if (!configured) {
         HEAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -361,8 +378,8 @@ static int launch_spmv_peer_t(const heat_matrix *A, const double *x, double *y, 
     const bool have_list = A->slices_all.p != nullptr && A->n_ghost > 0;
     const int64_t n_list = have_list ? A->n_int_slices + A->n_bnd_slices : A->n_slices;
     if (!have_list) peer.n_interior = n_list;
-    kern<<<grid, 8 * 32, smem, st>>>(A->slice_ptr.p, A->sell_col.p, A->sell_val.p, x, y, A->n_owned,
-                                    have_list ? A->slices_all.p : nullptr, n_list, gate, dot, peer, dict_of(A));
+    kern<<<grid, NW * 32, smem, st>>>(A->slice_ptr.p, A->sell_col.p, A->sell_val.p, x, y, A->n_owned,
+                                     have_list ? A->slices_all.p : nullptr, n_list, gate, dot, peer, dict_of(A));
     HEAT_LAUNCHED();
     return 0;
 }
@@ -378,9 +395,22 @@ int launch_spmv(const heat_matrix *A, const double *x, double *y, const int32_t 
     const int v = spmv_variant();
     const bool d = dot.out != nullptr;
     if (A->sell_idx8.p && v == 5) {      // byte-indexed column stream (sell.cu: every slice has a small offset table)
-        if (d && dot.with_yy) return launch_tma<2, 8, 2, 8, true>(A, x, y, slice_list, n_list, gate, dot, grid, st);
-        return d ? launch_tma<1, 8, 2, 8, true>(A, x, y, slice_list, n_list, gate, dot, grid, st)
-                 : launch_tma<0, 8, 2, 8, true>(A, x, y, slice_list, n_list, gate, dot, grid, st);
+        if (d && dot.with_yy) return launch_tma<2, 8, 2, kC8Warps, true, 2>(A, x, y, slice_list, n_list, gate, dot, grid, st);
+        switch (c8_cfg()) {
+            case 1: return d ? launch_tma<1, 8, 2, 8, true, 2>(A, x, y, slice_list, n_list, gate, dot, grid, st)
+                             : launch_tma<0, 8, 2, 8, true, 2>(A, x, y, slice_list, n_list, gate, dot, grid, st);
+            case 2: return d ? launch_tma<1, 8, 2, 11, true, 2>(A, x, y, slice_list, n_list, gate, dot, grid, st)
+                             : launch_tma<0, 8, 2, 11, true, 2>(A, x, y, slice_list, n_list, gate, dot, grid, st);
+            case 3: return d ? launch_tma<1, 6, 2, 12, true, 2>(A, x, y, slice_list, n_list, gate, dot, grid, st)
+                             : launch_tma<0, 6, 2, 12, true, 2>(A, x, y, slice_list, n_list, gate, dot, grid, st);
+            case 4: return d ? launch_tma<1, 6, 3, 10, true, 2>(A, x, y, slice_list, n_list, gate, dot, grid, st)
+                             : launch_tma<0, 6, 3, 10, true, 2>(A, x, y, slice_list, n_list, gate, dot, grid, st);
+            case 5: return d ? launch_tma<1, 4, 3, 10, true, 2>(A, x, y, slice_list, n_list, gate, dot, grid, st)
+                             : launch_tma<0, 4, 3, 10, true, 2>(A, x, y, slice_list, n_list, gate, dot, grid, st);
+            default: break;
+        }
+        return d ? launch_tma<1, 8, 2, kC8Warps, true, 2>(A, x, y, slice_list, n_list, gate, dot, grid, st)
+                 : launch_tma<0, 8, 2, kC8Warps, true, 2>(A, x, y, slice_list, n_list, gate, dot, grid, st);
     }
     if (d && dot.with_yy) {      // x.y and y.y in one pass (power method): default TMA config or direct loads
         if (v != 0) return launch_tma<2, 8, 2, 8>(A, x, y, slice_list, n_list, gate, dot, grid, st);
