@@ -639,6 +639,17 @@ extern "C" int heat_write_solution(heat_ctx *ctx, const heat_vector *X, int time
     if (ctx->rank == 0) field.resize((size_t)m.num_nodes);
     HEAT_TRY(heat_nodal_field(ctx, X, ctx->rank == 0 ? field.data() : nullptr, m.num_nodes));
     if (ctx->rank != 0) return 0;
+    return heat_write_nodal_field(ctx, field.data(), m.num_nodes, timestep);
+}
+
+// the file half of writeSolution (ExodusIO.hpp:2027-2069): ex_put_variable_param / ex_put_variable_names on
+// the first call, then ex_put_time + ex_put_var of one dense nodal array.  Host only (rank 0).
+extern "C" int heat_write_nodal_field(heat_ctx *ctx, const double *field_host, int64_t num_nodes, int timestep) {
+    if (!ctx || !field_host) HEAT_FAIL(2, "heat_write_nodal_field: null argument");
+    if (timestep < 0) HEAT_FAIL(2, "heat_write_nodal_field: negative timestep");
+    const HostMesh &m = ctx->mesh;
+    if (!m.valid || num_nodes != m.num_nodes) HEAT_FAIL(2, "heat_write_nodal_field: field must hold num_nodes = %lld values", (long long)m.num_nodes);
+    const double *field = field_host;
     if (!ctx->write_file) HEAT_FAIL(4, "heat_write_solution: no output file (call heat_create + heat_decompose)");
     ExoFile &wf = *ctx->write_file;
     NcFile &nc = wf.nc;
@@ -673,7 +684,7 @@ extern "C" int heat_write_solution(heat_ctx *ctx, const heat_vector *X, int time
     }
     const double t = (double)timestep;
     swap_copy(tw->raw.data() + (step - 1) * 8, &t, 1, 8);
-    swap_copy(vv->raw.data() + (step - 1) * N * 8, field.data(), (size_t)N, 8);
+    swap_copy(vv->raw.data() + (step - 1) * N * 8, field, (size_t)N, 8);
     wf.steps_written = nc.numrecs;
     // the first result call lays the file out again (new dimension + variables: ex_put_variable_param);
     // later calls only touch the record they write, like ex_put_var (:2056)

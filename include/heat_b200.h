@@ -163,6 +163,10 @@ int  heat_cg_iterations(heat_ctx *ctx, heat_matrix *A, heat_vector *X, const hea
 /* ---- output  (IO::decompose ExodusIO.hpp:1496-1969, IO::writeSolution :1972-2070) ------------ */
 int  heat_decompose(heat_ctx *ctx, int partitions);           /* rank 0 only, after heat_create   */
 int  heat_write_solution(heat_ctx *ctx, const heat_vector *X, int timestep);   /* collective      */
+/* the file half of writeSolution alone (ExodusIO.hpp:2027-2069): one dense nodal array as time step
+ * `timestep` of "Steady-State Heat Solution".  Pure host code; the first call defines the result
+ * variables and rewrites the file, later calls touch only their record.                           */
+int  heat_write_nodal_field(heat_ctx *ctx, const double *field_host, int64_t num_nodes, int timestep);
 /* dense nodal field writeSolution would store (DOF nodes from X, nodeset nodes = their id)       */
 int  heat_nodal_field(heat_ctx *ctx, const heat_vector *X, double *field_host, int64_t num_nodes);
 /* METIS_PartMeshDual with the reference's arguments (ExodusIO.hpp:1615); arrays are int64        */

@@ -227,3 +227,41 @@ def test_matrix_test_cli_usage(hb):
     exe = os.path.join(ROOT, "domain-decomposed-pde-solver_b200", "bin", "heat_matrix_test")
     p = subprocess.run([exe], capture_output=True, text=True)
     assert p.returncode != 0 and "No input file was provided; use the '--input' parameter!" in p.stderr
+
+
+def test_write_nodal_field_records_in_place(hb, host_io, tmp_path):
+    """The file half of IO::writeSolution (ExodusIO.hpp:2027-2069) without a GPU: the first call defines
+    the result variables (file laid out again), later calls append / overwrite single records in place;
+    the mesh part of the file must survive every update."""
+    from scipy.io import netcdf_file
+    src = mesh_path("bolted_bracket")
+    out = str(tmp_path / "fields.exo")
+    host_io.open(src, True)
+    host_io.create(out)
+    with pytest.raises(hb.HeatError):
+        host_io.write_nodal_field(np.zeros(4098), 0)            # before decompose: no output mesh yet
+    host_io.decompose(3)
+    N = 4098
+    rng = np.random.default_rng(0)
+    f = [rng.standard_normal(N) for _ in range(6)]
+    host_io.write_nodal_field(f[0], 0)
+    size1 = os.path.getsize(out)
+    host_io.write_nodal_field(f[1], 1)
+    host_io.write_nodal_field(f[2], 2)
+    assert os.path.getsize(out) == size1 + 2 * (N * 8 + 8)      # two records appended, nothing else rewritten
+    host_io.write_nodal_field(f[3], 1)                          # overwrite step 2 in place (the reference's D7 does this to step 1)
+    host_io.write_nodal_field(f[4], 5)                          # skipping steps leaves zero records in between
+    with pytest.raises(hb.HeatError):
+        host_io.write_nodal_field(f[0][:-1], 6)
+    nc = netcdf_file(out, "r", mmap=False)
+    vals = np.array(nc.variables["vals_nod_var1"].data)
+    tw = np.array(nc.variables["time_whole"].data)
+    assert vals.shape == (6, N)
+    np.testing.assert_array_equal(vals[0], f[0]); np.testing.assert_array_equal(vals[1], f[3])
+    np.testing.assert_array_equal(vals[2], f[2]); np.testing.assert_array_equal(vals[5], f[4])
+    assert not vals[3].any() and not vals[4].any()
+    np.testing.assert_array_equal(tw, [0, 1, 2, 0, 0, 5])
+    ref = netcdf_file(src, "r", mmap=False)
+    np.testing.assert_array_equal(np.array(nc.variables["coordx"].data), np.array(ref.variables["coordx"].data))
+    assert sum(nc.dimensions[f"num_el_in_blk{b}"] for b in (1, 2, 3)) == ref.dimensions["num_elem"]
+    nc.close(); ref.close()
