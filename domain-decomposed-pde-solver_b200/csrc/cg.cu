@@ -162,6 +162,7 @@ __global__ void __launch_bounds__(kBlock) cg_update_xr_peer_kernel(int64_t n, do
                                                                    unsigned long long seq_in,
                                                                    unsigned long long seq_out) {
     if (cg_done(g)) return;
+    if (threadIdx.x == 0) HEAT_TRACE_MIN(g.it, 1, 0);
     __shared__ double sh[2];
     if (threadIdx.x < 32) {
         double o[3];
@@ -169,6 +170,7 @@ __global__ void __launch_bounds__(kBlock) cg_update_xr_peer_kernel(int64_t n, do
         if (threadIdx.x == 0) { sh[0] = o[0]; sh[1] = ok ? 1.0 : 0.0; }
     }
     __syncthreads();
+    if (threadIdx.x == 0) HEAT_TRACE_MAX(g.it, 1, 1);
     if (sh[1] == 0.0) return;                              // communication timeout: I_STATUS = 3
     const double pap = sh[0];
     if (!(pap > 0.0)) {
@@ -200,6 +202,7 @@ __global__ void __launch_bounds__(kBlock) cg_update_xr_peer_kernel(int64_t n, do
         if (threadIdx.x == 0) H[g.it].alpha = alpha;
         if (threadIdx.x < 32) peer_red_push_warp(pr, seq_out, S[S_TMP0], S[S_TMP1], 0.0);
     }
+    if (threadIdx.x == 0) HEAT_TRACE_MAX(g.it, 1, 2);
 }
 
 int launch_cg_update_xr_peer(int64_t n, double *x, double *r, const double *p, const double *ap, const double *dinv,
@@ -241,6 +244,7 @@ __global__ void __launch_bounds__(kBlock) cg_update_p_peer_kernel(int64_t n, dou
                                                                   CgRec *H, int *I, PeerRed pr,
                                                                   unsigned long long seq_in, PeerPush push) {
     if (cg_done(g)) return;
+    if (threadIdx.x == 0) HEAT_TRACE_MIN(g.it, 2, 0);
     __shared__ double sh[3];
     if (threadIdx.x < 32) {
         double o[3];
@@ -248,6 +252,7 @@ __global__ void __launch_bounds__(kBlock) cg_update_p_peer_kernel(int64_t n, dou
         if (threadIdx.x == 0) { sh[0] = o[0]; sh[1] = o[1]; sh[2] = ok ? 1.0 : 0.0; }
     }
     __syncthreads();
+    if (threadIdx.x == 0) HEAT_TRACE_MAX(g.it, 2, 1);
     if (sh[2] == 0.0) return;
     const double rz_new = sh[0], rr_new = sh[1];
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -268,7 +273,15 @@ __global__ void __launch_bounds__(kBlock) cg_update_p_peer_kernel(int64_t n, dou
         const int64_t i = n - 1;
         p_out[i] = fma(beta, p_in[i], dinv[i] * r[i]);
     }
+    if (threadIdx.x == 0) HEAT_TRACE_MAX(g.it, 2, 2);
 }
+
+#ifdef HEAT_PEER_TRACE
+int trace_set_cg(TraceBuf *buf) {
+    HEAT_CUDA(cudaMemcpyToSymbol(g_trace, &buf, sizeof(buf)));
+    return 0;
+}
+#endif
 
 int launch_cg_update_p_peer(int64_t n, double *p_out, const double *p_in, const double *r, const double *dinv,
                             CgGate gate, CgRec *H, int *I, PeerRed pr, unsigned long long seq_in, PeerPush push,

@@ -83,6 +83,10 @@ constexpr int kSellChunk = 32 * kSellRowsPerLane;        // C: rows per SELL sli
 constexpr int kSellDictCap = 64;                         // most distinct col-row offsets a slice may have to be byte-indexed
 constexpr int kMaxPartials = 4096;                       // per-launch block partials capacity
 
+// one entry per slice in SpMV processing order (interior slices first, then boundary slices; natural
+// order on one GPU): everything a warp needs to start streaming the slice, in ONE 16-byte load
+struct SliceMeta { int64_t base; int32_t w; int32_t s; };   // entry offset, entries per row, slice id
+
 // scalar slots of the CG state (device doubles)
 enum {
     S_RZ0 = 0, S_RZ1 = 1,        // gamma = r.z, ping-pong by iteration parity
@@ -139,6 +143,7 @@ struct heat_matrix {
     int sell_tpad = 0;
     heat::DevBuf<int32_t> slices_interior, slices_boundary;   // slice id lists (multi-GPU overlap)
     heat::DevBuf<int32_t> slices_all;                         // interior list followed by boundary list
+    heat::DevBuf<heat::SliceMeta> slice_meta;                 // [n_slices] in slices_all order (natural order without ghosts)
     int64_t n_int_slices = 0, n_bnd_slices = 0;
     heat::DevBuf<double> dinv;           // 1/diag (owned)
     heat::DevBuf<double> diag;

@@ -37,12 +37,17 @@ struct SpmvPeer {             // peer-memory mode of the SpMV (single launch ove
     int *I = nullptr;
 };
 
+#ifdef HEAT_PEER_TRACE
+int trace_set_cg(TraceBuf *buf);
+int trace_set_spmv(TraceBuf *buf);
+#endif
 // ---- sell.cu ----
 int sell_from_csr(heat_matrix *A, cudaStream_t st);
 // ---- spmv.cu ----
-// y = A x over `n_list` slices (slice_list == nullptr: slices 0..n_list-1).  gate.H == nullptr
-// disables the CG stopping test; dot.out == nullptr disables the fused sum_i y_i * x_i.
-int launch_spmv(const heat_matrix *A, const double *x, double *y, const int32_t *slice_list,
+// y = A x over entries [first, first + n_list) of A->slice_meta (processing order: interior slices, then
+// boundary slices).  gate.H == nullptr disables the CG stopping test; dot.out == nullptr disables the
+// fused sum_i y_i * x_i.
+int launch_spmv(const heat_matrix *A, const double *x, double *y, int64_t first,
                 int64_t n_list, CgGate gate, DotOut dot, int grid, cudaStream_t st);
 int launch_spmv_peer(const heat_matrix *A, const double *x, double *y, CgGate gate, DotOut dot, SpmvPeer peer,
                      int grid, cudaStream_t st);

@@ -51,7 +51,28 @@ struct PeerPush {                      // producer side: where my boundary value
     int *ticket = nullptr;
 };
 
+// ---- optional timeline of the peer-path iteration (debug builds: make EXTRA=-DHEAT_PEER_TRACE) ----------
+// per iteration and kernel (0 = SpMV, 1 = update_xr, 2 = update_p): {first block in, last block through its
+// peer wait, last block out} in %globaltimer nanoseconds; dumped by solve_device to $HEAT_PEER_TRACE_FILE<rank>
+#ifdef HEAT_PEER_TRACE
+constexpr int kTraceIters = 2048;
+struct TraceBuf { unsigned long long t[kTraceIters][3][3]; };
+#endif
+
 #ifdef __CUDACC__
+#ifdef HEAT_PEER_TRACE
+static __device__ TraceBuf *g_trace = nullptr;             // one copy per translation unit (no -rdc): see trace_set_*
+__device__ __forceinline__ unsigned long long trace_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define HEAT_TRACE_MIN(it, k, slot) do { if (g_trace && (it) < kTraceIters) atomicMin(&g_trace->t[it][k][slot], trace_now()); } while (0)
+#define HEAT_TRACE_MAX(it, k, slot) do { if (g_trace && (it) < kTraceIters) atomicMax(&g_trace->t[it][k][slot], trace_now()); } while (0)
+#else
+#define HEAT_TRACE_MIN(it, k, slot) do { } while (0)
+#define HEAT_TRACE_MAX(it, k, slot) do { } while (0)
+#endif
 __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }

@@ -59,6 +59,16 @@ sell_fill_kernel(const int64_t *__restrict__ row_ptr, const int32_t *__restrict_
     if (lane == 0 && slice_is_boundary) slice_is_boundary[s] = ghost;
 }
 
+// packed per-slice metadata in processing order (list == nullptr: natural order)
+__global__ void slice_meta_kernel(const int64_t *__restrict__ slice_ptr, const int32_t *__restrict__ list, int64_t n_list,
+                                  SliceMeta *__restrict__ meta) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_list) return;
+    const int64_t s = list ? (int64_t)list[t] : t;
+    const int64_t b = slice_ptr[s];
+    meta[t] = SliceMeta{b, (int32_t)((slice_ptr[s + 1] - b) >> 6), (int32_t)s};
+}
+
 // Byte-indexed column stream.  One warp per slice collects the distinct (col - row) offsets of the
 // slice's 64 x w entries (first-seen order: k ascending, then lane, then the lane's first row) in a
 // shared-memory table.  On a structured mesh a slice has as many distinct offsets as the stencil has
@@ -220,6 +230,12 @@ int sell_from_csr(heat_matrix *A, cudaStream_t st) {
                 HEAT_CUDA(cudaMemcpyAsync(A->slices_boundary.p, lb.data(), sizeof(int32_t) * lb.size(), cudaMemcpyHostToDevice, st));
             HEAT_CUDA(cudaStreamSynchronize(st));
         }
+    }
+    HEAT_TRY(A->slice_meta.alloc((size_t)ns));
+    if (ns > 0) {
+        slice_meta_kernel<<<(unsigned)((ns + 255) / 256), 256, 0, st>>>(A->slice_ptr.p, A->n_ghost > 0 ? A->slices_all.p : nullptr, ns,
+                                                                      A->slice_meta.p);
+        HEAT_LAUNCHED();
     }
     HEAT_TRY(sell_build_dict(A, st));
     HEAT_TRY(launch_extract_diag(A, st));

@@ -32,16 +32,16 @@ int spmv_halo(heat_ctx *ctx, heat_matrix *A, double *x, double *y, CgGate gate, 
     if (!split) {
         const int g = spmv_grid(A->n_slices, sms);
         d.total_blocks = g;
-        return launch_spmv(A, x, y, nullptr, A->n_slices, gate, d, g, ctx->stream);
+        return launch_spmv(A, x, y, 0, A->n_slices, gate, d, g, ctx->stream);
     }
     const int g1 = spmv_grid(A->n_int_slices, sms), g2 = spmv_grid(A->n_bnd_slices, sms) > 2048 ? 2048 : spmv_grid(A->n_bnd_slices, sms);
     const int g1c = g1 > 2048 ? 2048 : g1;
     HEAT_TRY(halo_begin(ctx, A, x));
     d.part_offset = 0; d.total_blocks = g1c + g2;
-    HEAT_TRY(launch_spmv(A, x, y, A->slices_interior.p, A->n_int_slices, gate, d, g1c, ctx->stream));
+    HEAT_TRY(launch_spmv(A, x, y, 0, A->n_int_slices, gate, d, g1c, ctx->stream));
     HEAT_TRY(halo_end(ctx, A));
     d.part_offset = g1c;
-    HEAT_TRY(launch_spmv(A, x, y, A->slices_boundary.p, A->n_bnd_slices, gate, d, g2, ctx->stream));
+    HEAT_TRY(launch_spmv(A, x, y, A->n_int_slices, A->n_bnd_slices, gate, d, g2, ctx->stream));
     return 0;
 }
 
@@ -250,6 +250,17 @@ int solve_device(heat_ctx *ctx, heat_matrix *A, double *x, const double *b, cons
         HEAT_TRY(launch_axpby(n, 1.0, z, 0.0, p, vgrid, st));
     }
 
+#ifdef HEAT_PEER_TRACE
+    DevBuf<TraceBuf> trace;
+    const char *trace_file = getenv("HEAT_PEER_TRACE_FILE");
+    if (peer && trace_file) {
+        HEAT_TRY(trace.alloc(1));
+        std::vector<unsigned long long> init((size_t)kTraceIters * 9);
+        for (size_t q = 0; q < init.size(); ++q) init[q] = (q % 3 == 0) ? ~0ull : 0ull;
+        HEAT_CUDA(cudaMemcpy(trace.p, init.data(), sizeof(TraceBuf), cudaMemcpyHostToDevice));
+        HEAT_TRY(trace_set_cg(trace.p)); HEAT_TRY(trace_set_spmv(trace.p));
+    }
+#endif
     // ---- iterations, polled every check_every ----
     const int check = o.check_every > 0 ? o.check_every : 32;
     int launched = 0, h_iters = 0, h_status = 0;
@@ -310,6 +321,23 @@ int solve_device(heat_ctx *ctx, heat_matrix *A, double *x, const double *b, cons
         ctx->peer_red_seq += 2ull * (unsigned)o.max_iters + 4;
         ctx->peer_halo_epoch += (unsigned)o.max_iters + 4;
     }
+#ifdef HEAT_PEER_TRACE
+    if (trace.p) {
+        HEAT_CUDA(cudaStreamSynchronize(st));
+        std::vector<unsigned long long> h((size_t)kTraceIters * 9);
+        HEAT_CUDA(cudaMemcpy(h.data(), trace.p, sizeof(TraceBuf), cudaMemcpyDeviceToHost));
+        HEAT_TRY(trace_set_cg(nullptr)); HEAT_TRY(trace_set_spmv(nullptr));
+        FILE *fp = fopen((std::string(trace_file) + std::to_string(ctx->rank) + ".txt").c_str(), "w");
+        if (fp) {
+            const int nit = h_iters < kTraceIters ? h_iters : kTraceIters;
+            for (int it = 0; it < nit; ++it) {
+                for (int q = 0; q < 9; ++q) fprintf(fp, "%llu ", h[(size_t)it * 9 + q]);
+                fprintf(fp, "\n");
+            }
+            fclose(fp);
+        }
+    }
+#endif
     CgRec h0, hk;
     HEAT_CUDA(cudaMemcpyAsync(&h0, H, sizeof(CgRec), cudaMemcpyDeviceToHost, st));
     HEAT_CUDA(cudaMemcpyAsync(&hk, H + h_iters, sizeof(CgRec), cudaMemcpyDeviceToHost, st));

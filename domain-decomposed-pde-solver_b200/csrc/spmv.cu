@@ -130,23 +130,26 @@ struct TmaSmem {
     static constexpr int kColBytes = KC * kSellChunk * (C8 ? 1 : 4);
     static constexpr int kStageBytes = kValBytes + kColBytes;
     static constexpr int kTabBytes = C8 ? kSellDictCap * 4 : 0;
-    static constexpr int kWarpBytes = NSTAGE * (kStageBytes + kTabBytes);
+    static constexpr int kRing = NSTAGE + 2;                       // slices the issue cursor can be ahead of the consumer, + 1
+    static constexpr int kRingBytes = ((kRing * 8) + 15) & ~15;    // {slice id, width} per ring slot
+    static constexpr int kWarpBytes = NSTAGE * (kStageBytes + kTabBytes) + kRingBytes;
     static constexpr size_t total(int nwarps) { return (size_t)nwarps * kWarpBytes + (size_t)nwarps * NSTAGE * 8; }
 };
 
 template <int DOT, int KC, int NSTAGE, int NWARPS, bool PEER = false, bool C8 = false,
           int MINB = ((NWARPS <= 8 && KC <= 8) ? 2 : 1)>
 __global__ void __launch_bounds__(NWARPS * 32, MINB)
-sell_spmv_tma_kernel(const int64_t *__restrict__ slice_ptr, const int32_t *__restrict__ col,
+sell_spmv_tma_kernel(const SliceMeta *__restrict__ meta, const int32_t *__restrict__ col,
                      const double *__restrict__ val, const double *__restrict__ x, double *__restrict__ y,
-                     int64_t n_rows, const int32_t *__restrict__ slice_list, int64_t n_list, CgGate gate,
-                     DotOut dot, SpmvPeer peer, SellDict dict) {
+                     int64_t n_rows, int64_t n_list, CgGate gate, DotOut dot, SpmvPeer peer, SellDict dict) {
     if (gate_done(gate)) return;
+    if (PEER && threadIdx.x == 0) HEAT_TRACE_MIN(gate.it, 0, 0);
     using L = TmaSmem<KC, NSTAGE, C8>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char *my = smem_raw + (size_t)warp * L::kWarpBytes;
     unsigned char *my_tabs = my + NSTAGE * L::kStageBytes;           // C8: NSTAGE offset tables of this warp
+    int2 *ring = reinterpret_cast<int2 *>(my + NSTAGE * (L::kStageBytes + L::kTabBytes));   // {slice id, width} issue -> consume
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)NWARPS * L::kWarpBytes) + warp * NSTAGE;
     if (lane == 0) {
 #pragma unroll
@@ -159,15 +162,18 @@ sell_spmv_tma_kernel(const int64_t *__restrict__ slice_ptr, const int32_t *__res
     const uint64_t policy = l2_evict_first_policy();
     const int64_t W = (int64_t)gridDim.x * NWARPS;
     const int64_t first = (int64_t)blockIdx.x * NWARPS + warp;
-    // slice metadata is loaded ONE SLICE AHEAD of its use (slice_list -> slice_ptr is a chain of two
-    // dependent global loads; it must never sit on the path that issues the next TMA copy)
-    struct Meta { int64_t s, base; int w; };
+    // Slice metadata: ONE 16-byte load per slice (sell.cu packs {offset, width, id} in processing order), issued
+    // TWO slices ahead of its use by the issue cursor only — under a saturated memory system a load takes about
+    // as long as a warp needs for one slice, and a stalled issue cursor is a bubble in the TMA pipeline.  The
+    // consume cursor gets {id, width} through a small shared-memory ring written when the slice is first issued
+    // (ordered by the mbarrier phase the consumer waits for anyway).
+    struct Meta { int64_t base; int s, w; };
     auto load_meta = [&](int64_t t) -> Meta {
         Meta m{0, 0, 0};
         if (t < n_list) {
-            m.s = slice_list ? (int64_t)slice_list[t] : t;
-            m.base = slice_ptr[m.s];
-            m.w = (int)((slice_ptr[m.s + 1] - m.base) >> 6);
+            const int4 q = __ldg(reinterpret_cast<const int4 *>(meta + t));
+            m.base = ((int64_t)(unsigned)q.x) | ((int64_t)q.y << 32);
+            m.w = q.z; m.s = q.w;
         }
         return m;
     };
@@ -175,10 +181,11 @@ sell_spmv_tma_kernel(const int64_t *__restrict__ slice_ptr, const int32_t *__res
     // issue cursor (runs NSTAGE chunks ahead of the consume cursor)
     int64_t ti = first;
     int ki = 0, si = 0;                                              // si: ordinal of the slice being issued
-    Meta mi = load_meta(ti), mi_next = load_meta(ti + W);
+    Meta mi = load_meta(ti), mi_next = load_meta(ti + W), mi_next2 = load_meta(ti + 2 * W);
     auto issue = [&](int stage) {
         const int kc = (mi.w - ki) < KC ? (mi.w - ki) : KC;
         if (lane == 0) {
+            if (ki == 0) ring[si % L::kRing] = make_int2(mi.s, mi.w);
             if (kc > 0) {
                 unsigned char *dst = my + stage * L::kStageBytes;
                 const uint32_t vb = (uint32_t)kc * kSellChunk * 8, cb = (uint32_t)kc * kSellChunk * (C8 ? 1 : 4);
@@ -187,7 +194,7 @@ sell_spmv_tma_kernel(const int64_t *__restrict__ slice_ptr, const int32_t *__res
                 tma_load_1d(dst, val + mi.base + (int64_t)ki * kSellChunk, vb, bars + stage, policy);
                 if (C8) {
                     tma_load_1d(dst + L::kValBytes, dict.idx8 + mi.base + (int64_t)ki * kSellChunk, cb, bars + stage, policy);
-                    if (tb) tma_load_1d(my_tabs + (si % NSTAGE) * L::kTabBytes, dict.tab + mi.s * dict.tpad, tb, bars + stage, policy);
+                    if (tb) tma_load_1d(my_tabs + (si % NSTAGE) * L::kTabBytes, dict.tab + (int64_t)mi.s * dict.tpad, tb, bars + stage, policy);
                 } else {
                     tma_load_1d(dst + L::kValBytes, col + mi.base + (int64_t)ki * kSellChunk, cb, bars + stage, policy);
                 }
@@ -198,8 +205,8 @@ sell_spmv_tma_kernel(const int64_t *__restrict__ slice_ptr, const int32_t *__res
         ki += KC;
         if (ki >= mi.w) {
             ti += W; ki = 0; ++si;
-            mi = mi_next;
-            mi_next = load_meta(ti + W);
+            mi = mi_next; mi_next = mi_next2;
+            mi_next2 = load_meta(ti + 2 * W);
         }
     };
 #pragma unroll
@@ -209,19 +216,20 @@ sell_spmv_tma_kernel(const int64_t *__restrict__ slice_ptr, const int32_t *__res
     // consume cursor
     int64_t tc = first;
     int kc0 = 0, sc = 0;                                             // sc: ordinal of the slice being consumed
-    Meta mc = load_meta(tc), mc_next = load_meta(tc + W);
+    int2 mc = make_int2(0, 0);                                       // {slice id, width}: read from the ring per slice
     int stage = 0;
     uint32_t parity = 0;
     double acc0 = 0.0, acc1 = 0.0, dsum = 0.0, ysum = 0.0;
     bool halo_ready = !PEER;
     while (tc < n_list) {
         mbar_wait(bars + stage, parity);
-        const int kc = (mc.w - kc0) < KC ? (mc.w - kc0) : KC;
+        if (kc0 == 0) mc = ring[sc % L::kRing];
+        const int kc = (mc.y - kc0) < KC ? (mc.y - kc0) : KC;
         const double *vs = reinterpret_cast<const double *>(my + stage * L::kStageBytes) + 2 * lane;
         const int32_t *cs = reinterpret_cast<const int32_t *>(my + stage * L::kStageBytes + L::kValBytes) + 2 * lane;
         const unsigned char *is = my + stage * L::kStageBytes + L::kValBytes + 2 * lane;
         const int32_t *tb = reinterpret_cast<const int32_t *>(my_tabs + (sc % NSTAGE) * L::kTabBytes);
-        const int row0 = (int)(mc.s * kSellChunk) + 2 * lane;
+        const int row0 = mc.x * kSellChunk + 2 * lane;
         // the two column ids of this lane at entry k of the staged chunk
         auto cols_at = [&](int k) -> int2 {
             if (C8) {
@@ -235,6 +243,7 @@ sell_spmv_tma_kernel(const int64_t *__restrict__ slice_ptr, const int32_t *__res
             // Wait once per warp for their epoch flags, then gather through L2 (coherent), not L1.
             if (!halo_ready) {
                 if (lane == 0) peer_halo_wait(peer.halo, peer.I);
+                if (lane == 0) HEAT_TRACE_MAX(gate.it, 0, 1);
                 __syncwarp();
                 halo_ready = true;
             }
@@ -265,8 +274,8 @@ sell_spmv_tma_kernel(const int64_t *__restrict__ slice_ptr, const int32_t *__res
         __syncwarp();                                    // every lane is done with this stage
         if (ti < n_list) issue(stage);                   // refill it NSTAGE chunks ahead
         kc0 += KC;
-        if (kc0 >= mc.w) {                               // slice finished: write its 64 rows
-            const int64_t row = mc.s * kSellChunk + 2 * lane;
+        if (kc0 >= mc.y) {                               // slice finished: write its 64 rows
+            const int64_t row = (int64_t)mc.x * kSellChunk + 2 * lane;
             if (row + 1 < n_rows) {
                 *reinterpret_cast<double2 *>(y + row) = make_double2(acc0, acc1);
                 if (DOT) dsum += acc0 * __ldg(x + row) + acc1 * __ldg(x + row + 1);
@@ -278,8 +287,6 @@ sell_spmv_tma_kernel(const int64_t *__restrict__ slice_ptr, const int32_t *__res
             }
             acc0 = 0.0; acc1 = 0.0;
             tc += W; kc0 = 0; ++sc;
-            mc = mc_next;
-            mc_next = load_meta(tc + W);
         }
         if (++stage == NSTAGE) { stage = 0; parity ^= 1u; }
     }
@@ -297,7 +304,15 @@ sell_spmv_tma_kernel(const int64_t *__restrict__ slice_ptr, const int32_t *__res
             grid_sum<1, NWARPS>(acc, dot.partials, dot.part_offset, dot.total_blocks, dot.counter, out);
         }
     }
+    if (PEER && threadIdx.x == 0) HEAT_TRACE_MAX(gate.it, 0, 2);
 }
+
+#ifdef HEAT_PEER_TRACE
+int trace_set_spmv(TraceBuf *buf) {
+    HEAT_CUDA(cudaMemcpyToSymbol(g_trace, &buf, sizeof(buf)));
+    return 0;
+}
+#endif
 
 // -------------------------------------------------------------------------------------------------
 // launch
@@ -346,7 +361,7 @@ int spmv_grid(int64_t n_list, int sm_count) {
 static SellDict dict_of(const heat_matrix *A) { return SellDict{A->sell_idx8.p, A->sell_tab.p, A->sell_tpad}; }
 
 template <int DOT, int KC, int NSTAGE, int NWARPS, bool C8 = false, int MINB = ((NWARPS <= 8 && KC <= 8) ? 2 : 1)>
-static int launch_tma(const heat_matrix *A, const double *x, double *y, const int32_t *slice_list, int64_t n_list,
+static int launch_tma(const heat_matrix *A, const double *x, double *y, int64_t first, int64_t n_list,
                       CgGate gate, DotOut dot, int grid, cudaStream_t st) {
     auto kern = sell_spmv_tma_kernel<DOT, KC, NSTAGE, NWARPS, false, C8, MINB>;
     const size_t smem = TmaSmem<KC, NSTAGE, C8>::total(NWARPS);
@@ -355,7 +370,7 @@ static int launch_tma(const heat_matrix *A, const double *x, double *y, const in
         HEAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    kern<<<grid, NWARPS * 32, smem, st>>>(A->slice_ptr.p, A->sell_col.p, A->sell_val.p, x, y, A->n_owned, slice_list,
+    kern<<<grid, NWARPS * 32, smem, st>>>(A->slice_meta.p + first, A->sell_col.p, A->sell_val.p, x, y, A->n_owned,
                                          n_list, gate, dot, SpmvPeer(), dict_of(A));
     HEAT_LAUNCHED();
     return 0;
@@ -375,11 +390,10 @@ static int launch_spmv_peer_t(const heat_matrix *A, const double *x, double *y, 
         HEAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    const bool have_list = A->slices_all.p != nullptr && A->n_ghost > 0;
-    const int64_t n_list = have_list ? A->n_int_slices + A->n_bnd_slices : A->n_slices;
-    if (!have_list) peer.n_interior = n_list;
-    kern<<<grid, NW * 32, smem, st>>>(A->slice_ptr.p, A->sell_col.p, A->sell_val.p, x, y, A->n_owned,
-                                     have_list ? A->slices_all.p : nullptr, n_list, gate, dot, peer, dict_of(A));
+    const int64_t n_list = A->n_slices;                   // slice_meta order: interior slices, then boundary slices
+    if (A->n_ghost == 0) peer.n_interior = n_list;
+    kern<<<grid, NW * 32, smem, st>>>(A->slice_meta.p, A->sell_col.p, A->sell_val.p, x, y, A->n_owned, n_list, gate, dot,
+                                     peer, dict_of(A));
     HEAT_LAUNCHED();
     return 0;
 }
@@ -389,47 +403,48 @@ int launch_spmv_peer(const heat_matrix *A, const double *x, double *y, CgGate ga
                           : launch_spmv_peer_t<false>(A, x, y, gate, dot, peer, grid, st);
 }
 
-int launch_spmv(const heat_matrix *A, const double *x, double *y, const int32_t *slice_list,
+int launch_spmv(const heat_matrix *A, const double *x, double *y, int64_t first,
                 int64_t n_list, CgGate gate, DotOut dot, int grid, cudaStream_t st) {
     if (n_list <= 0 && dot.out == nullptr) return 0;
+    const int32_t *slice_list = A->n_ghost > 0 ? A->slices_all.p + first : nullptr;      // direct-load kernel only
     const int v = spmv_variant();
     const bool d = dot.out != nullptr;
     if (A->sell_idx8.p && v == 5) {      // byte-indexed column stream (sell.cu: every slice has a small offset table)
-        if (d && dot.with_yy) return launch_tma<2, 8, 2, kC8Warps, true, 2>(A, x, y, slice_list, n_list, gate, dot, grid, st);
+        if (d && dot.with_yy) return launch_tma<2, 8, 2, kC8Warps, true, 2>(A, x, y, first, n_list, gate, dot, grid, st);
         switch (c8_cfg()) {
-            case 1: return d ? launch_tma<1, 8, 2, 8, true, 2>(A, x, y, slice_list, n_list, gate, dot, grid, st)
-                             : launch_tma<0, 8, 2, 8, true, 2>(A, x, y, slice_list, n_list, gate, dot, grid, st);
-            case 2: return d ? launch_tma<1, 8, 2, 11, true, 2>(A, x, y, slice_list, n_list, gate, dot, grid, st)
-                             : launch_tma<0, 8, 2, 11, true, 2>(A, x, y, slice_list, n_list, gate, dot, grid, st);
-            case 3: return d ? launch_tma<1, 6, 2, 12, true, 2>(A, x, y, slice_list, n_list, gate, dot, grid, st)
-                             : launch_tma<0, 6, 2, 12, true, 2>(A, x, y, slice_list, n_list, gate, dot, grid, st);
-            case 4: return d ? launch_tma<1, 6, 3, 10, true, 2>(A, x, y, slice_list, n_list, gate, dot, grid, st)
-                             : launch_tma<0, 6, 3, 10, true, 2>(A, x, y, slice_list, n_list, gate, dot, grid, st);
-            case 5: return d ? launch_tma<1, 4, 3, 10, true, 2>(A, x, y, slice_list, n_list, gate, dot, grid, st)
-                             : launch_tma<0, 4, 3, 10, true, 2>(A, x, y, slice_list, n_list, gate, dot, grid, st);
+            case 1: return d ? launch_tma<1, 8, 2, 8, true, 2>(A, x, y, first, n_list, gate, dot, grid, st)
+                             : launch_tma<0, 8, 2, 8, true, 2>(A, x, y, first, n_list, gate, dot, grid, st);
+            case 2: return d ? launch_tma<1, 8, 2, 11, true, 2>(A, x, y, first, n_list, gate, dot, grid, st)
+                             : launch_tma<0, 8, 2, 11, true, 2>(A, x, y, first, n_list, gate, dot, grid, st);
+            case 3: return d ? launch_tma<1, 6, 2, 12, true, 2>(A, x, y, first, n_list, gate, dot, grid, st)
+                             : launch_tma<0, 6, 2, 12, true, 2>(A, x, y, first, n_list, gate, dot, grid, st);
+            case 4: return d ? launch_tma<1, 6, 3, 10, true, 2>(A, x, y, first, n_list, gate, dot, grid, st)
+                             : launch_tma<0, 6, 3, 10, true, 2>(A, x, y, first, n_list, gate, dot, grid, st);
+            case 5: return d ? launch_tma<1, 4, 3, 10, true, 2>(A, x, y, first, n_list, gate, dot, grid, st)
+                             : launch_tma<0, 4, 3, 10, true, 2>(A, x, y, first, n_list, gate, dot, grid, st);
             default: break;
         }
-        return d ? launch_tma<1, 8, 2, kC8Warps, true, 2>(A, x, y, slice_list, n_list, gate, dot, grid, st)
-                 : launch_tma<0, 8, 2, kC8Warps, true, 2>(A, x, y, slice_list, n_list, gate, dot, grid, st);
+        return d ? launch_tma<1, 8, 2, kC8Warps, true, 2>(A, x, y, first, n_list, gate, dot, grid, st)
+                 : launch_tma<0, 8, 2, kC8Warps, true, 2>(A, x, y, first, n_list, gate, dot, grid, st);
     }
     if (d && dot.with_yy) {      // x.y and y.y in one pass (power method): default TMA config or direct loads
-        if (v != 0) return launch_tma<2, 8, 2, 8>(A, x, y, slice_list, n_list, gate, dot, grid, st);
+        if (v != 0) return launch_tma<2, 8, 2, 8>(A, x, y, first, n_list, gate, dot, grid, st);
         sell_spmv_kernel<2><<<grid, kBlock, 0, st>>>(A->slice_ptr.p, A->sell_col.p, A->sell_val.p, x, y,
                                                     A->n_owned, slice_list, n_list, gate, dot);
         HEAT_LAUNCHED();
         return 0;
     }
     switch (v) {
-        case 1: return d ? launch_tma<1, 16, 2, 8>(A, x, y, slice_list, n_list, gate, dot, grid, st)
-                         : launch_tma<0, 16, 2, 8>(A, x, y, slice_list, n_list, gate, dot, grid, st);
-        case 2: return d ? launch_tma<1, 8, 3, 12>(A, x, y, slice_list, n_list, gate, dot, grid, st)
-                         : launch_tma<0, 8, 3, 12>(A, x, y, slice_list, n_list, gate, dot, grid, st);
-        case 3: return d ? launch_tma<1, 8, 2, 16>(A, x, y, slice_list, n_list, gate, dot, grid, st)
-                         : launch_tma<0, 8, 2, 16>(A, x, y, slice_list, n_list, gate, dot, grid, st);
-        case 4: return d ? launch_tma<1, 4, 3, 24>(A, x, y, slice_list, n_list, gate, dot, grid, st)
-                         : launch_tma<0, 4, 3, 24>(A, x, y, slice_list, n_list, gate, dot, grid, st);
-        case 5: return d ? launch_tma<1, 8, 2, 8>(A, x, y, slice_list, n_list, gate, dot, grid, st)
-                         : launch_tma<0, 8, 2, 8>(A, x, y, slice_list, n_list, gate, dot, grid, st);
+        case 1: return d ? launch_tma<1, 16, 2, 8>(A, x, y, first, n_list, gate, dot, grid, st)
+                         : launch_tma<0, 16, 2, 8>(A, x, y, first, n_list, gate, dot, grid, st);
+        case 2: return d ? launch_tma<1, 8, 3, 12>(A, x, y, first, n_list, gate, dot, grid, st)
+                         : launch_tma<0, 8, 3, 12>(A, x, y, first, n_list, gate, dot, grid, st);
+        case 3: return d ? launch_tma<1, 8, 2, 16>(A, x, y, first, n_list, gate, dot, grid, st)
+                         : launch_tma<0, 8, 2, 16>(A, x, y, first, n_list, gate, dot, grid, st);
+        case 4: return d ? launch_tma<1, 4, 3, 24>(A, x, y, first, n_list, gate, dot, grid, st)
+                         : launch_tma<0, 4, 3, 24>(A, x, y, first, n_list, gate, dot, grid, st);
+        case 5: return d ? launch_tma<1, 8, 2, 8>(A, x, y, first, n_list, gate, dot, grid, st)
+                         : launch_tma<0, 8, 2, 8>(A, x, y, first, n_list, gate, dot, grid, st);
         default: break;
     }
     if (d)
