@@ -134,7 +134,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": scaled, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"synthetic {nx}^3-node Kuhn tet cube, P1 heat, Jacobi-PCG", "n_dof": n_full, "nnz": nnz_full,
+        "config": {"workload": f"synthetic {nx}x{nx}x{nx}-node Kuhn tet cube (P1 FEM), jacobi-PCG (cg), CPU restatement", "n_dof": n_full, "nnz": nnz_full,
                    "note": "CPU restatement of the reference path (C/OpenMP oracle); the Trilinos/Belos binary cannot be built here"},
         "cpu_baseline": {"value": scaled, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": scaled, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
