@@ -67,6 +67,32 @@ def main():
                 rec["npart"] = npart.tolist()
             met[f"{m}:{nparts}"] = rec
     gold["metis_part_mesh_dual"] = met
+    # IO::getMatrix (ExodusIO.hpp:733-1489): whole-mesh Laplacian statistics from an independent scipy
+    # assembly + its largest eigenvalue (scipy eigsh) = what ExodusMatrixTest's power method converges to;
+    # node ownership histogram of the rank-by-rank restatement for the METIS element partition
+    import scipy.sparse as sp
+    gm = {}
+    for m, ncommon in (("bolted_bracket", 3), ("mitchell_tri", 2), ("rectangle-tris", 2)):
+        mesh = O.read_exodus(f"{REF}/{m}.exo")
+        c = mesh.conn.astype(np.int64)
+        npe = c.shape[1]
+        rows = np.repeat(c, npe, axis=1).ravel()
+        cols = np.tile(c, (1, npe)).ravel()
+        keep = rows != cols
+        Adj = sp.coo_matrix((np.ones(keep.sum()), (rows[keep], cols[keep])), shape=(mesh.num_nodes,) * 2).tocsr()
+        Adj.data[:] = 1.0
+        Lap = (sp.diags(np.asarray(Adj.sum(1)).ravel()) - Adj).tocsr()
+        lmax = float(spl.eigsh(Lap, k=1, which="LA", return_eigenvectors=False, tol=1e-12)[0]) if mesh.num_nodes > 20 else \
+            float(np.linalg.eigvalsh(Lap.toarray())[-1])
+        rec = {"n": int(Lap.shape[0]), "nnz": int(Lap.nnz), "trace": float(Lap.diagonal().sum()), "lambda_max": lmax}
+        for nparts in (2, 4):
+            if c.shape[0] < 4 * nparts:
+                continue
+            _, epart, _ = O.metis_part_mesh_dual(mesh.conn, mesh.num_nodes, ncommon, nparts)
+            owners = O.get_matrix_owners(mesh.conn, epart, nparts, mesh.num_nodes)
+            rec[f"owner_hist:{nparts}"] = np.bincount(owners, minlength=nparts).tolist()
+        gm[m] = rec
+    gold["get_matrix"] = gm
     with open(os.path.join(HERE, "golden_values.json"), "w") as f:
         json.dump(gold, f, indent=1, sort_keys=True)
     print("wrote", os.path.join(HERE, "golden_values.json"))

@@ -459,7 +459,7 @@ def test_cli_driver_end_to_end(hb, oracle, tmp_path):
 
 
 @pytest.mark.parametrize("name", ["bolted_bracket", "mitchell_tri", "2blocks", "rectangle-tris"])
-def test_get_matrix_and_power_method(hb, io, oracle, name):
+def test_get_matrix_and_power_method(hb, io, oracle, golden, name):
     """IO::getMatrix + PowerMethod::run (ExodusIO.hpp:733, ExodusMatrixTest.cpp:56-129) on one GPU:
     the whole-mesh Laplacian bit-exact, lambda within 1e-10 relative, same stop iteration."""
     mesh = oracle.read_exodus(mesh_path(name))
@@ -479,6 +479,11 @@ def test_get_matrix_and_power_method(hb, io, oracle, name):
         assert (pr.iters, pr.converged) == (it, conv), (pr, it, conv)
         assert abs(pr.lambda_ - lam) <= 1e-10 * abs(lam), (pr, lam)
         assert abs(pr.residual - res) <= 1e-6 * max(res, 1e-12) + 1e-9, (pr, res)
+    if name in golden["get_matrix"]:                                # independent pin: scipy's largest eigenvalue
+        g = golden["get_matrix"][name]
+        assert (A.info.n_global, A.info.nnz_global) == (g["n"], g["nnz"])
+        pr = io.power_method(A, 2000, 1e-6, 12345)
+        assert -1e-12 * pr.lambda_ <= g["lambda_max"] - pr.lambda_ <= 1e-5 * g["lambda_max"], (pr, g["lambda_max"])
     # P1 stiffness of the whole mesh (Neumann problem): rows sum to ~0
     if mesh.conn.shape[1] in (3, 4):
         K = io.getMatrix(hb.OP_P1_FEM)

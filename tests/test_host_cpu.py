@@ -178,7 +178,7 @@ def test_partition_and_plan_bit_exact(hb, oracle, name, P):
 
 @pytest.mark.parametrize("name", ["bolted_bracket", "mitchell_tri", "2blocks", "rectangle-tris"])
 @pytest.mark.parametrize("P", [2, 4, 8])
-def test_get_matrix_node_ownership_rule(hb, oracle, name, P):
+def test_get_matrix_node_ownership_rule(hb, oracle, golden, name, P):
     """IO::getMatrix's node ownership (ExodusIO.hpp:1191-1295) from the METIS element partition: the
     host routine against the rank-by-rank restatement in the oracle."""
     mesh = oracle.read_exodus(mesh_path(name))
@@ -189,6 +189,9 @@ def test_get_matrix_node_ownership_rule(hb, oracle, name, P):
     exp = oracle.get_matrix_owners(mesh.conn, epart, P, mesh.num_nodes)
     got = hb.node_owners(mesh.conn, mesh.num_nodes, epart, P)
     np.testing.assert_array_equal(got, exp)
+    key = f"owner_hist:{P}"
+    if name in golden["get_matrix"] and key in golden["get_matrix"][name]:
+        assert np.bincount(got, minlength=P).tolist() == golden["get_matrix"][name][key]
     # a node touched by ONE part only belongs to that part
     for v in range(0, mesh.num_nodes, max(1, mesh.num_nodes // 50)):
         parts = {int(epart[e]) for e in np.flatnonzero((mesh.conn == v).any(1))}

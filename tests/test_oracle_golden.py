@@ -241,3 +241,14 @@ def test_pcg_with_ilu0_oracle(oracle):
     x, it, *_ = oracle.pcg(s, prec=oracle.PREC_ILU0, tol=1e-10, max_iters=1000)
     xj, itj, *_ = oracle.pcg(s, tol=1e-10, max_iters=1000)
     assert it < itj / 2 and np.abs(x - xj).max() <= 1e-8 * np.abs(xj).max()
+
+
+@pytest.mark.parametrize("name", ["bolted_bracket", "mitchell_tri", "rectangle-tris"])
+def test_get_matrix_matches_golden(oracle, golden, name):
+    """Whole-mesh Laplacian of IO::getMatrix against the independent scipy assembly in the golden file, and
+    the power method of ExodusMatrixTest against scipy's largest eigenvalue."""
+    g = golden["get_matrix"][name]
+    s = oracle.get_matrix(oracle.read_exodus(mesh_path(name)))
+    assert (s.n, s.nnz) == (g["n"], g["nnz"]) and s.csr().diagonal().sum() == g["trace"]
+    lam, res, it, conv = oracle.power_method(s, oracle.hash_vector(np.arange(s.n), 12345), 2000, 1e-6)
+    assert -1e-12 * lam <= g["lambda_max"] - lam <= 1e-5 * g["lambda_max"], (lam, g["lambda_max"], it)
