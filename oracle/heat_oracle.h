@@ -8,11 +8,18 @@
  *   PowerMethod::run       /root/reference/ExodusMatrixTest.cpp:56-129
  *   (IO::getMatrix's ownership rule, ExodusIO.hpp:1089-1295, is restated in oracle.py)
  *
- * PARITY STATUS: "parity unpinned" against the reference binary.  The reference cannot be
- * compiled here (needs MPI, Trilinos, ParMETIS, SEACAS-Exodus; none present, no network) and
- * ships no golden vectors, tests or outputs of its own.  The oracle is pinned instead against
+ * PARITY STATUS.
+ *   oracle_assemble / get_matrix (ExodusIO.hpp): PINNED against the reference's own code.  oracle/_ref/
+ *   ref_driver compiles /root/reference/ExodusIO.hpp, unmodified, against single-rank stand-ins for its
+ *   third-party headers (oracle/ref_shim/README.md) and runs it; what it computed on all 17 meshes of the
+ *   reference's data/ (A, B, id map, getMatrix, decompose and writeSolution records) is committed as
+ *   tests/golden/ref_pins.json and reproduced bit for bit by tests/test_reference_pins.py (this oracle has
+ *   the FIXED semantics; the one documented transformation to the reference's off-by-one is pins.apply_d1).
+ *   oracle_pcg / gmres / ilu0 / power method (Belos, Ifpack2, Tpetra: third party, absent, version
+ *   unrecorded): "parity unpinned" against a reference binary; the reference ships no golden vectors, tests
+ *   or outputs of its own.  Pinned instead against
  *   (i)   the hand-checkable 3x3 system of data/rectangle-tris-boundary.exo,
- *   (ii)  an independent numpy/scipy restatement (oracle/oracle_np.py) incl. direct solves,
+ *   (ii)  an independent numpy/scipy restatement (oracle.assemble_np) incl. sparse direct solves,
  *   (iii) the analytic P1 solution T = 550 - 90 x on data/tet-cube-heat.exo,
  *   (iv)  METIS known answers with the library the container ships.
  *

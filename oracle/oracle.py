@@ -4,9 +4,12 @@ Wraps oracle/_build/libheat_oracle.so (plain-C restatement of ExodusIO.hpp:128-7
 CG form of BelosMueLuSolver.cpp:87-139) and adds an INDEPENDENT numpy/scipy restatement
 (`assemble_np`) plus a scipy Exodus reader, used to pin the C oracle.
 
-PARITY STATUS: "parity unpinned" against the reference binary (it needs MPI + Trilinos +
-ParMETIS + SEACAS-Exodus, none of which exist in this image) — pinned against hand-checked
-systems, scipy direct solves and analytic P1 solutions instead (tests/test_oracle_*.py).
+PARITY STATUS.  Assembly / getMatrix / decompose / writeSolution (ExodusIO.hpp): PINNED against the
+reference's own code — oracle/_ref/ref_driver runs /root/reference/ExodusIO.hpp, unmodified, on one
+rank (oracle/ref_shim/README.md); its outputs on all 17 meshes of the reference's data/ are committed as
+tests/golden/ref_pins.json and reproduced bit for bit (tests/test_reference_pins.py).  The Krylov solve
+(Belos/Ifpack2, third party, absent) stays "parity unpinned" against a reference binary — pinned against
+hand-checked systems, scipy direct solves and analytic P1 solutions instead (tests/test_oracle_golden.py).
 """
 from __future__ import annotations
 

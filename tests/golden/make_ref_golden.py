@@ -1,0 +1,59 @@
+"""Regenerates tests/golden/ref_pins.json by RUNNING THE REFERENCE'S OWN CODE (run in the build container, where
+/root/reference exists): oracle/_ref/ref_driver = /root/reference/ExodusIO.hpp compiled unmodified against the
+single-rank stand-ins of oracle/ref_shim/ (see its README.md), executed in the call order of the reference's
+main() on every mesh under the reference's data/ directory.
+
+Pinned per mesh: what IO::assemble returned (A, B, the reduced->original id map, the nodeset cache), what
+IO::getMatrix returned on one rank, and everything IO::decompose + IO::writeSolution handed to the Exodus API
+for 2 and 4 partitions — as sha256 digests of the arrays (full arrays for the tiny meshes).
+
+    python tests/golden/make_ref_golden.py
+"""
+import glob
+import json
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.join(HERE, "..", "..")
+sys.path.insert(0, os.path.join(ROOT, "oracle", "ref_shim"))
+import pins as P      # noqa: E402
+import run_ref as R   # noqa: E402
+
+DATA = "/root/reference/data"
+PARTS = (2, 4)
+
+
+def pins_for(path: str) -> dict:
+    entry = {"decompose": {}}
+    for nparts in PARTS:
+        out = R.run_reference(path, nparts, get_matrix=(nparts == PARTS[0]))
+        if "assemble" not in out:
+            raise RuntimeError(f"{path}: the reference's assemble did not finish: {out['stderr']}")
+        if nparts == PARTS[0]:
+            entry["assemble"] = P.summ_assemble(out["assemble"])
+            entry["getmatrix"] = P.summ_getmatrix(out["getmatrix"]) if "getmatrix" in out else {"failed": out["stderr"].strip().splitlines()[:1]}
+        if out["returncode"] == 0 and "solution" in out:
+            entry["decompose"][str(nparts)] = P.summ_output(P.canon_from_shimdump(out["solution"]))
+        else:   # e.g. initialguess.exo: element type "TET4" is rejected by the reference's decompose
+            entry["decompose"][str(nparts)] = {"failed": [l for l in out["stderr"].strip().splitlines() if "ref_driver" not in l][:1]}
+    return entry
+
+
+def main():
+    R.build(force=True)
+    files = sorted(f for f in glob.glob(os.path.join(DATA, "*.exo")) if not f.endswith(".ref.exo"))
+    gold = {"_how": "tests/golden/make_ref_golden.py: /root/reference/ExodusIO.hpp run on one rank through oracle/_ref/ref_driver",
+            "_solution_stand_in": "x[row] = 0.25 + 0.5*row + 4096*step for writeSolution(X, step), step = 0, 1"}
+    for f in files:
+        name = os.path.basename(f)[:-4]
+        gold[name] = pins_for(f)
+        a = gold[name]["assemble"]["A"]
+        print(f"{name}: n={a['n']} rows={a['nrows']} nnz={a['nnz']} trace={a['trace']:.0f} sumB={gold[name]['assemble']['sum_B']:.0f}")
+    with open(os.path.join(HERE, "ref_pins.json"), "w") as fp:
+        json.dump(gold, fp, indent=1, sort_keys=True)
+        fp.write("\n")
+
+
+if __name__ == "__main__":
+    main()
