@@ -88,7 +88,14 @@ template <class Scalar, class LO, class GO, class Node> class MultiVector;
 
 template <class Scalar = Details::DefaultTypes::scalar_type, class LO = Details::DefaultTypes::local_ordinal_type,
           class GO = Details::DefaultTypes::global_ordinal_type, class Node = Details::DefaultTypes::node_type>
-class CrsMatrix {
+class Operator {
+   public:
+    virtual ~Operator() = default;
+};
+
+template <class Scalar = Details::DefaultTypes::scalar_type, class LO = Details::DefaultTypes::local_ordinal_type,
+          class GO = Details::DefaultTypes::global_ordinal_type, class Node = Details::DefaultTypes::node_type>
+class CrsMatrix : public Operator<Scalar, LO, GO, Node> {
    public:
     typedef Scalar scalar_type;
     typedef LO local_ordinal_type;
@@ -166,6 +173,12 @@ class MultiVector {
     Teuchos::Array<Scalar> get1dView() const { return Teuchos::Array<Scalar>(v_.begin(), v_.end()); }
     Teuchos::RCP<const map_type> getMap() const { return map_; }
     size_t getNumVectors() const { return nvec_; }
+    Teuchos::RCP<const MultiVector> getVector(size_t j) const {            // column j as a one-column copy
+        auto *v = new MultiVector(map_, 1);
+        const size_t n = map_->getNodeNumElements();
+        for (size_t i = 0; i < n; ++i) v->v_[i] = v_[j * n + i];
+        return Teuchos::RCP<const MultiVector>(std::shared_ptr<const MultiVector>(v));
+    }
     global_size_t getGlobalLength() const { return map_->getGlobalNumElements(); }
     std::vector<Scalar> &shim_data() { return v_; }
     const std::vector<Scalar> &shim_data() const { return v_; }

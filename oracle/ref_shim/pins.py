@@ -69,6 +69,17 @@ def summ_assemble(d: dict) -> dict:
     return s
 
 
+def summ_dump_text(text: str) -> dict:
+    """the "<prefix><rank>.out" file of the reference (printCrsMatrix / printMultiVector, BelosMueLuSolver.cpp:37-84)
+    with the ~usec~ time stamps removed, as mpi_output_combiner.py removes them"""
+    import re
+    lines = [re.sub(r" ~[0-9]*~$", "", l) for l in text.splitlines()]
+    s = {"lines": len(lines), "sha": hashlib.sha256("\n".join(lines).encode()).hexdigest()[:32], "head": lines[:3], "tail": lines[-2:]}
+    if len(lines) <= SMALL:
+        s["text"] = lines
+    return s
+
+
 def parse_power_log(text: str) -> dict:
     """the lines PowerMethod::run prints (ExodusMatrixTest.cpp:107-124)"""
     import re

@@ -14,6 +14,7 @@
 //
 // Outputs (record container of exodus_shim.cpp):
 //   <out_prefix>.assemble.dump        n, row ids, CSR of A (columns ascending), B, reduced->original id map, nodesets
+//   <out_prefix>.mpi-proc-0.out       A and B printed by the reference's printCrsMatrix / printMultiVector (ref_dump.cpp)
 //   <out_prefix>.getmatrix.dump       the same for getMatrix, + the power method's lambda and its printed log
 //   <out_prefix>.solution.exo.shimdump   everything create/decompose/writeSolution handed to the Exodus API
 // every header ExodusIO.hpp pulls in goes first, so that the access hack below touches ExodusIO.hpp alone
@@ -41,6 +42,8 @@
 #include <cstring>
 #include <string>
 #include <vector>
+
+bool ref_dump_system(const Teuchos::RCP<Tpetra::CrsMatrix<>> &A, const Teuchos::RCP<Tpetra::MultiVector<>> &B, const std::string &path);   // ref_dump.cpp
 
 namespace {
 
@@ -107,6 +110,8 @@ int main(int argc, char **argv) {
         rec_i32(fp, "idmap_original", mv);
         dump_nodesets(fp, io.nodeSetMap);
         std::fclose(fp);
+
+        if (!ref_dump_system(A, B, prefix + ".mpi-proc-0.out")) return 1;
 
         if (!io.create(prefix + ".solution.exo")) return 1;
         if (!io.decompose(nparts, false)) { std::fprintf(stderr, "ref_driver: decompose failed\n"); return 1; }

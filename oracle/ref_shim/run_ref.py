@@ -41,4 +41,7 @@ def run_reference(exo_path: str, nparts: int = 2, get_matrix: bool = True, timeo
         for key, suffix in (("assemble", ".assemble.dump"), ("solution", ".solution.exo.shimdump"), ("getmatrix", ".getmatrix.dump")):
             if os.path.exists(prefix + suffix):
                 out[key] = dump_exo.load(prefix + suffix)
+        if os.path.exists(prefix + ".mpi-proc-0.out"):
+            with open(prefix + ".mpi-proc-0.out") as f:
+                out["dump_text"] = f.read()
         return out

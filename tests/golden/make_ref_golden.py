@@ -3,7 +3,8 @@
 single-rank stand-ins of oracle/ref_shim/ (see its README.md), executed in the call order of the reference's
 main() on every mesh under the reference's data/ directory.
 
-Pinned per mesh: what IO::assemble returned (A, B, the reduced->original id map, the nodeset cache), what
+Pinned per mesh: what IO::assemble returned (A, B, the reduced->original id map, the nodeset cache), the text its
+printCrsMatrix / printMultiVector write for them, what
 IO::getMatrix returned on one rank, and everything IO::decompose + IO::writeSolution handed to the Exodus API
 for 2 and 4 partitions — as sha256 digests of the arrays (full arrays for the tiny meshes).
 
@@ -32,6 +33,7 @@ def pins_for(path: str) -> dict:
             raise RuntimeError(f"{path}: the reference's assemble did not finish: {out['stderr']}")
         if nparts == PARTS[0]:
             entry["assemble"] = P.summ_assemble(out["assemble"])
+            entry["dump"] = P.summ_dump_text(out["dump_text"])
             entry["getmatrix"] = P.summ_getmatrix(out["getmatrix"]) if "getmatrix" in out else {"failed": out["stderr"].strip().splitlines()[:1]}
         if out["returncode"] == 0 and "solution" in out:
             entry["decompose"][str(nparts)] = P.summ_output(P.canon_from_shimdump(out["solution"]))

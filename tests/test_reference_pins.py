@@ -69,6 +69,7 @@ def test_fixture_is_what_the_reference_computes_live(ref_pins, name):
     out = R.run_reference(os.path.join(REF_DATA, name + ".exo"), 2)
     assert out["returncode"] == 0, out["stderr"]
     assert P.summ_assemble(out["assemble"]) == ref_pins[name]["assemble"]
+    assert P.summ_dump_text(out["dump_text"]) == ref_pins[name]["dump"]
     assert P.summ_getmatrix(out["getmatrix"]) == ref_pins[name]["getmatrix"]
     assert P.summ_output(P.canon_from_shimdump(out["solution"])) == ref_pins[name]["decompose"]["2"]
 
@@ -274,6 +275,26 @@ def test_gpu_power_method_equals_reference_loop(hb, gpu_io, ref_pins, name):
         assert int(mine[0]) == ref["iter"]
         assert mine[1] == pytest.approx(ref["lambda"], rel=1e-10)
         assert mine[2] == pytest.approx(ref["residual"], rel=1e-5, abs=1e-10)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["rectangle-tris-boundary", "bolted_bracket"])
+def test_gpu_cli_dump_equals_reference_text(hb, ref_pins, name, tmp_path):
+    """`heat_solver --dump` (heat::printCrsMatrix / printMultiVector of include/ExodusIO_b200.hpp) against the text
+    the reference's own printCrsMatrix / printMultiVector wrote for its A and B (BelosMueLuSolver.cpp:37-84, compiled
+    from that file): identical line for line once the ~usec~ stamps are removed.  Both meshes have their last node
+    in a nodeset, so D1 is inactive and the reference's system is the FIXED one."""
+    import re
+    import subprocess
+    exe = os.path.join(ROOT, "domain-decomposed-pde-solver_b200", "bin", "heat_solver")
+    prefix = str(tmp_path / "mpi-proc-")
+    p = subprocess.run([exe, f"--input={mesh_path(name)}", f"--solution={tmp_path / 's.exo'}", f"--outputPrefix={prefix}", "--dump",
+                        "--iterations=5"], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr
+    text = open(prefix + "0.out").read()
+    mine = text[:text.index("[Solution: X]")]                    # the reference run has no Belos, hence no X section
+    assert all(re.search(r" ~[0-9]+~$", l) for l in mine.splitlines() if not l.startswith("["))
+    assert P.summ_dump_text(mine) == ref_pins[name]["dump"]
 
 
 @pytest.mark.gpu
