@@ -93,6 +93,38 @@ def dump(exo_path: str, out_dir: str) -> str:
     return out
 
 
+def dump_arrays(name: str, out_dir: str, x, y, z, blocks, nodesets: dict, title: str = "synthetic") -> str:
+    """Writes the container for a mesh given as arrays (no Exodus file involved): blocks = [(elem_type, conn
+    [ne, npe] 0-based), ...], nodesets = {id: 0-based nodes}.  -> path of "<out_dir>/<name>.dump"; hand the
+    reference the file name "<name>"."""
+    N = len(x)
+    ne = sum(len(c) for _, c in blocks)
+    os.makedirs(out_dir, exist_ok=True)
+    out = os.path.join(out_dir, name + ".dump")
+    with open(out, "wb") as fp:
+        _rec(fp, "title", "str", title.encode())
+        for k, val in (("num_dim", 3 if z is not None else 2), ("num_nodes", N), ("num_elem", ne), ("num_el_blk", len(blocks)),
+                       ("num_node_sets", len(nodesets)), ("num_side_sets", 0)):
+            _rec(fp, k, "i32", [val])
+        _rec(fp, "coordx", "f64", x)
+        _rec(fp, "coordy", "f64", y)
+        if z is not None:
+            _rec(fp, "coordz", "f64", z)
+        _rec(fp, "node_num_map", "i32", np.arange(1, N + 1))
+        _rec(fp, "elem_map", "i32", np.arange(1, ne + 1))
+        _rec(fp, "eb_ids", "i32", np.arange(1, len(blocks) + 1))
+        for b, (etype, conn) in enumerate(blocks, 1):
+            conn = np.asarray(conn)
+            _rec(fp, f"eb{b}_type", "str", etype.encode())
+            _rec(fp, f"eb{b}_nelem", "i32", [conn.shape[0]])
+            _rec(fp, f"eb{b}_npe", "i32", [conn.shape[1]])
+            _rec(fp, f"eb{b}_conn", "i32", conn + 1)
+        _rec(fp, "ns_ids", "i32", list(nodesets))
+        for s, (sid, nodes) in enumerate(nodesets.items(), 1):
+            _rec(fp, f"ns{s}_entries", "i32", np.asarray(nodes, dtype=np.int64) + 1)
+    return out
+
+
 def load(path: str) -> dict:
     """Reads a container (a .dump made here or a .shimdump written by the shim's ex_close)."""
     recs = {}

@@ -30,10 +30,15 @@ def build(force: bool = False) -> str:
     return DRIVER
 
 
-def run_reference(exo_path: str, nparts: int = 2, get_matrix: bool = True, timeout: int = 600) -> dict:
+def run_reference(exo_path: str, nparts: int = 2, get_matrix: bool = True, timeout: int = 600, arrays=None) -> dict:
+    """arrays = (x, y, z, blocks, nodesets) (see dump_exo.dump_arrays) runs the reference on a mesh held in memory;
+    exo_path is then only the name the reference is given."""
     build()
     with tempfile.TemporaryDirectory() as tmp:
-        dump_exo.dump(exo_path, tmp)
+        if arrays is None:
+            dump_exo.dump(exo_path, tmp)
+        else:
+            dump_exo.dump_arrays(os.path.basename(exo_path), tmp, *arrays)
         prefix = os.path.join(tmp, "out")
         cmd = [DRIVER, exo_path, prefix, str(nparts)] + ([] if get_matrix else ["--no-getmatrix"])
         p = subprocess.run(cmd, env=dict(os.environ, REF_SHIM_DUMP_DIR=tmp), capture_output=True, text=True, timeout=timeout)

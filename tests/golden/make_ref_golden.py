@@ -42,6 +42,41 @@ def pins_for(path: str) -> dict:
     return entry
 
 
+CUBES = [(5, 5, 5), (6, 4, 3), (3, 3, 9), (9, 9, 9), (17, 17, 17), (33, 17, 9)]
+# tiny meshes that exercise the corners of IO::assemble (one TETRA block, coordinates irrelevant): name -> (num_nodes, conn, nodesets)
+EDGE = {
+    "d3_single_dof": (5, [[0, 1, 2, 3], [0, 2, 3, 4]], {7: [0, 2, 3, 4]}),                  # the DOF's neighbours are all Dirichlet (D3)
+    "d3_two_dofs": (6, [[0, 1, 2, 3], [2, 3, 4, 5]], {7: [0, 2, 3, 5]}),
+    "isolated_node": (6, [[0, 1, 3, 4], [1, 3, 4, 5]], {9: [5]}),                           # node 2 is in no element
+    "empty_nodeset": (5, [[0, 1, 2, 3], [1, 2, 3, 4]], {3: [], 9: [4]}),
+    "overlapping_nodesets": (6, [[0, 1, 2, 3], [1, 2, 3, 4], [2, 3, 4, 5]], {5: [0, 5], 2: [5], 8: [0]}),   # D2
+}
+
+
+def synthetic_pins() -> dict:
+    """the reference on meshes held in memory: the Kuhn tet cubes of the benchmark family (from
+    the oracle's explicit cube mesh) and the edge cases above"""
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as O
+    O.build()
+    syn = {}
+    for dims in CUBES:
+        m = O.cube_mesh(*dims)
+        out = R.run_reference("cube.exo", 2, get_matrix=False, arrays=(m.x, m.y, m.z, [("TETRA", m.conn)], m.nodesets))
+        assert out["returncode"] == 0, out["stderr"]
+        syn["cube:%dx%dx%d" % dims] = {"assemble": P.summ_assemble(out["assemble"]),
+                                       "decompose": {"2": P.summ_output(P.canon_from_shimdump(out["solution"]))}}
+    for name, (N, conn, ns) in EDGE.items():
+        x = np.arange(N, dtype=np.float64)
+        out = R.run_reference(name + ".exo", 2, get_matrix=False, arrays=(x, 0 * x, 0 * x, [("TETRA", np.asarray(conn, dtype=np.int32))], ns))
+        assert out["returncode"] == 0, out["stderr"]
+        syn["edge:" + name] = {"mesh": {"num_nodes": N, "conn": conn, "nodesets": {str(k): v for k, v in ns.items()}},
+                               "assemble": P.summ_assemble(out["assemble"]),
+                               "decompose": {"2": P.summ_output(P.canon_from_shimdump(out["solution"]))}}
+    return syn
+
+
 def main():
     R.build(force=True)
     files = sorted(f for f in glob.glob(os.path.join(DATA, "*.exo")) if not f.endswith(".ref.exo"))
@@ -52,6 +87,8 @@ def main():
         gold[name] = pins_for(f)
         a = gold[name]["assemble"]["A"]
         print(f"{name}: n={a['n']} rows={a['nrows']} nnz={a['nnz']} trace={a['trace']:.0f} sumB={gold[name]['assemble']['sum_B']:.0f}")
+    gold["_synthetic"] = synthetic_pins()
+    print("synthetic:", ", ".join(gold["_synthetic"]))
     with open(os.path.join(HERE, "ref_pins.json"), "w") as fp:
         json.dump(gold, fp, indent=1, sort_keys=True)
         fp.write("\n")

@@ -153,6 +153,80 @@ def test_reference_rejects_tet4_blocks(ref_pins):
     assert e["assemble"]["A"] == ref_pins["bolted_bracket"]["assemble"]["A"]        # assemble takes any clique
 
 
+# ---- the reference on meshes held in memory: the benchmark's Kuhn cubes and the corners of assemble ------------------
+def _syn(ref_pins, prefix):
+    return sorted(k for k in ref_pins["_synthetic"] if k.startswith(prefix))
+
+
+with open(os.path.join(GOLDEN, "ref_pins.json")) as _f:
+    _SYN = sorted(json.load(_f)["_synthetic"])
+CUBES = [k for k in _SYN if k.startswith("cube:")]
+EDGES = [k for k in _SYN if k.startswith("edge:")]
+
+
+def _drop_rows_the_reference_never_inserts(A):
+    """SURVEY.md D3: a DOF row with no DOF neighbour never reaches insertGlobalValues (ExodusIO.hpp:380-386, :591);
+    the FIXED semantics keep its diagonal.  Rows holding only a diagonal entry are exactly those."""
+    A = A.tocsr().copy()
+    lone = np.flatnonzero(np.diff(A.indptr) == 1)
+    keep = np.ones(A.nnz, dtype=bool)
+    keep[A.indptr[lone]] = False
+    rows = np.repeat(np.arange(A.shape[0]), np.diff(A.indptr))[keep]
+    return sp.csr_matrix((A.data[keep], (rows, A.indices[keep])), shape=A.shape), lone
+
+
+@pytest.mark.parametrize("key", CUBES)
+def test_c_oracle_kuhn_cube_equals_reference(oracle, ref_pins, key):
+    """The benchmark family: the reference's own assemble on the explicit Kuhn tet cube.  The
+    last node lies on the i = nx-1 face (nodeset 100), so D1 is inactive and the reference's system IS the FIXED one."""
+    dims = tuple(int(v) for v in key[5:].split("x"))
+    s = oracle.assemble(oracle.cube_mesh(*dims), oracle.GRAPH_LAPLACIAN)
+    want = ref_pins["_synthetic"][key]["assemble"]
+    _same(P.summ_scipy(s.csr()), want["A"], CSR_KEYS)
+    assert P._arr(s.b, "<f8") == want["B"]
+    assert P._arr(s.red2orig, "<i8") == want["idmap_original"]
+
+
+def _edge_mesh(oracle, spec):
+    x = np.arange(spec["num_nodes"], dtype=np.float64)
+    ns = {int(k): np.asarray(v, dtype=np.int64) for k, v in spec["nodesets"].items()}
+    conn = np.asarray(spec["conn"], dtype=np.int32)
+    return oracle.Mesh(x, 0 * x, 0 * x, conn, ns, "TETRA", 3, [len(conn)])
+
+
+def _check_edge_against_reference(A, b, r2o, want):
+    """FIXED system (scipy A, b, reduced->original) vs the reference's: identical except for the rows the reference
+    never inserts (D3), which are also missing from its id map"""
+    ref_like, lone = _drop_rows_the_reference_never_inserts(A)
+    _same(P.summ_scipy(ref_like), want["A"], CSR_KEYS)
+    assert P._arr(b, "<f8") == want["B"]                                  # the RHS is complete in the reference too (:671-687)
+    kept = np.setdiff1d(np.arange(A.shape[0]), lone)
+    assert P._arr(kept, "<i8") == want["idmap_reduced"]
+    assert P._arr(np.asarray(r2o)[kept], "<i8") == want["idmap_original"]
+
+
+@pytest.mark.parametrize("key", EDGES)
+def test_c_oracle_edge_cases_against_reference(oracle, ref_pins, key):
+    e = ref_pins["_synthetic"][key]
+    s = oracle.assemble(_edge_mesh(oracle, e["mesh"]), oracle.GRAPH_LAPLACIAN)
+    _check_edge_against_reference(s.csr(), s.b, s.red2orig, e["assemble"])
+
+
+def test_reference_defects_seen_live(ref_pins):
+    """What the reference's writeSolution records show on the corner meshes"""
+    syn = ref_pins["_synthetic"]
+    # D3: the lone DOF (node 1) is missing from globalIDMap, so its value lands on node 0 — a nodeset node (id 7)
+    assert syn["edge:d3_single_dof"]["assemble"]["A"]["nrows"] == 0 and syn["edge:d3_single_dof"]["assemble"]["B"]["data"] == [21.0]
+    assert syn["edge:d3_single_dof"]["decompose"]["2"]["steps"][0]["data"] == [0.25, 0.0, 7.0, 7.0, 7.0]
+    # a node in no element: row 2 is never inserted, x[2] = 1.25 overwrites node 0
+    assert syn["edge:isolated_node"]["decompose"]["2"]["steps"][0]["data"] == [1.25, 0.75, 0.0, 1.75, 2.25, 9.0]
+    # D2: the RHS takes the LOWEST id of a node in several nodesets (sum_B = 21), the output field the LARGEST (8 and 5)
+    o = syn["edge:overlapping_nodesets"]
+    assert o["assemble"]["sum_B"] == 21.0 and o["decompose"]["2"]["steps"][0]["data"] == [8.0, 0.25, 0.75, 1.25, 1.75, 5.0]
+    # D7: writeSolution(X, 0) writes step 1 twice, so only two steps exist after writeSolution(X, 0), (X, 1)
+    assert o["decompose"]["2"]["times"] == [0.0, 1.0]
+
+
 # ---- decompose: the product's output file against the reference's Exodus calls --------------------------------------
 @pytest.fixture(scope="module")
 def hb():
@@ -248,6 +322,35 @@ def test_gpu_assemble_equals_reference(hb, gpu_io, oracle, ref_pins, name):
     _same(P.summ_scipy(M), want["A"], CSR_KEYS)
     assert P._arr(b, "<f8") == want["B"]
     assert P._arr(r2o, "<i8") == want["idmap_original"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("explicit", [False, True])
+@pytest.mark.parametrize("key", CUBES)
+def test_gpu_kuhn_cube_equals_reference(hb, gpu_io, ref_pins, key, explicit):
+    """The synthetic cubes of the benchmark: `cube_fill_kernel` (analytic connectivity, 24 incident tets recomputed
+    per row) and the explicit-mesh kernels, graph-Laplacian mode, against the reference's own assemble."""
+    dims = tuple(int(v) for v in key[5:].split("x"))
+    gpu_io.mesh_cube(*dims, explicit_mesh=explicit)
+    A, X, B = gpu_io.assemble(hb.OP_GRAPH_LAPLACIAN)
+    rp, col, val = A.csr()
+    n = len(rp) - 1
+    want = ref_pins["_synthetic"][key]["assemble"]
+    _same(P.summ_scipy(sp.csr_matrix((val, col, rp), shape=(n, n))), want["A"], CSR_KEYS)
+    assert P._arr(B.numpy(), "<f8") == want["B"]
+    assert P._arr(A.red2orig(), "<i8") == want["idmap_original"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("key", EDGES)
+def test_gpu_edge_cases_against_reference(hb, gpu_io, oracle, ref_pins, key):
+    e = ref_pins["_synthetic"][key]
+    m = _edge_mesh(oracle, e["mesh"])
+    gpu_io.mesh_set(m.x, m.y, m.z, m.conn, {k: v for k, v in m.nodesets.items()}, num_dim=3)
+    A, X, B = gpu_io.assemble(hb.OP_GRAPH_LAPLACIAN, hb.PART_METIS_KWAY)
+    rp, col, val = A.csr()
+    n = len(rp) - 1
+    _check_edge_against_reference(sp.csr_matrix((val, col, rp), shape=(n, n)), B.numpy(), A.red2orig(), e["assemble"])
 
 
 @pytest.mark.gpu
