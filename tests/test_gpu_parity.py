@@ -237,6 +237,55 @@ def test_full_size_256_properties(hb):
     io.close()
 
 
+def test_full_size_512_headline_config_properties(hb):
+    """BASELINE.json configs[3] on ONE GPU at FULL size — the workload bench.py times (512^3 nodes, 133.7 M DOF, 2.0 G
+    nonzeros, byte-indexed SELL stream) — through size-independent properties: the documented counts, the exact
+    discrete solution (A x* = b to rounding: one SpMV checks all 2 G matrix entries and the RHS against the analytic
+    field), linearity of the SpMV, symmetry (u.Av = v.Au), and 100 PCG iterations whose recurrence residual equals the
+    true one and which reduce the energy norm of the error."""
+    n = 512
+    io = hb.IO(0)
+    io.mesh_cube(n, n, n)
+    A, X, B = io.assemble(hb.OP_P1_FEM)
+    mi = A.info
+    assert (mi.n_global, mi.nnz_global, mi.n_owned) == (133_693_440, 1_999_132_662, 133_693_440)     # SURVEY.md §8d config 4
+    assert mi.col_index_bytes == 1                                         # the bench's column stream
+    gid = np.arange(mi.n_owned)
+    xstar = 1000.0 - 900.0 * ((gid % (n - 2)) + 1) / (n - 1)
+    del gid
+    xs, y = A.new_vector().set(xstar), A.new_vector()
+    io.spmv(A, xs, y)
+    b = B.numpy()
+    bmax = np.abs(b).max()
+    assert np.abs(y.numpy() - b).max() <= 1e-9 * bmax
+    del xstar
+    u, v = A.hash_vector(1), A.hash_vector(2)
+    yu, yv = A.new_vector(), A.new_vector()
+    io.spmv(A, u, yu); io.spmv(A, v, yv)
+    uh, vh, yuh, yvh = u.numpy(), v.numpy(), yu.numpy(), yv.numpy()
+    assert abs(np.dot(uh, yvh) - np.dot(vh, yuh)) <= 1e-10 * (np.linalg.norm(uh) * np.linalg.norm(yvh))   # symmetry
+    xs.set(2.0 * uh + 3.0 * vh)
+    io.spmv(A, xs, y)
+    rhs = 2.0 * yuh + 3.0 * yvh
+    assert np.abs(y.numpy() - rhs).max() <= 1e-12 * np.abs(rhs).max()                                       # linearity
+    del uh, vh, yuh, yvh, rhs
+    r = io.cg_iterations(A, X, B, 100, solver=hb.SOLVER_CG, prec=hb.PREC_JACOBI)
+    assert r.iters == 100
+    io.spmv(A, X, y)
+    resid = b - y.numpy()
+    res = np.linalg.norm(resid) / np.linalg.norm(b)
+    assert abs(res - r.achieved_tol) <= 1e-6 * res                         # the recurrence residual IS the true residual
+    # CG minimises the energy norm of the error over the Krylov space: ||x* - x_100||_A^2 = (x* - x).(b - A x) must have
+    # dropped below ||x*||_A^2 = x*.b (the residual 2-norm itself need not be monotone)
+    gid = np.arange(mi.n_owned)
+    err = 1000.0 - 900.0 * ((gid % (n - 2)) + 1) / (n - 1)
+    e0 = float(np.dot(err, b))
+    err -= X.numpy()
+    e100 = float(np.dot(err, resid))
+    assert 0.0 < e100 < e0, (e100, e0)
+    io.close()
+
+
 def test_full_size_256_graph_rowsums(hb):
     n = 256
     io = hb.IO(0)
