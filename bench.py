@@ -121,6 +121,23 @@ def cpu_run(sample_n, iters, steps, warmup, full_n):
     return raw * sysm.n / full_n, raw, dt * 1e3, O.num_threads(), t_asm, sysm.n, sysm.nnz
 
 
+def reference_assembly_sample(n=41):
+    """Assembly seconds of THE REFERENCE'S OWN IO::assemble (oracle/_ref/ref_driver = /root/reference/ExodusIO.hpp
+    compiled unmodified against single-rank stand-ins, oracle/ref_shim/README.md) on an n^3-node Kuhn cube, one host
+    thread — the reported CPU figure beside `assemble_ms`.  None if the binary did not travel."""
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "oracle", "ref_shim"))
+        import oracle as O
+        import run_ref as R
+        m = O.cube_mesh(n, n, n)
+        out = R.run_reference("cube.exo", 2, get_matrix=False, timeout=120, arrays=(m.x, m.y, m.z, [("TETRA", m.conn)], m.nodesets))
+        t = out["timing"]["assemble_s"]
+        return {"kind": "reference", "seconds": t, "nodes": n ** 3, "us_per_node": 1e6 * t / n ** 3, "cores": 1,
+                "sample": f"IO::assemble of the reference itself (graph Laplacian, one rank) on a {n}^3-node Kuhn tet cube"}
+    except Exception as e:      # noqa: BLE001 — a reported extra, never a reason to lose the bench line
+        return {"kind": "reference", "unavailable": f"{type(e).__name__}: {e}"[:200]}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -136,7 +153,8 @@ def run_reference(args):
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"synthetic {nx}x{nx}x{nx}-node Kuhn tet cube (P1 FEM), jacobi-PCG (cg), CPU restatement", "n_dof": n_full, "nnz": nnz_full,
                    "note": "CPU restatement of the reference path (C/OpenMP oracle); the Trilinos/Belos binary cannot be built here"},
-        "cpu_baseline": {"value": scaled, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": scaled, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                         "assembly_reference": reference_assembly_sample()},
         "e2e": {"value": scaled, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -274,7 +292,8 @@ def run_ours(args):
         cpu = {"value": scaled, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": (f"C/OpenMP restatement of the reference path on a {args.cpu_sample}^3-node cube ({n_s} DOF, P1), "
                           f"{args.cpu_iters} Jacobi-PCG iterations x2; scaled by DOF ratio to {nx}^3; raw {raw:.2f} it/s; "
-                          f"CPU assembly {t_asm:.1f} s")}
+                          f"CPU assembly {t_asm:.1f} s"),
+               "assembly_reference": reference_assembly_sample()}
 
     if rank == 0:
         metric = METRIC

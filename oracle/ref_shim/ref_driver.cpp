@@ -15,6 +15,7 @@
 // Outputs (record container of exodus_shim.cpp):
 //   <out_prefix>.assemble.dump        n, row ids, CSR of A (columns ascending), B, reduced->original id map, nodesets
 //   <out_prefix>.mpi-proc-0.out       A and B printed by the reference's printCrsMatrix / printMultiVector (ref_dump.cpp)
+//   <out_prefix>.timing               wall seconds of the reference's assemble / decompose / writeSolution / getMatrix calls
 //   <out_prefix>.getmatrix.dump       the same for getMatrix, + the power method's lambda and its printed log
 //   <out_prefix>.solution.exo.shimdump   everything create/decompose/writeSolution handed to the Exodus API
 // every header ExodusIO.hpp pulls in goes first, so that the access hack below touches ExodusIO.hpp alone
@@ -38,6 +39,7 @@
 #undef main
 #undef private
 
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -79,6 +81,8 @@ void dump_nodesets(FILE *fp, const std::map<int, std::set<idx_t>> &ns) {
     }
 }
 
+double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
 }  // namespace
 
 int main(int argc, char **argv) {
@@ -95,7 +99,13 @@ int main(int argc, char **argv) {
         if (!io.open(input, true)) return 1;
         Teuchos::RCP<Tpetra::CrsMatrix<>> A;
         Teuchos::RCP<Tpetra::MultiVector<>> X, B;
+        const double t0 = now();
         if (!io.assemble(&A, &X, &B, false)) { std::fprintf(stderr, "ref_driver: assemble failed\n"); return 1; }
+        const double t_assemble = now() - t0;
+        {
+            FILE *tf = std::fopen((prefix + ".timing").c_str(), "w");
+            if (tf) { std::fprintf(tf, "assemble_s %.6f\n", t_assemble); std::fclose(tf); }
+        }
 
         FILE *fp = std::fopen((prefix + ".assemble.dump").c_str(), "wb");
         if (!fp) return 1;
@@ -114,13 +124,17 @@ int main(int argc, char **argv) {
         if (!ref_dump_system(A, B, prefix + ".mpi-proc-0.out")) return 1;
 
         if (!io.create(prefix + ".solution.exo")) return 1;
+        const double t1 = now();
         if (!io.decompose(nparts, false)) { std::fprintf(stderr, "ref_driver: decompose failed\n"); return 1; }
+        const double t_decompose = now() - t1, t2 = now();
         // stand-in for the iterates of the Belos loop (BelosMueLuSolver.cpp:113-116): float-exact values keyed on the row id
         const auto gids = X->getMap()->getNodeElementList();
         for (int step = 0; step < 2; ++step) {
             for (int l = 0; l < gids.size(); ++l) X->shim_data()[(size_t)l] = 0.25 + 0.5 * (double)gids[l] + 4096.0 * step;
             if (!io.writeSolution(X, step, false)) return 1;
         }
+        FILE *tf = std::fopen((prefix + ".timing").c_str(), "a");
+        if (tf) { std::fprintf(tf, "decompose_s %.6f\nwrite_solution_2_steps_s %.6f\n", t_decompose, now() - t2); std::fclose(tf); }
     }   // ~IO closes both files: the shim flushes <prefix>.solution.exo.shimdump
     if (get_matrix) {
         ExodusIO::IO io;

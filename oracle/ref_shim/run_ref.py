@@ -25,8 +25,12 @@ def available() -> bool:
 
 
 def build(force: bool = False) -> str:
-    if force or not os.path.exists(DRIVER):
+    """(re)builds oracle/_ref/ref_driver where the reference's sources exist; elsewhere (the GPU box) the prebuilt
+    binary that travelled with the repo is used as it is"""
+    if available() and (force or not os.path.exists(DRIVER)):
         subprocess.run(["make", "-C", ORACLE, "ref"] + (["-B"] if force else []), check=True, capture_output=True)
+    if not os.path.exists(DRIVER):
+        raise FileNotFoundError(f"{DRIVER} is not built and /root/reference is absent")
     return DRIVER
 
 
@@ -46,6 +50,9 @@ def run_reference(exo_path: str, nparts: int = 2, get_matrix: bool = True, timeo
         for key, suffix in (("assemble", ".assemble.dump"), ("solution", ".solution.exo.shimdump"), ("getmatrix", ".getmatrix.dump")):
             if os.path.exists(prefix + suffix):
                 out[key] = dump_exo.load(prefix + suffix)
+        if os.path.exists(prefix + ".timing"):
+            with open(prefix + ".timing") as f:
+                out["timing"] = {k: float(v) for k, v in (line.split() for line in f if line.strip())}
         if os.path.exists(prefix + ".mpi-proc-0.out"):
             with open(prefix + ".mpi-proc-0.out") as f:
                 out["dump_text"] = f.read()
