@@ -265,6 +265,23 @@ def test_decompose_file_equals_reference_records(hb, ref_pins, name, parts, tmp_
     _same(got, want, OUT_KEYS)
 
 
+def test_cpp_mirror_decompose_equals_reference_records(hb, ref_pins, tmp_path):
+    """include/ExodusIO_b200.hpp — the class a maintainer swaps in for ExodusIO.hpp — compiled with g++ and driven in
+    the reference's call order on a host-only context: bool returns, failure messages, the no-CPU-fallback rule,
+    and an output file identical (as records) to what the reference's own decompose wrote."""
+    import subprocess
+    exe = str(tmp_path / "mirror_host_test")
+    libdir = os.path.dirname(hb.LIB_PATH)
+    subprocess.run(["g++", "-O1", "-std=c++17", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", "mirror_host_test.cpp"),
+                    "-o", exe, "-L", libdir, "-lheat_b200", f"-Wl,-rpath,{libdir}"], check=True, capture_output=True, text=True)
+    for name, parts in (("bolted_bracket", 2), ("rectangle-tris-boundary", 4), ("2blocks", 2)):
+        out = str(tmp_path / f"{name}.exo")
+        p = subprocess.run([exe, mesh_path(name), out, str(parts)], capture_output=True, text=True, timeout=120)
+        assert p.returncode == 0, (p.returncode, p.stderr)
+        assert "no CPU fallback" in p.stderr and "ex_open" in p.stderr          # the two expected failures were reported
+        _same(P.summ_output(P.canon_from_exodus(out)), ref_pins[name]["decompose"][str(parts)], OUT_KEYS)
+
+
 def test_write_nodal_field_equals_reference_records(hb, oracle, ref_pins, tmp_path):
     """The file half of writeSolution without a GPU: the dense nodal arrays the reference built for the stand-in
     iterates (x[row] = 0.25 + 0.5 row + 4096 step) are rebuilt here from the oracle's id map and written through
