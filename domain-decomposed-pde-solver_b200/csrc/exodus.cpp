@@ -557,6 +557,17 @@ extern "C" int heat_decompose(heat_ctx *ctx, int partitions) {
     for (const char *n : {"coordx", "coordy", "coordz", "coord", "coor_names", "elem_map", "ns_status", "ns_names",
                           "ss_status", "ss_names", "qa_records", "info_records", "node_num_map"})
         copy_var(n);
+    // ex_get_map / ex_get_node_num_map hand out the identity 1..N when the file stores no map, and the reference
+    // writes whatever it got (ExodusIO.hpp:1742-1745, :1962-1966): the output always carries both maps
+    auto identity_map = [&](const char *name, const char *dim, int64_t len) {
+        if (out.var(name) || len <= 0 || out.dim_id(dim) < 0) return;
+        std::vector<int32_t> ids((size_t)len);
+        for (int64_t i = 0; i < len; ++i) ids[(size_t)i] = (int32_t)(i + 1);
+        NcVar &v = out.add_var(name, NC_INT, {dim});
+        NcFile::put_ints(v, ids.data(), ids.size());
+    };
+    identity_map("elem_map", "num_elem", m.num_elem);
+    identity_map("node_num_map", "num_nodes", m.num_nodes);
     for (const NcVar &v : in.vars) {
         const std::string &n = v.name;
         if (n.compare(0, 7, "ns_prop") == 0 || n.compare(0, 7, "ss_prop") == 0 || n.compare(0, 7, "node_ns") == 0 ||

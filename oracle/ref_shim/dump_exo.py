@@ -64,8 +64,8 @@ def dump(exo_path: str, out_dir: str) -> str:
                 _rec(fp, nm, "f64", c[i])
         # libexodus hands out the identity when a map is not stored
         _rec(fp, "node_num_map", "i32", v["node_num_map"].data if "node_num_map" in v else np.arange(1, N + 1))
-        emap = v["elem_map"].data if "elem_map" in v else (v["elem_num_map"].data if "elem_num_map" in v else np.arange(1, ne + 1))
-        _rec(fp, "elem_map", "i32", emap)
+        # ex_get_map reads the element ORDER map "elem_map" only (not the id map "elem_num_map")
+        _rec(fp, "elem_map", "i32", v["elem_map"].data if "elem_map" in v else np.arange(1, ne + 1))
         if nblk:
             _rec(fp, "eb_ids", "i32", v["eb_prop1"].data)
         for b in range(1, nblk + 1):

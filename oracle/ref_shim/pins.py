@@ -60,6 +60,46 @@ def apply_d1(A, b):
     return out, np.asarray(b)[:n].copy()
 
 
+def rows_the_reference_inserts(conn, num_nodes: int, nodesets: dict) -> np.ndarray:
+    """a DOF row reaches insertGlobalValues only if the node has at least one neighbour that is in no
+    nodeset (ExodusIO.hpp:380-386, :591).  -> boolean per DOF node, in reduced (ascending node id) order."""
+    conn = np.asarray(conn, dtype=np.int64)
+    in_set = np.zeros(num_nodes, dtype=bool)
+    for nodes in nodesets.values():
+        in_set[np.asarray(nodes, dtype=np.int64)] = True
+    has = np.zeros(num_nodes, dtype=bool)
+    free_in_elem = (~in_set)[conn]                                   # [ne, npe]
+    nfree = free_in_elem.sum(1)
+    for a in range(conn.shape[1]):                                   # node a of an element sees the OTHER free nodes of it
+        others = nfree - free_in_elem[:, a]
+        np.logical_or.at(has, conn[:, a], others > 0)
+    return has[~in_set]
+
+
+def reference_view(A, b, r2o, conn, num_nodes: int, nodesets: dict):
+    """The FIXED system (scipy A, RHS b, reduced->original map r2o; every node outside the nodesets is a DOF, rows
+    with only Dirichlet neighbours keep their diagonal) seen through the reference's defects, i.e. what the
+    reference's own IO::assemble returns for the same mesh:
+      D3  rows of DOFs without a DOF neighbour are never inserted and have no id-map entry (B keeps its entry);
+      D1  if the last mesh node is a DOF it is dropped: apply_d1.
+    -> (A_ref, b_ref, idmap_reduced, idmap_original)"""
+    import scipy.sparse as sp
+    A = A.tocsr()
+    inserted = rows_the_reference_inserts(conn, num_nodes, nodesets)
+    n = A.shape[0]
+    assert inserted.size == n
+    rows = np.repeat(np.arange(n), np.diff(A.indptr))
+    keep = inserted[rows]
+    A = sp.csr_matrix((A.data[keep], (rows[keep], A.indices[keep])), shape=A.shape)
+    r2o = np.asarray(r2o)
+    last_is_dof = n > 0 and r2o[-1] == num_nodes - 1
+    if last_is_dof:
+        A, b = apply_d1(A, b)
+        inserted, r2o = inserted[:-1], r2o[:-1]
+    kept = np.flatnonzero(inserted)
+    return A, np.asarray(b), kept, r2o[kept]
+
+
 def summ_assemble(d: dict) -> dict:
     """d = run_reference(...)["assemble"]"""
     s = {"A": summ_csr(int(d["n"][0]), d["A_rows"], d["A_rowptr"], d["A_cols"], d["A_vals"]),

@@ -164,17 +164,6 @@ CUBES = [k for k in _SYN if k.startswith("cube:")]
 EDGES = [k for k in _SYN if k.startswith("edge:")]
 
 
-def _drop_rows_the_reference_never_inserts(A):
-    """SURVEY.md D3: a DOF row with no DOF neighbour never reaches insertGlobalValues (ExodusIO.hpp:380-386, :591);
-    the FIXED semantics keep its diagonal.  Rows holding only a diagonal entry are exactly those."""
-    A = A.tocsr().copy()
-    lone = np.flatnonzero(np.diff(A.indptr) == 1)
-    keep = np.ones(A.nnz, dtype=bool)
-    keep[A.indptr[lone]] = False
-    rows = np.repeat(np.arange(A.shape[0]), np.diff(A.indptr))[keep]
-    return sp.csr_matrix((A.data[keep], (rows, A.indices[keep])), shape=A.shape), lone
-
-
 @pytest.mark.parametrize("key", CUBES)
 def test_c_oracle_kuhn_cube_equals_reference(oracle, ref_pins, key):
     """The benchmark family: the reference's own assemble on the explicit Kuhn tet cube.  The
@@ -194,22 +183,22 @@ def _edge_mesh(oracle, spec):
     return oracle.Mesh(x, 0 * x, 0 * x, conn, ns, "TETRA", 3, [len(conn)])
 
 
-def _check_edge_against_reference(A, b, r2o, want):
-    """FIXED system (scipy A, b, reduced->original) vs the reference's: identical except for the rows the reference
-    never inserts (D3), which are also missing from its id map"""
-    ref_like, lone = _drop_rows_the_reference_never_inserts(A)
-    _same(P.summ_scipy(ref_like), want["A"], CSR_KEYS)
-    assert P._arr(b, "<f8") == want["B"]                                  # the RHS is complete in the reference too (:671-687)
-    kept = np.setdiff1d(np.arange(A.shape[0]), lone)
+def _check_edge_against_reference(A, b, r2o, mesh, want):
+    """FIXED system (scipy A, b, reduced->original) seen through the reference's defects (pins.reference_view: D3 rows
+    never inserted and absent from the id map, D1 drop of the last node) vs the reference's own output"""
+    Ar, br, kept, orig = P.reference_view(A, b, r2o, mesh.conn, mesh.num_nodes, mesh.nodesets)
+    _same(P.summ_scipy(Ar), want["A"], CSR_KEYS)
+    assert P._arr(br, "<f8") == want["B"]                                 # the RHS is complete in the reference too (:671-687)
     assert P._arr(kept, "<i8") == want["idmap_reduced"]
-    assert P._arr(np.asarray(r2o)[kept], "<i8") == want["idmap_original"]
+    assert P._arr(orig, "<i8") == want["idmap_original"]
 
 
 @pytest.mark.parametrize("key", EDGES)
 def test_c_oracle_edge_cases_against_reference(oracle, ref_pins, key):
     e = ref_pins["_synthetic"][key]
-    s = oracle.assemble(_edge_mesh(oracle, e["mesh"]), oracle.GRAPH_LAPLACIAN)
-    _check_edge_against_reference(s.csr(), s.b, s.red2orig, e["assemble"])
+    m = _edge_mesh(oracle, e["mesh"])
+    s = oracle.assemble(m, oracle.GRAPH_LAPLACIAN)
+    _check_edge_against_reference(s.csr(), s.b, s.red2orig, m, e["assemble"])
 
 
 def test_reference_defects_seen_live(ref_pins):
@@ -367,7 +356,7 @@ def test_gpu_edge_cases_against_reference(hb, gpu_io, oracle, ref_pins, key):
     A, X, B = gpu_io.assemble(hb.OP_GRAPH_LAPLACIAN, hb.PART_METIS_KWAY)
     rp, col, val = A.csr()
     n = len(rp) - 1
-    _check_edge_against_reference(sp.csr_matrix((val, col, rp), shape=(n, n)), B.numpy(), A.red2orig(), e["assemble"])
+    _check_edge_against_reference(sp.csr_matrix((val, col, rp), shape=(n, n)), B.numpy(), A.red2orig(), m, e["assemble"])
 
 
 @pytest.mark.gpu
