@@ -98,3 +98,34 @@ def test_fixed_oracles_seen_through_the_defects_equal_reference_on_random_meshes
         assert P._arr(br, "<f8") == want["B"]
         assert P._arr(kept, "<i8") == want["idmap_reduced"]
         assert P._arr(orig, "<i8") == want["idmap_original"]
+
+
+@pytest.mark.parametrize("seed", SEEDS)
+def test_get_matrix_and_power_method_equal_reference_on_random_meshes(oracle, driver, seed, tmp_path):
+    """IO::getMatrix on one rank + the reference's own PowerMethod::run.  The reference builds its row map from the
+    nodes that occur in an element (ExodusIO.hpp:1296-1305), so a node in no element has no row there; the oracle
+    keeps such a node as an all-zero row (it is never owned, cf. oracle.get_matrix_owners)."""
+    src = str(tmp_path / "m.exo")
+    parts = exo_fuzz.write_random(src, seed)
+    ref = R.run_reference(src, parts, get_matrix=True)
+    assert "getmatrix" in ref, ref["stderr"]
+    want = P.summ_getmatrix(ref["getmatrix"])
+    mesh = oracle.read_exodus(src)
+    s = oracle.get_matrix(mesh, oracle.GRAPH_LAPLACIAN)
+    used = np.zeros(mesh.num_nodes, dtype=bool)
+    used[np.unique(mesh.conn)] = True
+    A = s.csr()
+    assert all(A[i].nnz == 1 and A[i, i] == 0 for i in np.flatnonzero(~used))
+    A.eliminate_zeros()
+    got = P.summ_scipy(A, row_base=1)
+    got["n"] = int(used.sum())
+    for k in CSR_KEYS:
+        assert got[k] == want["A"][k], (k, got[k], want["A"][k])
+    for sid, nodes in mesh.nodesets.items():                      # nodeSetMap: 1-based; nodes outside every element are not listed
+        listed = np.unique(np.asarray(nodes)[used[np.asarray(nodes)]]) + 1
+        assert P._arr(listed, "<i8") == want["nodesets"].get(str(sid), P._arr([], "<i8")), sid
+    if used.all():
+        pm = want["power_method"]
+        lam, res, it, conv = oracle.power_method(s, oracle.hash_vector(np.arange(s.n), 12345), pm["niters"], pm["tolerance"])
+        assert (it, conv) == (pm["stop_iter"], pm["converged"])
+        assert lam == pytest.approx(pm["lambda"], rel=1e-9)
