@@ -319,7 +319,10 @@ def run_ours(args):
                                                           + (", byte-indexed columns)" if mi.col_index_bytes == 1 else ")"), "achieved": per_gpu_gbs, "peak": peak,
                          "unit": "GB/s", "frac": per_gpu_gbs / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": spmv_bytes(n_full, nnz_full) / world, "ms_per_launch": ms_spmv,
-                         "launches_timed": n_spmv},
+                         "launches_timed": n_spmv,
+                         # the byte-indexed format moves FEWER bytes than the algorithmic CSR figure, hence frac > 1;
+                         # the DRAM rate actually sustained = ncu traffic per launch / the launch time measured here
+                         "dram_gbs_from_traffic": (traffic / (ms_spmv * 1e-3) / 1e9) if traffic else None},
             "roofline_cg_iteration": ({"bound": "hbm", "achieved": cg_gbs_per_gpu, "peak": peak, "unit": "GB/s",
                                        "frac": cg_gbs_per_gpu / peak,
                                        "algorithmic_bytes_per_iteration": cg_iter_bytes(n_full, nnz_full) / world}
