@@ -132,17 +132,26 @@ def test_get_matrix_and_power_method_equal_reference_on_random_meshes(oracle, dr
 
 
 @pytest.mark.skipif(not os.path.isdir("/root/reference/data"), reason="needs the reference's data/ directory (build container)")
-def test_decompose_equals_reference_on_every_result_file_of_the_reference(hb, driver, tmp_path):
+def test_assemble_and_decompose_equal_reference_on_every_result_file_of_the_reference(hb, oracle, driver, tmp_path):
     """The 58 `*.ref.exo` files of the reference's data/ (Plato outputs: meshes WITH nodal / element results, time
     steps, QA records) through both decomposers.  Where the reference accepts the element type the product's file
     carries exactly the reference's records; "TET4" / "tet" blocks are rejected by the reference —
-    the product takes the upper-case "TET" prefix as tetrahedra and rejects the rest like the reference."""
+    the product takes the upper-case "TET" prefix as tetrahedra and rejects the rest like the reference.  IO::assemble
+    accepts every file: the C oracle seen through pins.reference_view equals the reference's A, B and id map on all."""
     import glob
     files = sorted(glob.glob("/root/reference/data/*.ref.exo"))
     assert len(files) >= 50
     compared = rejected_by_both = lenient = 0
     for f in files:
         ref = R.run_reference(f, 2, get_matrix=False)
+        want_asm = P.summ_assemble(ref["assemble"])
+        mesh = oracle.read_exodus(f)
+        s = oracle.assemble(mesh, oracle.GRAPH_LAPLACIAN)
+        Ar, br, kept, orig = P.reference_view(s.csr(), s.b, s.red2orig, mesh.conn, mesh.num_nodes, mesh.nodesets)
+        got_asm = P.summ_scipy(Ar)
+        for k in CSR_KEYS:
+            assert got_asm[k] == want_asm["A"][k], (os.path.basename(f), k)
+        assert P._arr(br, "<f8") == want_asm["B"] and P._arr(orig, "<i8") == want_asm["idmap_original"], os.path.basename(f)
         out = str(tmp_path / "o.exo")
         h = C.c_void_p()
         assert hb.lib().heat_ctx_create(-1, C.byref(h)) == 0
