@@ -271,6 +271,26 @@ def test_cpp_mirror_decompose_equals_reference_records(hb, ref_pins, tmp_path):
         _same(P.summ_output(P.canon_from_exodus(out)), ref_pins[name]["decompose"][str(parts)], OUT_KEYS)
 
 
+def test_cli_heat_decompose_mirrors_the_references_decompose_test(hb, ref_pins, tmp_path):
+    """bin/heat_decompose = ExodusIODecomposeTest.cpp: same flags, same messages; its output file against the records
+    of the reference's own decompose"""
+    import subprocess
+    exe = os.path.join(ROOT, "domain-decomposed-pde-solver_b200", "bin", "heat_decompose")
+    for args, msg in (([], "No input file was provided; use the '--input' parameter!"),
+                      ([f"--input={mesh_path('2blocks')}"], "No output file was provided; use the '--output' parameter!"),
+                      ([f"--input={mesh_path('2blocks')}", f"--output={tmp_path / 'x.exo'}"],
+                       "Number of partitions to decompose the mesh has not been provided; use the '--partitions' parameter!"),
+                      ([f"--input={tmp_path / 'missing.exo'}", f"--output={tmp_path / 'x.exo'}", "--partitions=2"], "Failed to open input Exodus file")):
+        p = subprocess.run([exe] + args, capture_output=True, text=True)
+        assert p.returncode != 0 and msg in p.stderr, (args, p.stderr)
+    for name, parts in (("tet-cube-heat", 4), ("mitchell_tri", 2), ("2blocks", 4)):
+        out = str(tmp_path / f"{name}.exo")
+        p = subprocess.run([exe, f"--input={mesh_path(name)}", f"--output={out}", f"--partitions={parts}", "--no-verbose"],
+                           capture_output=True, text=True, timeout=120)
+        assert p.returncode == 0, p.stderr
+        _same(P.summ_output(P.canon_from_exodus(out)), ref_pins[name]["decompose"][str(parts)], OUT_KEYS)
+
+
 def test_write_nodal_field_equals_reference_records(hb, oracle, ref_pins, tmp_path):
     """The file half of writeSolution without a GPU: the dense nodal arrays the reference built for the stand-in
     iterates (x[row] = 0.25 + 0.5 row + 4096 step) are rebuilt here from the oracle's id map and written through
@@ -384,6 +404,17 @@ def test_gpu_power_method_equals_reference_loop(hb, gpu_io, ref_pins, name):
         assert int(mine[0]) == ref["iter"]
         assert mine[1] == pytest.approx(ref["lambda"], rel=1e-10)
         assert mine[2] == pytest.approx(ref["residual"], rel=1e-5, abs=1e-10)
+
+
+@pytest.mark.gpu
+def test_gpu_cli_heat_assemble_test(hb):
+    """bin/heat_assemble_test = ExodusAssembleTest.cpp (open -> assemble, nothing else)"""
+    import subprocess
+    exe = os.path.join(ROOT, "domain-decomposed-pde-solver_b200", "bin", "heat_assemble_test")
+    p = subprocess.run([exe, f"--input={mesh_path('bolted_bracket')}", "--verbose"], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0 and "DOF rows: 3764" in p.stdout and "nnz: 46222" in p.stdout, (p.stdout, p.stderr)
+    p = subprocess.run([exe], capture_output=True, text=True)
+    assert p.returncode != 0 and "No input file was provided; use the '--input' parameter!" in p.stderr
 
 
 @pytest.mark.gpu
