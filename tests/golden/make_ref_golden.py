@@ -90,8 +90,8 @@ def main():
     gold["_synthetic"] = synthetic_pins()
     print("synthetic:", ", ".join(gold["_synthetic"]))
     with open(os.path.join(HERE, "ref_pins.json"), "w") as fp:
-        json.dump(gold, fp, indent=1, sort_keys=True)
-        fp.write("\n")
+        # one mesh per line: compact, and a regenerated fixture diffs mesh by mesh
+        fp.write("{\n" + ",\n".join(f"{json.dumps(k)}: {json.dumps(gold[k], sort_keys=True)}" for k in sorted(gold)) + "\n}\n")
 
 
 if __name__ == "__main__":
