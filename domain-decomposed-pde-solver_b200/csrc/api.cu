@@ -268,6 +268,16 @@ extern "C" int heat_ctx_set_stream(heat_ctx *ctx, void *cuda_stream) {
     return 0;
 }
 
+extern "C" int heat_ctx_set_output(heat_ctx *ctx, int word_size, int largest_nodeset_id) {
+    if (!ctx) HEAT_FAIL(2, "null ctx");
+    if (word_size != 4 && word_size != 8) HEAT_FAIL(2, "heat_ctx_set_output: word size must be 4 or 8, not %d", word_size);
+    if (ctx->write_file && ctx->write_file->nc.dim_id("num_nodes") >= 0 && word_size != ctx->out_word_size)
+        HEAT_FAIL(4, "heat_ctx_set_output: the output mesh is already written with word size %d", ctx->out_word_size);
+    ctx->out_word_size = word_size;
+    ctx->out_largest_id = largest_nodeset_id != 0;
+    return 0;
+}
+
 extern "C" int heat_close(heat_ctx *ctx) {
     if (!ctx) return 0;
     if (ctx->device >= 0) {

@@ -201,6 +201,8 @@ struct heat_ctx {
     ExoFile *write_file = nullptr;       // writeFID (ExodusIO.hpp:2083)
     std::string write_path;
     bool printed_time_zero = false;      // printedTimeZero (ExodusIO.hpp:2084)
+    int out_word_size = 8;               // Exodus word size of the output file; the reference: sizeof(real_t) (:104-105)
+    bool out_largest_id = false;         // output field of a node in several nodesets: largest id (:1983-1989) instead of the RHS's
     // state cached by assemble for writeSolution (ExodusIO.hpp:2086-2098)
     std::vector<double> node_bc;         // NaN for DOF nodes, else lowest nodeset id
     std::vector<double> node_bc_hi;      // highest nodeset id (reference output rule, :1983-1989)

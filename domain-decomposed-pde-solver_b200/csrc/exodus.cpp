@@ -185,6 +185,11 @@ std::string NcFile::get_att_string(const std::vector<NcAtt> &atts, const std::st
     return "";
 }
 void NcFile::put_doubles(NcVar &v, const double *p, size_t n) { v.type = NC_DOUBLE; v.raw.resize(n * 8); swap_copy(v.raw.data(), p, n, 8); }
+void NcFile::put_floats(NcVar &v, const double *p, size_t n) {
+    v.type = NC_FLOAT;
+    v.raw.resize(n * 4);
+    for (size_t i = 0; i < n; ++i) { const float f = (float)p[i]; swap_copy(v.raw.data() + 4 * i, &f, 1, 4); }
+}
 void NcFile::put_ints(NcVar &v, const int32_t *p, size_t n) { v.type = NC_INT; v.raw.resize(n * 4); swap_copy(v.raw.data(), p, n, 4); }
 void NcFile::put_chars(NcVar &v, const char *p, size_t n) { v.type = NC_CHAR; v.raw.assign((const uint8_t *)p, (const uint8_t *)p + n); }
 NcAtt NcFile::make_att_string(const std::string &n, const std::string &val) {
@@ -604,6 +609,18 @@ extern "C" int heat_decompose(heat_ctx *ctx, int partitions) {
         NcFile::put_ints(cv, conn.data(), conn.size());
         cv.atts.push_back(NcFile::make_att_string("elem_type", m.elem_type));
     }
+    if (ctx->out_word_size == 4) {
+        // the reference creates its output with cpu/io word size sizeof(real_t) (ExodusIO.hpp:104-105): with a METIS
+        // whose real_t is float, every floating-point record (coordinates, distribution factors, times) is float32
+        for (NcVar &v : out.vars) {
+            if (v.type != NC_DOUBLE) continue;
+            const std::vector<double> d = out.get_doubles(v);
+            NcFile::put_floats(v, d.data(), d.size());
+        }
+    }
+    for (NcAtt &a : out.gatts)
+        if (a.name == "floating_point_word_size") a = NcFile::make_att_int("floating_point_word_size", ctx->out_word_size);
+    if (!out.gatt("floating_point_word_size")) out.gatts.push_back(NcFile::make_att_int("floating_point_word_size", ctx->out_word_size));
     out.numrecs = 0;
     ctx->write_file->nc = std::move(out);
     ctx->write_file->have_results = false;
@@ -635,7 +652,8 @@ extern "C" int heat_nodal_field(heat_ctx *ctx, const heat_vector *X, double *fie
     int64_t r = 0;
     for (int64_t g = 0; g < m.num_nodes; ++g) {
         const double bc = ctx->node_bc[(size_t)g];
-        field[g] = std::isnan(bc) ? xg[(size_t)r++] : bc;       // nodeset node = its id (lowest id, as the RHS; D2)
+        // nodeset node = its id: the one the RHS used (lowest, D2 fixed) or, on request, the largest as the reference writes
+        field[g] = std::isnan(bc) ? xg[(size_t)r++] : (ctx->out_largest_id ? ctx->node_bc_hi[(size_t)g] : bc);
     }
     return 0;
 }
@@ -677,25 +695,34 @@ extern "C" int heat_write_nodal_field(heat_ctx *ctx, const double *field_host, i
         strncpy(nm.data(), var_name, (size_t)len_name - 1);
         NcVar &nv = nc.add_var("name_nod_var", NC_CHAR, {"num_nod_var", "len_name"});
         NcFile::put_chars(nv, nm.data(), nm.size());
-        NcVar &vv = nc.add_var("vals_nod_var1", NC_DOUBLE, {"time_step", "num_nodes"});
+        const int real_type = ctx->out_word_size == 4 ? NC_FLOAT : NC_DOUBLE;
+        NcVar &vv = nc.add_var("vals_nod_var1", real_type, {"time_step", "num_nodes"});
         vv.is_record = true;
         NcVar *tw = nc.var("time_whole");
-        if (!tw) { tw = &nc.add_var("time_whole", NC_DOUBLE, {"time_step"}); }
-        tw->is_record = true; tw->type = NC_DOUBLE; tw->raw.clear();
+        if (!tw) { tw = &nc.add_var("time_whole", real_type, {"time_step"}); }
+        tw->is_record = true; tw->type = real_type; tw->raw.clear();
         nc.numrecs = 0;
         ctx->printed_time_zero = true;
     }
     NcVar *tw = nc.var("time_whole");
     NcVar *vv = nc.var("vals_nod_var1");
     const int64_t step = (int64_t)timestep + 1;                 // 1-based Exodus step (:2043, :2056)
+    const int64_t ws = nc_type_size(vv->type);                  // 8, or 4 when the file is written as the reference does (D6)
     if (step > nc.numrecs) {
-        tw->raw.resize((size_t)(step * 8), 0);
-        vv->raw.resize((size_t)(step * N * 8), 0);
+        tw->raw.resize((size_t)(step * ws), 0);
+        vv->raw.resize((size_t)(step * N * ws), 0);
         nc.numrecs = step;
     }
     const double t = (double)timestep;
-    swap_copy(tw->raw.data() + (step - 1) * 8, &t, 1, 8);
-    swap_copy(vv->raw.data() + (step - 1) * N * 8, field, (size_t)N, 8);
+    if (ws == 8) {
+        swap_copy(tw->raw.data() + (step - 1) * 8, &t, 1, 8);
+        swap_copy(vv->raw.data() + (step - 1) * N * 8, field, (size_t)N, 8);
+    } else {
+        const float tf = (float)t;                              // real_t t = (real_t) timestep (:2042)
+        swap_copy(tw->raw.data() + (step - 1) * 4, &tf, 1, 4);
+        uint8_t *dst = vv->raw.data() + (step - 1) * N * 4;
+        for (int64_t g = 0; g < N; ++g) { const float f = (float)field[g]; swap_copy(dst + 4 * g, &f, 1, 4); }
+    }
     wf.steps_written = nc.numrecs;
     // the first result call lays the file out again (new dimension + variables: ex_put_variable_param);
     // later calls only touch the record they write, like ex_put_var (:2056)

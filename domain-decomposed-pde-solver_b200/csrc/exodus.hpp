@@ -44,6 +44,7 @@ struct NcFile {
     std::vector<int64_t> get_ints(const NcVar &v) const;
     std::string get_att_string(const std::vector<NcAtt> &atts, const std::string &n) const;
     static void put_doubles(NcVar &v, const double *p, size_t n);
+    static void put_floats(NcVar &v, const double *p, size_t n);      // stored as NC_FLOAT (rounded to float32)
     static void put_ints(NcVar &v, const int32_t *p, size_t n);
     static void put_chars(NcVar &v, const char *p, size_t n);
     static NcAtt make_att_string(const std::string &n, const std::string &val);

@@ -62,7 +62,7 @@ class PlanSizes(C.Structure):
 
 # every symbol include/heat_b200.h declares (tests check the .so exports all of them)
 ABI_SYMBOLS = [
-    "heat_last_error", "heat_version", "heat_device_count", "heat_kernel_launches", "heat_ctx_create", "heat_ctx_set_stream", "heat_open",
+    "heat_last_error", "heat_version", "heat_device_count", "heat_kernel_launches", "heat_ctx_create", "heat_ctx_set_stream", "heat_ctx_set_output", "heat_open",
     "heat_create", "heat_close", "heat_mesh_set", "heat_mesh_cube", "heat_mesh_nodeset_ids", "heat_comm_unique_id", "heat_comm_init",
     "heat_comm_rank", "heat_assemble", "heat_get_matrix", "heat_node_owners", "heat_matrix_owned_nodeset", "heat_power_method", "heat_solve_opts_default", "heat_solve", "heat_solve_trajectory", "heat_solve_host", "heat_spmv",
     "heat_cg_iterations", "heat_decompose", "heat_write_solution", "heat_write_nodal_field", "heat_nodal_field", "heat_decompose_partition",
@@ -89,6 +89,7 @@ def lib():
     L.heat_kernel_launches.restype = C.c_ulonglong
     L.heat_ctx_create.argtypes = [C.c_int, C.POINTER(vp)]
     L.heat_ctx_set_stream.argtypes = [vp, vp]
+    L.heat_ctx_set_output.argtypes = [vp, C.c_int, C.c_int]
     L.heat_open.argtypes = [vp, C.c_char_p, C.c_int]
     L.heat_create.argtypes = [vp, C.c_char_p]
     L.heat_close.argtypes = [vp]
@@ -318,6 +319,11 @@ class IO:
         """cudaStream_t as an int, or a torch.cuda.Stream."""
         s = getattr(stream, "cuda_stream", stream)
         _check(lib().heat_ctx_set_stream(self.h, C.c_void_p(int(s))))
+
+    def set_output(self, word_size: int = 8, largest_nodeset_id: bool = False):
+        """output conventions of a reference build: float32 records (real_t = float, ExodusIO.hpp:104-105) and the
+        largest nodeset id in the written field (:1983-1989)"""
+        _check(lib().heat_ctx_set_output(self.h, int(word_size), int(bool(largest_nodeset_id))))
 
     @staticmethod
     def comm_unique_id() -> bytes:

@@ -11,6 +11,7 @@ int main(int argc, char *argv[]) {
     std::string inputFile, outputFile;
     size_t numPartitions = 0;
     bool verbose = false;
+    heat::Options opt;
     for (int i = 1; i < argc; ++i) {
         const std::string a = argv[i];
         if (a.compare(0, 8, "--input=") == 0) inputFile = a.substr(8);
@@ -18,6 +19,7 @@ int main(int argc, char *argv[]) {
         else if (a.compare(0, 13, "--partitions=") == 0) numPartitions = (size_t)std::strtoull(a.c_str() + 13, nullptr, 10);
         else if (a == "--verbose") verbose = true;
         else if (a == "--no-verbose") verbose = false;
+        else if (a == "--real4") opt.output_word_size = 4;                       // float32 output like a float-real_t reference build
         else { std::cerr << "unknown option '" << a << "'" << std::endl; return EXIT_FAILURE; }
     }
     if (inputFile.empty()) {
@@ -32,7 +34,6 @@ int main(int argc, char *argv[]) {
         std::cerr << "Number of partitions to decompose the mesh has not been provided; use the '--partitions' parameter!" << std::endl;
         return EXIT_FAILURE;
     }
-    heat::Options opt;
     opt.device = -1;                       // host-only context
     ExodusIO::IO io(opt);
     if (!io.open(inputFile, true)) {

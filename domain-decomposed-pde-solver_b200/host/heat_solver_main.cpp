@@ -55,6 +55,8 @@ int main(int argc, char *argv[]) {
         else if (a == "--verbose") verbose = true;
         else if (a == "--no-verbose") verbose = false;
         else if (a == "--dump") dump = true;
+        else if (a == "--real4") opt.output_word_size = 4;                       // float32 output like a float-real_t reference build
+        else if (a == "--reference-output") { opt.output_word_size = 4; opt.output_largest_nodeset_id = true; }
         else { std::cerr << "unknown option '" << a << "'" << std::endl; return EXIT_FAILURE; }
     }
     if (inputFile.empty()) {

@@ -44,6 +44,8 @@ struct Options {                 // knobs the reference hard-codes (ExodusIO.hpp
     double cheb_lambda_max = 0.0;
     int write_every = 0;         // 0: write the final field only; k: every k iterations (the reference: 1)
     int gmres_restart = 300;     // HEAT_SOLVER_GMRES: Belos "Num Blocks"
+    int output_word_size = 8;    // 4: write float32 records like a reference built on a float real_t METIS (ExodusIO.hpp:104-105)
+    bool output_largest_nodeset_id = false;   // nodes in several nodesets: largest id in the output field (:1983-1989)
     bool literal_loop = false;   // reproduce the reference's loop literally: numIterations solves with
                                  // "Maximum Iterations" = 1, field written after each (BelosMueLuSolver.cpp:102,113-133)
 };
@@ -56,6 +58,7 @@ class IO {
    public:
     explicit IO(const heat::Options &opt = heat::Options()) : opt_(opt) {
         if (heat_ctx_create(opt.device, &ctx_)) std::cerr << "heat_ctx_create: " << heat_last_error() << std::endl;
+        else if (heat_ctx_set_output(ctx_, opt.output_word_size, opt.output_largest_nodeset_id ? 1 : 0)) perror_("heat_ctx_set_output");
     }
     IO(const IO &) = delete;
     IO &operator=(const IO &) = delete;

@@ -58,6 +58,14 @@ unsigned long long heat_kernel_launches(void);
 /* ---- lifecycle: IO() / open / create / ~IO  (ExodusIO.hpp:85, :88-100, :103-114, :2072-2079) */
 int  heat_ctx_create(int device, heat_ctx **out);
 int  heat_ctx_set_stream(heat_ctx *ctx, void *cuda_stream);   /* cudaStream_t; default: own stream */
+/* Output conventions of a particular reference BUILD (defaults 8 / 0 = fp64 records, defect D2 fixed):
+ *   word_size 4           the reference opens and creates its files with cpu/io word size sizeof(real_t)
+ *                         (ExodusIO.hpp:89-90, :104-105); with a METIS whose real_t is float — the usual build —
+ *                         coordinates, distribution factors, time values and nodal results are written as float32.
+ *   largest_nodeset_id!=0 a node that belongs to several nodesets shows the LARGEST id in the written field, as the
+ *                         reference's writeSolution does (:1983-1989), instead of the id its right-hand side used.
+ * Call before heat_decompose.  Pure host state.                                                                   */
+int  heat_ctx_set_output(heat_ctx *ctx, int word_size, int largest_nodeset_id);
 int  heat_open(heat_ctx *ctx, const char *path, int read_only);
 int  heat_create(heat_ctx *ctx, const char *path);
 int  heat_close(heat_ctx *ctx);                               /* closes files, frees everything   */

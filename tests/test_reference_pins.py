@@ -271,6 +271,38 @@ def test_cpp_mirror_decompose_equals_reference_records(hb, ref_pins, tmp_path):
         _same(P.summ_output(P.canon_from_exodus(out)), ref_pins[name]["decompose"][str(parts)], OUT_KEYS)
 
 
+@pytest.mark.parametrize("name", [n for n in _all_meshes() if n != "initialguess"])
+def test_real4_output_is_the_reference_builds_file(hb, ref_pins, name, tmp_path):
+    """heat_ctx_set_output(ctx, 4, ...): the reference creates its output with word size sizeof(real_t) = 4 on the usual
+    METIS build (ExodusIO.hpp:104-105).  With that convention the product's file holds float32 records
+    that equal the reference's WITHOUT any cast on our side, and it still opens with the product's own reader."""
+    from scipy.io import netcdf_file
+    io = _host_io(hb)
+    out = str(tmp_path / "solution.exo")
+    try:
+        with pytest.raises(hb.HeatError, match="word size must be 4 or 8"):
+            io.set_output(5)
+        io.set_output(4)
+        io.open(_path(name), True)
+        io.create(out)
+        io.decompose(2)
+        with pytest.raises(hb.HeatError, match="already written with word size 4"):
+            io.set_output(8)
+    finally:
+        io.close()
+    nc = netcdf_file(out, "r", mmap=False)
+    assert nc.floating_point_word_size == 4
+    floats = [v for v in nc.variables.values() if v.data.dtype.kind == "f"]
+    assert floats and all(v.data.dtype.itemsize == 4 for v in floats)
+    nc.close()
+    _same(P.summ_output(P.canon_from_exodus(out)), ref_pins[name]["decompose"]["2"], OUT_KEYS)
+    again = _host_io(hb)
+    try:
+        again.open(out, True)                                     # float32 coordinates read back by the product's reader
+    finally:
+        again.close()
+
+
 def test_cli_heat_decompose_mirrors_the_references_decompose_test(hb, ref_pins, tmp_path):
     """bin/heat_decompose = ExodusIODecomposeTest.cpp: same flags, same messages; its output file against the records
     of the reference's own decompose"""
@@ -283,15 +315,16 @@ def test_cli_heat_decompose_mirrors_the_references_decompose_test(hb, ref_pins, 
                       ([f"--input={tmp_path / 'missing.exo'}", f"--output={tmp_path / 'x.exo'}", "--partitions=2"], "Failed to open input Exodus file")):
         p = subprocess.run([exe] + args, capture_output=True, text=True)
         assert p.returncode != 0 and msg in p.stderr, (args, p.stderr)
-    for name, parts in (("tet-cube-heat", 4), ("mitchell_tri", 2), ("2blocks", 4)):
+    for name, parts, extra in (("tet-cube-heat", 4, []), ("mitchell_tri", 2, ["--real4"]), ("2blocks", 4, [])):
         out = str(tmp_path / f"{name}.exo")
-        p = subprocess.run([exe, f"--input={mesh_path(name)}", f"--output={out}", f"--partitions={parts}", "--no-verbose"],
+        p = subprocess.run([exe, f"--input={mesh_path(name)}", f"--output={out}", f"--partitions={parts}", "--no-verbose"] + extra,
                            capture_output=True, text=True, timeout=120)
         assert p.returncode == 0, p.stderr
         _same(P.summ_output(P.canon_from_exodus(out)), ref_pins[name]["decompose"][str(parts)], OUT_KEYS)
 
 
-def test_write_nodal_field_equals_reference_records(hb, oracle, ref_pins, tmp_path):
+@pytest.mark.parametrize("word_size", [8, 4])
+def test_write_nodal_field_equals_reference_records(hb, oracle, ref_pins, tmp_path, word_size):
     """The file half of writeSolution without a GPU: the dense nodal arrays the reference built for the stand-in
     iterates (x[row] = 0.25 + 0.5 row + 4096 step) are rebuilt here from the oracle's id map and written through
     the product; variable name, time values and both records must equal what the reference gave ex_put_*.
@@ -302,6 +335,7 @@ def test_write_nodal_field_equals_reference_records(hb, oracle, ref_pins, tmp_pa
     io = _host_io(hb)
     out = str(tmp_path / "solution.exo")
     try:
+        io.set_output(word_size)
         io.open(mesh_path(name), True)
         io.create(out)
         io.decompose(2)
@@ -311,7 +345,9 @@ def test_write_nodal_field_equals_reference_records(hb, oracle, ref_pins, tmp_pa
             io.write_nodal_field(field, step)
     finally:
         io.close()
-    got = P.summ_output(P.canon_from_exodus(out))
+    canon = P.canon_from_exodus(out)
+    assert all(np.asarray(a).dtype.itemsize == word_size for a in canon["steps"])
+    got = P.summ_output(canon)
     want = ref_pins[name]["decompose"]["2"]
     _same(got, want, ("var_names", "times", "steps"))
     assert want["steps"][1]["data"] == [50.0, 50.0, 4096.25, 4096.75, 50.0, 4097.25, 200.0, 200.0, 200.0]
@@ -404,6 +440,25 @@ def test_gpu_power_method_equals_reference_loop(hb, gpu_io, ref_pins, name):
         assert int(mine[0]) == ref["iter"]
         assert mine[1] == pytest.approx(ref["lambda"], rel=1e-10)
         assert mine[2] == pytest.approx(ref["residual"], rel=1e-5, abs=1e-10)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["bolted_bracket", "rectangle-tris-boundary"])
+def test_gpu_reference_output_conventions_give_the_references_file(hb, gpu_io, ref_pins, name, tmp_path):
+    """set_output(4, largest_nodeset_id=True) + the reference's call order: where D1 is inactive (last node in a
+    nodeset) the WHOLE output file — mesh, float32 records, both result steps, the 32 nodes of bolted_bracket that sit
+    in two nodesets included — equals what the reference handed to the Exodus API, with no exception list."""
+    out = str(tmp_path / "solution.exo")
+    gpu_io.set_output(4, True)
+    gpu_io.open(mesh_path(name), True)
+    A, X, B = gpu_io.assemble(hb.OP_GRAPH_LAPLACIAN, hb.PART_METIS_KWAY)
+    gpu_io.create(out)
+    gpu_io.decompose(2)
+    for step in (0, 1):
+        X.set(0.25 + 0.5 * np.arange(len(X)) + 4096.0 * step)
+        gpu_io.writeSolution(X, step)
+    gpu_io.close()
+    _same(P.summ_output(P.canon_from_exodus(out)), ref_pins[name]["decompose"]["2"], OUT_KEYS + ("var_names", "times", "steps"))
 
 
 @pytest.mark.gpu
