@@ -40,7 +40,7 @@ static void slab_range(int nz, int P, int r, int &k0, int &k1) {
 }
 
 // node_bc from nodesets: lowest id wins (RHS rule, ExodusIO.hpp:676-681); hi = highest id (:1983-1989)
-static void build_node_bc(heat_ctx *ctx) {
+void build_node_bc(heat_ctx *ctx) {
     const HostMesh &m = ctx->mesh;
     const double nanv = std::numeric_limits<double>::quiet_NaN();
     ctx->node_bc.assign((size_t)m.num_nodes, nanv);

@@ -209,3 +209,7 @@ struct heat_ctx {
     int64_t n_global = 0;
     std::vector<int64_t> owned_gids;     // reduced global ids of this rank's rows (globalIDMap keys, :2092-2098)
 };
+
+// node_bc / node_bc_hi of the context's mesh from its nodesets (api.cu); host only
+namespace heat { void build_node_bc(heat_ctx *ctx); }
+

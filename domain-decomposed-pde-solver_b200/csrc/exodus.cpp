@@ -627,6 +627,41 @@ extern "C" int heat_decompose(heat_ctx *ctx, int partitions) {
     return nc_write(ctx->write_file->path, ctx->write_file->nc);
 }
 
+// The scatter half of writeSolution (ExodusIO.hpp:1981-1989 + :2045-2055): solution in reduced-id order -> dense nodal
+// array, nodeset nodes = their id.  Pure host code.
+static int scatter_reduced(heat_ctx *ctx, const double *xg, int64_t n, double *field) {
+    const HostMesh &m = ctx->mesh;
+    if (m.is_cube) {
+        if (n != (int64_t)(m.nx - 2) * m.ny * m.nz) HEAT_FAIL(2, "nodal field: the mesh has %lld unknowns, the vector %lld", (long long)((int64_t)(m.nx - 2) * m.ny * m.nz), (long long)n);
+        int64_t r = 0;
+        for (int64_t g = 0; g < m.num_nodes; ++g) {
+            const int i = (int)(g % m.nx);
+            field[g] = (i == 0) ? 1000.0 : (i == m.nx - 1) ? 100.0 : xg[(size_t)r++];
+        }
+        return 0;
+    }
+    if ((int64_t)ctx->node_bc.size() != m.num_nodes) heat::build_node_bc(ctx);
+    int64_t ndof = 0;
+    for (int64_t g = 0; g < m.num_nodes; ++g) ndof += std::isnan(ctx->node_bc[(size_t)g]) ? 1 : 0;
+    if (ndof != n) HEAT_FAIL(2, "nodal field: the mesh has %lld unknowns, the vector %lld", (long long)ndof, (long long)n);
+    int64_t r = 0;
+    for (int64_t g = 0; g < m.num_nodes; ++g) {
+        const double bc = ctx->node_bc[(size_t)g];
+        // nodeset node = its id: the one the RHS used (lowest, D2 fixed) or, on request, the largest as the reference writes
+        field[g] = std::isnan(bc) ? xg[(size_t)r++] : (ctx->out_largest_id ? ctx->node_bc_hi[(size_t)g] : bc);
+    }
+    return 0;
+}
+
+extern "C" int heat_scatter_nodal_field(heat_ctx *ctx, const double *x_reduced_host, int64_t n_global, double *field_host,
+                                        int64_t num_nodes) {
+    if (!ctx || !x_reduced_host || !field_host) HEAT_FAIL(2, "heat_scatter_nodal_field: null argument");
+    const HostMesh &m = ctx->mesh;
+    if (!m.valid) HEAT_FAIL(4, "heat_scatter_nodal_field: no mesh");
+    if (num_nodes != m.num_nodes) HEAT_FAIL(2, "heat_scatter_nodal_field: field must hold num_nodes = %lld values", (long long)m.num_nodes);
+    return scatter_reduced(ctx, x_reduced_host, n_global, field_host);
+}
+
 // dense nodal field on rank 0 (ExodusIO.hpp:1981-1989 + :2045-2055); other ranks send their rows
 extern "C" int heat_nodal_field(heat_ctx *ctx, const heat_vector *X, double *field, int64_t num_nodes) {
     if (!ctx || !X) HEAT_FAIL(2, "heat_nodal_field: null argument");
@@ -641,21 +676,7 @@ extern "C" int heat_nodal_field(heat_ctx *ctx, const heat_vector *X, double *fie
     HEAT_TRY(heat::comm_gather_reduced(ctx, xl, ctx->n_global, xg));           // rank 0: x in reduced-id order
     if (ctx->rank != 0) return 0;
     if (!field || num_nodes != m.num_nodes) HEAT_FAIL(2, "heat_nodal_field: field must hold num_nodes = %lld values", (long long)m.num_nodes);
-    if (m.is_cube) {
-        int64_t r = 0;
-        for (int64_t g = 0; g < m.num_nodes; ++g) {
-            const int i = (int)(g % m.nx);
-            field[g] = (i == 0) ? 1000.0 : (i == m.nx - 1) ? 100.0 : xg[(size_t)r++];
-        }
-        return 0;
-    }
-    int64_t r = 0;
-    for (int64_t g = 0; g < m.num_nodes; ++g) {
-        const double bc = ctx->node_bc[(size_t)g];
-        // nodeset node = its id: the one the RHS used (lowest, D2 fixed) or, on request, the largest as the reference writes
-        field[g] = std::isnan(bc) ? xg[(size_t)r++] : (ctx->out_largest_id ? ctx->node_bc_hi[(size_t)g] : bc);
-    }
-    return 0;
+    return scatter_reduced(ctx, xg.data(), (int64_t)xg.size(), field);
 }
 
 // IO::writeSolution (ExodusIO.hpp:1972-2070): nodal variable "Steady-State Heat Solution",

@@ -65,7 +65,7 @@ ABI_SYMBOLS = [
     "heat_last_error", "heat_version", "heat_device_count", "heat_kernel_launches", "heat_ctx_create", "heat_ctx_set_stream", "heat_ctx_set_output", "heat_open",
     "heat_create", "heat_close", "heat_mesh_set", "heat_mesh_cube", "heat_mesh_nodeset_ids", "heat_comm_unique_id", "heat_comm_init",
     "heat_comm_rank", "heat_assemble", "heat_get_matrix", "heat_node_owners", "heat_matrix_owned_nodeset", "heat_power_method", "heat_solve_opts_default", "heat_solve", "heat_solve_trajectory", "heat_solve_host", "heat_spmv",
-    "heat_cg_iterations", "heat_decompose", "heat_write_solution", "heat_write_nodal_field", "heat_nodal_field", "heat_decompose_partition",
+    "heat_cg_iterations", "heat_decompose", "heat_write_solution", "heat_write_nodal_field", "heat_nodal_field", "heat_scatter_nodal_field", "heat_decompose_partition",
     "heat_matrix_get_info", "heat_matrix_export_csr", "heat_matrix_export_maps", "heat_matrix_export_plan",
     "heat_matrix_export_red2orig", "heat_matrix_export_ilu0", "heat_matrix_free", "heat_vector_create", "heat_vector_size",
     "heat_vector_device_ptr", "heat_vector_set", "heat_vector_get", "heat_vector_fill", "heat_vector_fill_hash",
@@ -115,6 +115,7 @@ def lib():
     L.heat_decompose.argtypes = [vp, C.c_int]
     L.heat_write_solution.argtypes = [vp, vp, C.c_int]
     L.heat_nodal_field.argtypes = [vp, vp, dp, C.c_int64]
+    L.heat_scatter_nodal_field.argtypes = [vp, dp, C.c_int64, dp, C.c_int64]
     L.heat_write_nodal_field.argtypes = [vp, dp, C.c_int64, C.c_int]
     L.heat_decompose_partition.argtypes = [vp, C.c_int, i64p, i64p, i64p]
     L.heat_matrix_get_info.argtypes = [vp, C.POINTER(MatrixInfo)]
@@ -416,6 +417,13 @@ class IO:
         f = np.ascontiguousarray(field, dtype=np.float64)
         _check(lib().heat_write_nodal_field(self.h, _ptr(f, C.c_double), f.size, timestep))
         return True
+
+    def scatter_nodal_field(self, x_reduced, num_nodes: int) -> np.ndarray:
+        """host solution in reduced-id order -> dense nodal array (nodeset nodes = their id); no GPU involved"""
+        x = np.ascontiguousarray(x_reduced, dtype=np.float64)
+        out = np.empty(max(num_nodes, 1), dtype=np.float64)
+        _check(lib().heat_scatter_nodal_field(self.h, _ptr(x, C.c_double), x.size, _ptr(out, C.c_double), num_nodes))
+        return out[:num_nodes]
 
     def nodal_field(self, vec: Vector, num_nodes: int) -> np.ndarray:
         out = np.empty(num_nodes, dtype=np.float64)

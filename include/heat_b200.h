@@ -177,6 +177,11 @@ int  heat_write_solution(heat_ctx *ctx, const heat_vector *X, int timestep);   /
 int  heat_write_nodal_field(heat_ctx *ctx, const double *field_host, int64_t num_nodes, int timestep);
 /* dense nodal field writeSolution would store (DOF nodes from X, nodeset nodes = their id)       */
 int  heat_nodal_field(heat_ctx *ctx, const heat_vector *X, double *field_host, int64_t num_nodes);
+/* the scatter half alone, for a solution held on the HOST in reduced-id order (what heat_solve_host returns on one
+ * rank, heat_matrix_export_red2orig gives the order): with heat_write_nodal_field it completes the host-buffer path
+ * solve -> field -> file without a device vector.  Pure host code.                                  */
+int  heat_scatter_nodal_field(heat_ctx *ctx, const double *x_reduced_host, int64_t n_global, double *field_host,
+                              int64_t num_nodes);
 /* METIS_PartMeshDual with the reference's arguments (ExodusIO.hpp:1615); arrays are int64        */
 int  heat_decompose_partition(heat_ctx *ctx, int partitions, int64_t *objval, int64_t *epart_host,
                               int64_t *npart_host);

@@ -353,6 +353,48 @@ def test_write_nodal_field_equals_reference_records(hb, oracle, ref_pins, tmp_pa
     assert want["steps"][1]["data"] == [50.0, 50.0, 4096.25, 4096.75, 50.0, 4097.25, 200.0, 200.0, 200.0]
 
 
+@pytest.mark.parametrize("name", [n for n in _all_meshes() if n != "initialguess"])
+def test_host_scatter_and_write_give_the_references_whole_file(hb, oracle, ref_pins, name, tmp_path):
+    """The host-buffer path solution -> nodal field -> file (heat_scatter_nodal_field + heat_write_nodal_field, the code
+    heat_write_solution runs after its gather) under the reference's output conventions (float32, largest nodeset id):
+    mesh, both result steps, times and variable name equal the reference's records on every mesh.  Where D1 is active
+    the reference has no row for the last node and leaves its value 0; that one value is zeroed here, nothing else."""
+    mesh = oracle.read_exodus(_path(name))
+    n = ref_pins[name]["assemble"]["A"]["n"] + (1 if _d1_active(mesh) else 0)             # FIXED number of unknowns
+    io = _host_io(hb)
+    out = str(tmp_path / "solution.exo")
+    try:
+        io.set_output(4, True)
+        io.open(_path(name), True)
+        io.create(out)
+        io.decompose(2)
+        with pytest.raises(hb.HeatError, match="unknowns"):
+            io.scatter_nodal_field(np.zeros(n + 1), mesh.num_nodes)
+        for step in (0, 1):
+            field = io.scatter_nodal_field(0.25 + 0.5 * np.arange(n) + 4096.0 * step, mesh.num_nodes)
+            if _d1_active(mesh):
+                field[-1] = 0.0
+            io.write_nodal_field(field, step)
+    finally:
+        io.close()
+    _same(P.summ_output(P.canon_from_exodus(out)), ref_pins[name]["decompose"]["2"], OUT_KEYS + ("var_names", "times", "steps"))
+
+
+def test_host_scatter_default_convention_uses_the_rhs_id(hb, oracle):
+    """default (D2 fixed): a node in several nodesets shows the id its right-hand side used — the lowest"""
+    mesh = oracle.read_exodus(mesh_path("bolted_bracket"))
+    s = oracle.assemble(mesh, oracle.GRAPH_LAPLACIAN)
+    io = _host_io(hb)
+    try:
+        io.open(mesh_path("bolted_bracket"), True)
+        field = io.scatter_nodal_field(np.arange(s.n) + 0.5, mesh.num_nodes)
+    finally:
+        io.close()
+    np.testing.assert_array_equal(field, oracle.scatter_field(s, np.arange(s.n) + 0.5))
+    both = np.intersect1d(mesh.nodesets[1], mesh.nodesets[10])
+    assert len(both) == 32 and np.all(field[both] == 1.0)
+
+
 # ---- the CUDA path against the reference ---------------------------------------------------------------------------
 GPU_MESHES = [n for n in SHIPPED]
 
