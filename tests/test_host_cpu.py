@@ -268,3 +268,31 @@ def test_write_nodal_field_records_in_place(hb, host_io, tmp_path):
     np.testing.assert_array_equal(np.array(nc.variables["coordx"].data), np.array(ref.variables["coordx"].data))
     assert sum(nc.dimensions[f"num_el_in_blk{b}"] for b in (1, 2, 3)) == ref.dimensions["num_elem"]
     nc.close(); ref.close()
+
+
+def test_write_nodal_field_records_in_place_float32(hb, host_io, tmp_path):
+    """the same record discipline with the reference build's word size 4 (heat_ctx_set_output): records of N*4 + 4 bytes"""
+    from scipy.io import netcdf_file
+    out = str(tmp_path / "fields32.exo")
+    host_io.set_output(4)
+    host_io.open(mesh_path("mitchell_tri"), True)
+    host_io.create(out)
+    host_io.decompose(2)
+    N = 828
+    rng = np.random.default_rng(1)
+    f = [rng.standard_normal(N) * 1e3 for _ in range(4)]
+    host_io.write_nodal_field(f[0], 0)
+    size1 = os.path.getsize(out)
+    host_io.write_nodal_field(f[1], 1)
+    host_io.write_nodal_field(f[2], 3)                          # step 3 is skipped: a zero record
+    assert os.path.getsize(out) == size1 + 3 * (N * 4 + 4)
+    host_io.write_nodal_field(f[3], 0)                          # overwrite step 1 in place
+    nc = netcdf_file(out, "r", mmap=False)
+    vals, tw = np.array(nc.variables["vals_nod_var1"].data), np.array(nc.variables["time_whole"].data)
+    assert vals.dtype.itemsize == 4 and tw.dtype.itemsize == 4 and vals.shape == (4, N) and nc.floating_point_word_size == 4
+    np.testing.assert_array_equal(vals[0], f[3].astype(np.float32)); np.testing.assert_array_equal(vals[1], f[1].astype(np.float32))
+    np.testing.assert_array_equal(vals[3], f[2].astype(np.float32))
+    assert not vals[2].any()
+    np.testing.assert_array_equal(tw, [0, 1, 0, 3])
+    nc.close()
+
