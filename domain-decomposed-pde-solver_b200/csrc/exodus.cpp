@@ -609,14 +609,16 @@ extern "C" int heat_decompose(heat_ctx *ctx, int partitions) {
         NcFile::put_ints(cv, conn.data(), conn.size());
         cv.atts.push_back(NcFile::make_att_string("elem_type", m.elem_type));
     }
-    if (ctx->out_word_size == 4) {
-        // the reference creates its output with cpu/io word size sizeof(real_t) (ExodusIO.hpp:104-105): with a METIS
-        // whose real_t is float, every floating-point record (coordinates, distribution factors, times) is float32
-        for (NcVar &v : out.vars) {
-            if (v.type != NC_DOUBLE) continue;
-            const std::vector<double> d = out.get_doubles(v);
-            NcFile::put_floats(v, d.data(), d.size());
-        }
+    // The reference creates its output with cpu/io word size sizeof(real_t) whatever the input holds (ExodusIO.hpp:
+    // 104-105): with a METIS whose real_t is float every floating-point record (coordinates, distribution factors,
+    // times) is float32.  Here the word size is the context's (8 unless heat_ctx_set_output asked for 4), and every
+    // floating-point variable copied from the input is brought to it.
+    for (NcVar &v : out.vars) {
+        if (v.type != NC_DOUBLE && v.type != NC_FLOAT) continue;
+        if (nc_type_size(v.type) == ctx->out_word_size) continue;
+        const std::vector<double> d = out.get_doubles(v);
+        if (ctx->out_word_size == 4) NcFile::put_floats(v, d.data(), d.size());
+        else NcFile::put_doubles(v, d.data(), d.size());
     }
     for (NcAtt &a : out.gatts)
         if (a.name == "floating_point_word_size") a = NcFile::make_att_int("floating_point_word_size", ctx->out_word_size);

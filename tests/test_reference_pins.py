@@ -296,11 +296,22 @@ def test_real4_output_is_the_reference_builds_file(hb, ref_pins, name, tmp_path)
     assert floats and all(v.data.dtype.itemsize == 4 for v in floats)
     nc.close()
     _same(P.summ_output(P.canon_from_exodus(out)), ref_pins[name]["decompose"]["2"], OUT_KEYS)
+    # the float32 file as INPUT of a default (fp64) context: the output word size is the context's, not the input's
     again = _host_io(hb)
+    out8 = str(tmp_path / "solution8.exo")
     try:
-        again.open(out, True)                                     # float32 coordinates read back by the product's reader
+        again.open(out, True)
+        again.create(out8)
+        again.decompose(2)
     finally:
         again.close()
+    nc = netcdf_file(out8, "r", mmap=False)
+    assert nc.floating_point_word_size == 8
+    assert all(v.data.dtype.itemsize == 8 for v in nc.variables.values() if v.data.dtype.kind == "f")
+    nc.close()
+    c4, c8 = P.canon_from_exodus(out), P.canon_from_exodus(out8)
+    for a, b in zip(c4["coords"], c8["coords"]):
+        np.testing.assert_array_equal(np.asarray(a, dtype=np.float64), b)
 
 
 def test_cli_heat_decompose_mirrors_the_references_decompose_test(hb, ref_pins, tmp_path):
