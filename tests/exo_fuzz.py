@@ -1,24 +1,24 @@
 """Random small Exodus-II files for the fuzz tests (written with scipy.io.netcdf_file in Exodus' netCDF conventions):
 1-3 element blocks of one type (TRI3 / TRI / TETRA / TETRA4 / HEX8) with random connectivity, 0-3 nodesets (random ids,
 possibly overlapping, unsorted, with or without distribution factors), 0-2 sidesets, with or without node_num_map /
-elem_map.  Deliberately ugly meshes: isolated nodes, disconnected pieces, DOFs with only Dirichlet neighbours."""
+elem_map, stored as float64 or float32.  Deliberately ugly meshes: isolated nodes, disconnected pieces, DOFs with only Dirichlet neighbours."""
 import numpy as np
 from scipy.io import netcdf_file
 
 
-def write_exodus(path, rng, N, blocks, nodesets, sidesets, with_nmap, with_emap, title, ndim=3):
+def write_exodus(path, rng, N, blocks, nodesets, sidesets, with_nmap, with_emap, title, ndim=3, real="d"):
     nc = netcdf_file(path, "w", version=2)
     nc.title = title.encode()
     nc.api_version = np.float32(8.03)
     nc.version = np.float32(8.03)
-    nc.floating_point_word_size = np.int32(8)
+    nc.floating_point_word_size = np.int32(8 if real == "d" else 4)
     nc.file_size = np.int32(1)
     ne = sum(len(c) for _, c in blocks)
     nc.createDimension("time_step", None)
     for name, ln in (("len_string", 33), ("len_line", 81), ("four", 4), ("len_name", 33), ("num_dim", ndim), ("num_nodes", N),
                      ("num_elem", ne), ("num_el_blk", len(blocks))):
         nc.createDimension(name, ln)
-    nc.createVariable("time_whole", "d", ("time_step",))
+    nc.createVariable("time_whole", real, ("time_step",))
     v = nc.createVariable("eb_status", "i", ("num_el_blk",)); v[:] = 1
     v = nc.createVariable("eb_prop1", "i", ("num_el_blk",)); v[:] = np.arange(10, 10 + len(blocks)); v.name = b"ID"
     if nodesets:
@@ -33,21 +33,21 @@ def write_exodus(path, rng, N, blocks, nodesets, sidesets, with_nmap, with_emap,
         nc.createDimension(f"num_nod_ns{k}", len(nodes))
         v = nc.createVariable(f"node_ns{k}", "i", (f"num_nod_ns{k}",)); v[:] = nodes + 1
         if df is not None:
-            v = nc.createVariable(f"dist_fact_ns{k}", "d", (f"num_nod_ns{k}",)); v[:] = df
+            v = nc.createVariable(f"dist_fact_ns{k}", real, (f"num_nod_ns{k}",)); v[:] = df
     for k, (_, elems, sides, df) in enumerate(sidesets, 1):
         nc.createDimension(f"num_side_ss{k}", len(elems))
         v = nc.createVariable(f"elem_ss{k}", "i", (f"num_side_ss{k}",)); v[:] = elems + 1
         v = nc.createVariable(f"side_ss{k}", "i", (f"num_side_ss{k}",)); v[:] = sides
         if df is not None:
             nc.createDimension(f"num_df_ss{k}", len(df))
-            v = nc.createVariable(f"dist_fact_ss{k}", "d", (f"num_df_ss{k}",)); v[:] = df
+            v = nc.createVariable(f"dist_fact_ss{k}", real, (f"num_df_ss{k}",)); v[:] = df
     for k, (etype, conn) in enumerate(blocks, 1):
         nc.createDimension(f"num_el_in_blk{k}", conn.shape[0])
         nc.createDimension(f"num_nod_per_el{k}", conn.shape[1])
         v = nc.createVariable(f"connect{k}", "i", (f"num_el_in_blk{k}", f"num_nod_per_el{k}")); v[:] = conn + 1
         v.elem_type = etype.encode()
     for nm in ("coordx", "coordy", "coordz")[:ndim]:
-        v = nc.createVariable(nm, "d", ("num_nodes",)); v[:] = rng.uniform(-5, 5, N)
+        v = nc.createVariable(nm, real, ("num_nodes",)); v[:] = rng.uniform(-5, 5, N)
     v = nc.createVariable("coor_names", "c", ("num_dim", "len_name"))
     for i in range(ndim):
         v[i, 0] = b"xyz"[i:i + 1]
@@ -87,5 +87,5 @@ def random_case(seed: int):
 def write_random(path: str, seed: int) -> int:
     """writes the file of `seed`; -> the number of partitions to decompose it into"""
     rng, N, blocks, nodesets, sidesets, nm, em, title, parts = random_case(seed)
-    write_exodus(path, rng, N, blocks, nodesets, sidesets, nm, em, title)
+    write_exodus(path, rng, N, blocks, nodesets, sidesets, nm, em, title, real="f" if seed % 3 == 2 else "d")   # every third file is float32
     return parts
