@@ -661,6 +661,7 @@ extern "C" int heat_scatter_nodal_field(heat_ctx *ctx, const double *x_reduced_h
     const HostMesh &m = ctx->mesh;
     if (!m.valid) HEAT_FAIL(4, "heat_scatter_nodal_field: no mesh");
     if (num_nodes != m.num_nodes) HEAT_FAIL(2, "heat_scatter_nodal_field: field must hold num_nodes = %lld values", (long long)m.num_nodes);
+    if (!m.is_cube) heat::build_node_bc(ctx);          // from the CURRENT mesh: no assemble call need have come before
     return scatter_reduced(ctx, x_reduced_host, n_global, field_host);
 }
 

@@ -406,6 +406,32 @@ def test_host_scatter_default_convention_uses_the_rhs_id(hb, oracle):
     assert len(both) == 32 and np.all(field[both] == 1.0)
 
 
+def test_host_scatter_on_cubes_and_memory_meshes(hb, oracle):
+    """the other two mesh sources: analytic Kuhn cubes (nodesets 1000 / 100 on the x faces) and heat_mesh_set"""
+    io = _host_io(hb)
+    try:
+        io.mesh_cube(6, 4, 3)
+        m = oracle.cube_mesh(6, 4, 3)
+        s = oracle.assemble(m, oracle.GRAPH_LAPLACIAN)
+        x = np.arange(s.n) + 0.25
+        np.testing.assert_array_equal(io.scatter_nodal_field(x, m.num_nodes), oracle.scatter_field(s, x))
+        with pytest.raises(hb.HeatError, match="unknowns"):
+            io.scatter_nodal_field(x[:-1], m.num_nodes)
+        with pytest.raises(hb.HeatError, match="num_nodes"):
+            io.scatter_nodal_field(x, m.num_nodes - 1)
+        ns = {7: np.array([0, 5]), 3: np.array([5])}
+        io.mesh_set(m.x, m.y, m.z, m.conn, ns)
+        f = io.scatter_nodal_field(np.arange(m.num_nodes - 2) + 0.5, m.num_nodes)
+        assert f[0] == 7.0 and f[5] == 3.0 and f[1] == 0.5 and f[-1] == m.num_nodes - 2.5
+        io.set_output(8, True)
+        assert io.scatter_nodal_field(np.zeros(m.num_nodes - 2), m.num_nodes)[5] == 7.0        # largest id on request
+        io.mesh_set(m.x, m.y, m.z, m.conn, {9: np.array([1])})                                  # same size, other nodesets:
+        f = io.scatter_nodal_field(np.zeros(m.num_nodes - 1), m.num_nodes)                     # nothing stale may survive
+        assert f[1] == 9.0 and f[0] == 0.0 and f[5] == 0.0
+    finally:
+        io.close()
+
+
 # ---- the CUDA path against the reference ---------------------------------------------------------------------------
 GPU_MESHES = [n for n in SHIPPED]
 
