@@ -25,7 +25,7 @@ import pins as P          # noqa: E402
 import run_ref as R       # noqa: E402
 import exo_fuzz           # noqa: E402
 
-SEEDS = list(range(48))
+SEEDS = list(range(int(os.environ.get("HEAT_FUZZ_SEEDS", "48"))))      # HEAT_FUZZ_SEEDS=2000 for a longer offline run
 CSR_KEYS = ("n", "nrows", "nnz", "trace", "sum", "rows", "rowptr", "cols", "vals")
 OUT_KEYS = ("title", "num_dim", "num_nodes", "num_elem", "num_el_blk", "num_node_sets", "num_side_sets", "coords", "elem_map",
             "node_num_map", "blocks", "nodesets", "sidesets")
