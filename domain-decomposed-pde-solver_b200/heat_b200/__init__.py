@@ -65,7 +65,7 @@ ABI_SYMBOLS = [
     "heat_last_error", "heat_version", "heat_device_count", "heat_kernel_launches", "heat_ctx_create", "heat_ctx_set_stream", "heat_ctx_set_output", "heat_open",
     "heat_create", "heat_close", "heat_mesh_set", "heat_mesh_cube", "heat_mesh_nodeset_ids", "heat_comm_unique_id", "heat_comm_init",
     "heat_comm_rank", "heat_assemble", "heat_get_matrix", "heat_node_owners", "heat_matrix_owned_nodeset", "heat_power_method", "heat_solve_opts_default", "heat_solve", "heat_solve_trajectory", "heat_solve_host", "heat_spmv",
-    "heat_cg_iterations", "heat_decompose", "heat_write_solution", "heat_write_nodal_field", "heat_nodal_field", "heat_scatter_nodal_field", "heat_decompose_partition",
+    "heat_cg_iterations", "heat_decompose", "heat_write_solution", "heat_write_nodal_field", "heat_nodal_field", "heat_scatter_nodal_field", "heat_reference_view_csr", "heat_decompose_partition",
     "heat_matrix_get_info", "heat_matrix_export_csr", "heat_matrix_export_maps", "heat_matrix_export_plan",
     "heat_matrix_export_red2orig", "heat_matrix_export_ilu0", "heat_matrix_free", "heat_vector_create", "heat_vector_size",
     "heat_vector_device_ptr", "heat_vector_set", "heat_vector_get", "heat_vector_fill", "heat_vector_fill_hash",
@@ -116,6 +116,7 @@ def lib():
     L.heat_write_solution.argtypes = [vp, vp, C.c_int]
     L.heat_nodal_field.argtypes = [vp, vp, dp, C.c_int64]
     L.heat_scatter_nodal_field.argtypes = [vp, dp, C.c_int64, dp, C.c_int64]
+    L.heat_reference_view_csr.argtypes = [vp, C.c_int64, i64p, i32p, dp, dp, i64p, i64p, i64p, i64p, i32p, dp, dp, i64p, i64p, i64p]
     L.heat_write_nodal_field.argtypes = [vp, dp, C.c_int64, C.c_int]
     L.heat_decompose_partition.argtypes = [vp, C.c_int, i64p, i64p, i64p]
     L.heat_matrix_get_info.argtypes = [vp, C.POINTER(MatrixInfo)]
@@ -424,6 +425,27 @@ class IO:
         out = np.empty(max(num_nodes, 1), dtype=np.float64)
         _check(lib().heat_scatter_nodal_field(self.h, _ptr(x, C.c_double), x.size, _ptr(out, C.c_double), num_nodes))
         return out[:num_nodes]
+
+    def reference_view(self, row_ptr, col, val, b, red2orig):
+        """the FIXED system (e.g. Matrix.csr(), B.numpy(), Matrix.red2orig() on one rank) as the reference's own
+        IO::assemble returns it for this mesh (defects D1 and D3) -> (row_ptr, col, val, b, idmap_reduced, idmap_original)"""
+        row_ptr = np.ascontiguousarray(row_ptr, dtype=np.int64)
+        col = np.ascontiguousarray(col, dtype=np.int32)
+        val = np.ascontiguousarray(val, dtype=np.float64)
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        r2o = np.ascontiguousarray(red2orig, dtype=np.int64)
+        n = row_ptr.size - 1
+        no, nnz, nm = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+        head = (self.h, n, _ptr(row_ptr, C.c_int64), _ptr(col, C.c_int32) if col.size else None, _ptr(val, C.c_double) if val.size else None,
+                _ptr(b, C.c_double) if b.size else None, _ptr(r2o, C.c_int64) if r2o.size else None, C.byref(no), C.byref(nnz))
+        _check(lib().heat_reference_view_csr(*head, None, None, None, None, C.byref(nm), None, None))
+        rp = np.zeros(no.value + 1, dtype=np.int64)
+        co, va = np.zeros(max(nnz.value, 1), dtype=np.int32), np.zeros(max(nnz.value, 1), dtype=np.float64)
+        bo = np.zeros(max(no.value, 1), dtype=np.float64)
+        ir, io_ = np.zeros(max(nm.value, 1), dtype=np.int64), np.zeros(max(nm.value, 1), dtype=np.int64)
+        _check(lib().heat_reference_view_csr(*head, _ptr(rp, C.c_int64), _ptr(co, C.c_int32), _ptr(va, C.c_double), _ptr(bo, C.c_double),
+                                             C.byref(nm), _ptr(ir, C.c_int64), _ptr(io_, C.c_int64)))
+        return rp, co[: nnz.value], va[: nnz.value], bo[: no.value], ir[: nm.value], io_[: nm.value]
 
     def nodal_field(self, vec: Vector, num_nodes: int) -> np.ndarray:
         out = np.empty(num_nodes, dtype=np.float64)

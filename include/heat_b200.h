@@ -182,6 +182,17 @@ int  heat_nodal_field(heat_ctx *ctx, const heat_vector *X, double *field_host, i
  * solve -> field -> file without a device vector.  Pure host code.                                  */
 int  heat_scatter_nodal_field(heat_ctx *ctx, const double *x_reduced_host, int64_t n_global, double *field_host,
                               int64_t num_nodes);
+/* The system the REFERENCE's IO::assemble returns for the context's mesh (one rank), derived from the FIXED system
+ * this library assembles (heat_matrix_export_csr / heat_vector_get / heat_matrix_export_red2orig): the rows of
+ * unknowns without an unknown neighbour are never inserted and have no id-map entry (defect D3, ExodusIO.hpp:
+ * 380-386, :591), and if the last mesh node is an unknown it is dropped and the entries that referenced it are
+ * summed into column 0 (defect D1, :220, :440, :598).  For diffing against a Trilinos run; held to the reference's
+ * own output by tests/test_reference_pins.py.  Call with row_ptr_out == NULL for the sizes (n_out, nnz_out,
+ * n_map_out), then with arrays of n_out+1 / nnz_out / nnz_out / n_out / n_map_out / n_map_out entries.  Host only. */
+int  heat_reference_view_csr(heat_ctx *ctx, int64_t n, const int64_t *row_ptr, const int32_t *col, const double *val,
+                             const double *b, const int64_t *red2orig, int64_t *n_out, int64_t *nnz_out,
+                             int64_t *row_ptr_out, int32_t *col_out, double *val_out, double *b_out,
+                             int64_t *n_map_out, int64_t *idmap_reduced_out, int64_t *idmap_original_out);
 /* METIS_PartMeshDual with the reference's arguments (ExodusIO.hpp:1615); arrays are int64        */
 int  heat_decompose_partition(heat_ctx *ctx, int partitions, int64_t *objval, int64_t *epart_host,
                               int64_t *npart_host);

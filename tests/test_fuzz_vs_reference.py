@@ -81,7 +81,7 @@ def test_decompose_file_equals_reference_on_random_meshes(hb, driver, seed, tmp_
 
 
 @pytest.mark.parametrize("seed", SEEDS)
-def test_fixed_oracles_seen_through_the_defects_equal_reference_on_random_meshes(oracle, driver, seed, tmp_path):
+def test_fixed_oracles_seen_through_the_defects_equal_reference_on_random_meshes(hb, oracle, driver, seed, tmp_path):
     src = str(tmp_path / "m.exo")
     parts = exo_fuzz.write_random(src, seed)
     ref = R.run_reference(src, parts, get_matrix=False)
@@ -90,6 +90,21 @@ def test_fixed_oracles_seen_through_the_defects_equal_reference_on_random_meshes
     mesh = oracle.read_exodus(src)
     s = oracle.assemble(mesh, oracle.GRAPH_LAPLACIAN)
     An, bn, r2on = oracle.assemble_np(mesh, oracle.GRAPH_LAPLACIAN)
+    # the product's own transformation (csrc/refview.cpp, host code) on the C oracle's arrays
+    import scipy.sparse as sp
+    h = C.c_void_p()
+    assert hb.lib().heat_ctx_create(-1, C.byref(h)) == 0
+    io = hb.IO.__new__(hb.IO)
+    io.h = h
+    try:
+        io.open(src, True)
+        rp, col, val, bv, kept_p, orig_p = io.reference_view(s.row_ptr, s.col, s.val, s.b, s.red2orig)
+    finally:
+        io.close()
+    got_p = P.summ_scipy(sp.csr_matrix((val, col, rp), shape=(len(rp) - 1, len(rp) - 1)))
+    for k in CSR_KEYS:
+        assert got_p[k] == want["A"][k], ("product view", k, got_p[k], want["A"][k])
+    assert P._arr(bv, "<f8") == want["B"] and P._arr(kept_p, "<i8") == want["idmap_reduced"] and P._arr(orig_p, "<i8") == want["idmap_original"]
     for A, b, r2o in ((s.csr(), s.b, s.red2orig), (An, bn, r2on)):
         Ar, br, kept, orig = P.reference_view(A, b, r2o, mesh.conn, mesh.num_nodes, mesh.nodesets)
         got = P.summ_scipy(Ar)

@@ -116,6 +116,35 @@ def test_c_oracle_fixed_semantics_project_onto_reference(oracle, ref_pins, name)
     assert P._arr(r2o, "<i8") == want["idmap_original"]
 
 
+def _summ_product_view(view):
+    """digest of what heat_reference_view_csr returned, in the fixture's terms (rows that exist = rows with entries)"""
+    rp, col, val, b, kept, orig = view
+    for k in range(len(rp) - 1):
+        assert np.all(np.diff(col[rp[k]:rp[k + 1]]) > 0)            # columns ascending, no duplicates
+    n = len(rp) - 1
+    return P.summ_scipy(sp.csr_matrix((val, col, rp), shape=(n, n))), b, kept, orig
+
+
+@pytest.mark.parametrize("name", _all_meshes())
+def test_product_reference_view_equals_reference(hb, oracle, ref_pins, name):
+    """heat_reference_view_csr (csrc/refview.cpp, host code of the product): the FIXED system -> the system the
+    reference's own IO::assemble returned, bit for bit, on every mesh (defects D1 / D3 applied inside the product)"""
+    mesh = oracle.read_exodus(_path(name))
+    s = oracle.assemble(mesh, oracle.GRAPH_LAPLACIAN)
+    io = _host_io(hb)
+    try:
+        io.open(_path(name), True)
+        A, b, kept, orig = _summ_product_view(io.reference_view(s.row_ptr, s.col, s.val, s.b, s.red2orig))
+        with pytest.raises(hb.HeatError, match="unknowns"):
+            io.reference_view(s.row_ptr[:-1], s.col, s.val, s.b[:-1], s.red2orig[:-1])
+    finally:
+        io.close()
+    want = ref_pins[name]["assemble"]
+    _same(A, want["A"], CSR_KEYS)
+    assert P._arr(b, "<f8") == want["B"]
+    assert P._arr(kept, "<i8") == want["idmap_reduced"] and P._arr(orig, "<i8") == want["idmap_original"]
+
+
 @pytest.mark.parametrize("name", [n for n in _all_meshes() if n != "initialguess"])
 def test_c_oracle_get_matrix_equals_reference(oracle, ref_pins, name):
     """IO::getMatrix on one rank: rows and columns are 1-based node ids, nodesets are returned 1-based and are
@@ -199,6 +228,23 @@ def test_c_oracle_edge_cases_against_reference(oracle, ref_pins, key):
     m = _edge_mesh(oracle, e["mesh"])
     s = oracle.assemble(m, oracle.GRAPH_LAPLACIAN)
     _check_edge_against_reference(s.csr(), s.b, s.red2orig, m, e["assemble"])
+
+
+@pytest.mark.parametrize("key", EDGES)
+def test_product_reference_view_on_corner_cases(hb, oracle, ref_pins, key):
+    e = ref_pins["_synthetic"][key]
+    m = _edge_mesh(oracle, e["mesh"])
+    s = oracle.assemble(m, oracle.GRAPH_LAPLACIAN)
+    io = _host_io(hb)
+    try:
+        io.mesh_set(m.x, m.y, m.z, m.conn, dict(m.nodesets))
+        A, b, kept, orig = _summ_product_view(io.reference_view(s.row_ptr, s.col, s.val, s.b, s.red2orig))
+    finally:
+        io.close()
+    want = e["assemble"]
+    _same(A, want["A"], CSR_KEYS)
+    assert P._arr(b, "<f8") == want["B"]
+    assert P._arr(kept, "<i8") == want["idmap_reduced"] and P._arr(orig, "<i8") == want["idmap_original"]
 
 
 def test_reference_defects_seen_live(ref_pins):
@@ -457,6 +503,12 @@ def test_gpu_assemble_equals_reference(hb, gpu_io, oracle, ref_pins, name):
     n = len(rp) - 1
     M, b, r2o = sp.csr_matrix((val, col, rp), shape=(n, n)), B.numpy(), A.red2orig()
     want = ref_pins[name]["assemble"]
+    # (1) the product end to end: device assembly -> heat_reference_view_csr (host) = the reference's output
+    Av, bv, kept, orig = _summ_product_view(gpu_io.reference_view(rp, col, val, b, r2o))
+    _same(Av, want["A"], CSR_KEYS)
+    assert P._arr(bv, "<f8") == want["B"]
+    assert P._arr(kept, "<i8") == want["idmap_reduced"] and P._arr(orig, "<i8") == want["idmap_original"]
+    # (2) the same through the test-side transformation
     if _d1_active(mesh):
         M, b = P.apply_d1(M, b)
         r2o = r2o[:-1]
