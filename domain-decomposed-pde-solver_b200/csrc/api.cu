@@ -52,7 +52,7 @@ void build_node_bc(heat_ctx *ctx) {
 }
 
 static int finish_matrix(heat_ctx *ctx, heat_matrix *A) {
-    HEAT_TRY(sell_from_csr(A, ctx->stream));
+    if (!A->sell_val.p) HEAT_TRY(sell_from_csr(A, ctx->stream));      // not assembled straight into SELL
     HEAT_TRY(ensure_workspace(A, false, false));
     HaloPlan &h = A->halo;
     if (h.n_neighbors > 0) {
@@ -101,7 +101,14 @@ static int assemble_cube_analytic(heat_ctx *ctx, int mode, heat_matrix *A, heat_
     A->owned_contiguous = true;
     A->gid0 = c.plane * c.k0;
     HEAT_TRY(new_vector(ctx, A, B));
-    HEAT_TRY(cube_assemble(c, mode, A, (*B)->d.p, ctx->stream));
+    {
+        const char *how = getenv("HEAT_CUBE_ASSEMBLY");                // "csr": the CSR-first path
+        const char *cidx = getenv("HEAT_SPMV_CIDX");                   // 0: int32 column stream
+        bool done = false;
+        if (!(how && strcmp(how, "csr") == 0))
+            HEAT_TRY(cube_assemble_sell(c, mode, !(cidx && atoi(cidx) == 0), A, (*B)->d.p, ctx->stream, &done));
+        if (!done) HEAT_TRY(cube_assemble(c, mode, A, (*B)->d.p, ctx->stream));
+    }
     // halo plan: rank-1 (lower plane) first, then rank+1 — ghosts grouped by owner ascending
     HaloPlan &h = A->halo;
     h.send_ptr.assign(1, 0); h.recv_ptr.assign(1, 0);
@@ -148,6 +155,8 @@ static int assemble_general(heat_ctx *ctx, int mode, int partitioner, const std:
         HEAT_TRY(A->val.alloc((size_t)ga.nnz));
         HEAT_TRY(ga.fill_values(mode, ga.n, nullptr, nullptr, ga.grow_ptr.p, nullptr, A->val.p, (*B)->d.p, st));
         HEAT_CUDA(cudaStreamSynchronize(st));
+        for (int q = 0; q < 4; ++q) A->asm_phase_ms[q] = ga.phase_ms[q];
+        A->assemble_fill_ms = ga.phase_ms[3];
         A->row_ptr = std::move(ga.grow_ptr);
         A->col = std::move(ga.gcol);
         A->red2orig_owned.resize((size_t)ga.n);
@@ -215,6 +224,8 @@ static int assemble_general(heat_ctx *ctx, int mode, int partitioner, const std:
     HEAT_TRY(new_vector(ctx, A, B));
     HEAT_TRY(ga.fill_values(mode, sz.n_owned, d_owned.p, d_g2l.p, A->row_ptr.p, A->col.p, A->val.p, (*B)->d.p, st));
     HEAT_CUDA(cudaStreamSynchronize(st));
+    for (int q = 0; q < 4; ++q) A->asm_phase_ms[q] = ga.phase_ms[q];
+    A->assemble_fill_ms = ga.phase_ms[3];
     return 0;
 }
 
@@ -527,6 +538,13 @@ extern "C" int heat_spmv(heat_ctx *ctx, heat_matrix *A, heat_vector *x, heat_vec
     return spmv_halo(ctx, A, x->d.p, y->d.p, nogate, nullptr);
 }
 
+extern "C" int heat_spmv_peer(heat_ctx *ctx, heat_matrix *A, heat_vector *x, heat_vector *y, int repeat,
+                              double *xy_global, double *kernel_ms) {
+    if (!ctx || !A || !x || !y) HEAT_FAIL(2, "heat_spmv_peer: null argument");
+    if (x->n_owned != A->n_owned || y->n_owned != A->n_owned || x == y) HEAT_FAIL(2, "heat_spmv_peer: bad vectors");
+    return spmv_peer_once(ctx, A, x->d.p, y->d.p, repeat, xy_global, kernel_ms);
+}
+
 // ---- inspection ------------------------------------------------------------------------------------
 extern "C" int heat_matrix_get_info(const heat_matrix *A, heat_matrix_info *info) {
     if (!A || !info) HEAT_FAIL(2, "heat_matrix_get_info: null argument");
@@ -543,12 +561,19 @@ extern "C" int heat_matrix_get_info(const heat_matrix *A, heat_matrix_info *info
     info->assemble_ms = A->assemble_ms;
     info->peer_path = A->peer ? 1 : 0;
     info->col_index_bytes = A->sell_idx8.p ? 1 : 4;
+    info->assemble_fill_ms = A->assemble_fill_ms;
+    for (int q = 0; q < 4; ++q) info->asm_phase_ms[q] = A->asm_phase_ms[q];
+    info->csr_resident = A->row_ptr.p ? 1 : 0;
+    info->matrix_bytes = (int64_t)(A->row_ptr.n * 8 + A->col.n * 4 + A->val.n * 8 + A->sell_val.n * 8 + A->sell_col.n * 4 +
+                                   A->sell_idx8.n + A->sell_tab.n * 4 + A->slice_ptr.n * 8 + A->slice_meta.n * 16 +
+                                   A->sell_rowlen.n + A->diag.n * 8 + A->dinv.n * 8);
     return 0;
 }
 
 extern "C" int heat_matrix_export_csr(const heat_matrix *A, int64_t *row_ptr, int32_t *col, double *val) {
     if (!A) HEAT_FAIL(2, "null matrix");
     HEAT_CUDA(cudaSetDevice(A->ctx->device));
+    HEAT_TRY(sell_to_csr(const_cast<heat_matrix *>(A), A->ctx->stream));     // assembled straight into SELL: build it now
     HEAT_CUDA(cudaStreamSynchronize(A->ctx->stream));
     if (row_ptr) HEAT_CUDA(cudaMemcpy(row_ptr, A->row_ptr.p, sizeof(int64_t) * (size_t)(A->n_owned + 1), cudaMemcpyDeviceToHost));
     if (col && A->nnz) HEAT_CUDA(cudaMemcpy(col, A->col.p, sizeof(int32_t) * (size_t)A->nnz, cudaMemcpyDeviceToHost));

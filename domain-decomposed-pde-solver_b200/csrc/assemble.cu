@@ -18,6 +18,8 @@
 
 #include "assemble.cuh"
 #include "device_utils.cuh"
+#include "kernels.cuh"
+#include "sell_dict.cuh"
 
 namespace heat {
 
@@ -204,6 +206,21 @@ values_kernel(int64_t n_owned, const int32_t *__restrict__ owned, const int32_t 
     b[l] = bsum;
 }
 
+// elapsed device time between two points of a stream (both events are created and destroyed here)
+struct StreamTimer {
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaStream_t st;
+    explicit StreamTimer(cudaStream_t s) : st(s) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, st); }
+    float stop() {                                       // synchronises the stream
+        float ms = 0.f;
+        cudaEventRecord(e1, st);
+        cudaEventSynchronize(e1);
+        cudaEventElapsedTime(&ms, e0, e1);
+        return ms;
+    }
+    ~StreamTimer() { if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); }
+};
+
 int GeneralAssembler::upload(const HostMesh &m, const std::vector<double> &node_bc, cudaStream_t st) {
     N = m.num_nodes; ne = m.num_elem; npe = m.npe; has_z = !m.z.empty();
     HEAT_TRY(x.alloc((size_t)N)); HEAT_TRY(y.alloc((size_t)N)); HEAT_TRY(z.alloc((size_t)N));
@@ -284,6 +301,7 @@ int GeneralAssembler::build_pattern(cudaStream_t st) {
     // ---- node -> incident elements, ascending element id: stable radix sort of (node, elem) ----
     const int64_t total = ne * npe;
     {
+        StreamTimer t_sort(st);
         DevBuf<int32_t> keys_in, elems_in, keys_out;
         HEAT_TRY(keys_in.alloc((size_t)total)); HEAT_TRY(elems_in.alloc((size_t)total));
         HEAT_TRY(keys_out.alloc((size_t)total)); HEAT_TRY(n2e.alloc((size_t)total));
@@ -300,7 +318,7 @@ int GeneralAssembler::build_pattern(cudaStream_t st) {
         }
         n2e_ptr_kernel<<<(unsigned)((N + 1 + 255) / 256), 256, 0, st>>>(N, total, keys_out.p, n2e_ptr.p);
         HEAT_LAUNCHED();
-        HEAT_CUDA(cudaStreamSynchronize(st));
+        phase_ms[0] = t_sort.stop();
     }
 
     // ---- pattern of all reduced rows ----
@@ -310,9 +328,11 @@ int GeneralAssembler::build_pattern(cudaStream_t st) {
     HEAT_TRY(grow_ptr.alloc((size_t)n + 1));
     HEAT_CUDA(cudaMemsetAsync(row_len.p, 0, sizeof(int64_t) * (size_t)(n + 1), st));
     if (n > 0) {
+        StreamTimer t_count(st);
         pattern_count_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(n, red2orig.p, red.p, n2e_ptr.p, n2e.p, npe,
                                                                        conn.p, row_len.p, ovf.p);
         HEAT_LAUNCHED();
+        phase_ms[1] = t_count.stop();
     }
     {
         size_t tb = 0;
@@ -334,9 +354,11 @@ int GeneralAssembler::build_pattern(cudaStream_t st) {
     }
     HEAT_TRY(gcol.alloc((size_t)nnz));
     if (n > 0) {
+        StreamTimer t_fill(st);
         pattern_fill_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(n, red2orig.p, red.p, n2e_ptr.p, n2e.p, npe,
                                                                       conn.p, grow_ptr.p, gcol.p, ovf.p);
         HEAT_LAUNCHED();
+        phase_ms[2] = t_fill.stop();
     }
     return 0;
 }
@@ -349,10 +371,12 @@ int GeneralAssembler::fill_values(int mode, int64_t n_owned, const int32_t *d_ow
     if (n_owned == 0) return 0;
     DevBuf<int> ovf; HEAT_TRY(ovf.alloc(1));
     HEAT_CUDA(cudaMemsetAsync(ovf.p, 0, sizeof(int), st));
+    StreamTimer t_val(st);
     values_kernel<<<(unsigned)((n_owned + 127) / 128), 128, 0, st>>>(
         n_owned, d_owned, d_g2l, red2orig.p, red.p, n2e_ptr.p, n2e.p, npe, conn.p, x.p, y.p, has_z ? z.p : nullptr,
         bc.p, grow_ptr.p, gcol.p, d_lrow_ptr, d_lcol, d_lval, d_b, mode, ovf.p);
     HEAT_LAUNCHED();
+    phase_ms[3] = t_val.stop();
     return 0;
 }
 
@@ -475,6 +499,352 @@ cube_fill_kernel(CubeGeom c, int mode, const int64_t *__restrict__ row_ptr, int3
         }
     }
     b[l] = bsum;
+}
+
+// =================================================================================================
+// analytic Kuhn-cube path, DIRECT to the SpMV format (default): one warp per 64-row SELL slice
+// =================================================================================================
+// What IO::assemble's insertGlobalValues + fillComplete (ExodusIO.hpp:591-609) amount to for the structured
+// benchmark cubes, without ever materialising a CSR: each warp computes the 64 rows of one slice (lane l: rows
+// l and l+32 of the slice, i.e. neighbouring nodes along x), stages the slice in shared memory in its final
+// SELL layout [entry k][row], builds the slice's offset table and 1-byte indices there (sell_dict.cuh) and
+// writes values / indices with ONE TMA bulk store each (cp.async.bulk.global.shared::cta) — fully coalesced,
+// 8 + 1 bytes per stored entry, against the 12-byte CSR written row by row at a 180-byte stride (and then
+// re-read, re-written as SELL and scanned twice for the dictionary) of the CSR-first path below.
+// The element arithmetic is the oracle's, operation for operation and in the same order (ascending element
+// id), so the values stay bit-identical: the 8 cells x 6 permutations around a node are unrolled at compile
+// time (which vertex of which permutation the node is, and which stencil slot each of the tet's vertices
+// lands in, are constants), node coordinates are evaluated once per row (9 divisions instead of 288).
+constexpr int kCubeTileVal = 15 * kSellChunk * 8;       // 7680 B
+constexpr int kCubeTileCol = 15 * kSellChunk * 4;       // 3840 B
+constexpr int kCubeTileIdx = 15 * kSellChunk;           //  960 B
+constexpr int kCubeTileTab = kSellDictCap * 4;          //  256 B
+constexpr int kCubeTileBytes = kCubeTileVal + kCubeTileCol + kCubeTileIdx + kCubeTileTab;   // 12736 B per warp
+constexpr int kCubeWarps = 8;
+
+__host__ __device__ constexpr int kuhn_axis(int pm, int q) {        // axis of step q of permutation pm (lexicographic)
+    return pm == 0 ? (q == 0 ? 0 : q == 1 ? 1 : 2) : pm == 1 ? (q == 0 ? 0 : q == 1 ? 2 : 1) :
+           pm == 2 ? (q == 0 ? 1 : q == 1 ? 0 : 2) : pm == 3 ? (q == 0 ? 1 : q == 1 ? 2 : 0) :
+           pm == 4 ? (q == 0 ? 2 : q == 1 ? 0 : 1) : (q == 0 ? 2 : q == 1 ? 1 : 0);
+}
+// coordinate d of vertex q of permutation pm, relative to the cell's first node: 1 once axis d has been stepped
+__host__ __device__ constexpr int kuhn_vtx(int pm, int q, int d) {
+    int v = 0;
+    for (int t = 0; t < q; ++t) v += (kuhn_axis(pm, t) == d) ? 1 : 0;
+    return v;
+}
+__host__ __device__ constexpr int kuhn_vertex_of(int pm, int ox, int oy, int oz) {   // -1: the node is not on pm's path
+    for (int q = 0; q < 4; ++q)
+        if (kuhn_vtx(pm, q, 0) == ox && kuhn_vtx(pm, q, 1) == oy && kuhn_vtx(pm, q, 2) == oz) return q;
+    return -1;
+}
+
+// contributions of tet (cell = node - (OX,OY,OZ), permutation PM) to the row of the node.  X[t], Y[t], Z[t] are
+// the coordinates of grid lines i-1+t, j-1+t, k-1+t.
+template <int OX, int OY, int OZ, int PM>
+__device__ __forceinline__ void kuhn_tet_row(const double (&X)[3], const double (&Y)[3], const double (&Z)[3],
+                                             bool at_lo, bool at_hi, double (&v)[15], double &bsum) {
+    constexpr int a = kuhn_vertex_of(PM, OX, OY, OZ);
+    if constexpr (a >= 0) {
+        double p[4][3], G[4][3], s;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            p[q][0] = X[1 - OX + kuhn_vtx(PM, q, 0)];
+            p[q][1] = Y[1 - OY + kuhn_vtx(PM, q, 1)];
+            p[q][2] = Z[1 - OZ + kuhn_vtx(PM, q, 2)];
+        }
+        tet_G(p, G, s);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const double kab = ((G[a][0] * G[q][0] + G[a][1] * G[q][1]) + G[a][2] * G[q][2]) * s;
+            const int di = kuhn_vtx(PM, q, 0) - OX, dj = kuhn_vtx(PM, q, 1) - OY, dk = kuhn_vtx(PM, q, 2) - OZ;
+            const int code = (di != 0) + 2 * (dj != 0) + 4 * (dk != 0);
+            const int slot = (di + dj + dk) > 0 ? 7 + code : 7 - code;
+            if (di < 0 && at_lo) { const double t2 = kab * 1000.0; bsum = bsum - t2; }
+            else if (di > 0 && at_hi) { const double t2 = kab * 100.0; bsum = bsum - t2; }
+            else v[slot] += kab;
+        }
+    }
+}
+template <int OX, int OY, int OZ>
+__device__ __forceinline__ void kuhn_cell_row(const double (&X)[3], const double (&Y)[3], const double (&Z)[3],
+                                              bool at_lo, bool at_hi, double (&v)[15], double &bsum) {
+    kuhn_tet_row<OX, OY, OZ, 0>(X, Y, Z, at_lo, at_hi, v, bsum);
+    kuhn_tet_row<OX, OY, OZ, 1>(X, Y, Z, at_lo, at_hi, v, bsum);
+    kuhn_tet_row<OX, OY, OZ, 2>(X, Y, Z, at_lo, at_hi, v, bsum);
+    kuhn_tet_row<OX, OY, OZ, 3>(X, Y, Z, at_lo, at_hi, v, bsum);
+    kuhn_tet_row<OX, OY, OZ, 4>(X, Y, Z, at_lo, at_hi, v, bsum);
+    kuhn_tet_row<OX, OY, OZ, 5>(X, Y, Z, at_lo, at_hi, v, bsum);
+}
+
+// the 15 slot values + right-hand side of node (i,j,k)
+__device__ __forceinline__ void cube_row_values(const CubeGeom &c, int mode, int i, int j, int k, double (&v)[15], double &bsum) {
+#pragma unroll
+    for (int s = 0; s < 15; ++s) v[s] = 0.0;
+    bsum = 0.0;
+    if (mode == HEAT_OP_GRAPH_LAPLACIAN) {
+        int deg = 0;
+#pragma unroll
+        for (int s = 0; s < 15; ++s) {
+            if (s == 7) continue;
+            int di, dj, dk;
+            slot_delta(s, di, dj, dk);
+            const int ii = i + di, jj = j + dj, kk = k + dk;
+            if (ii < 0 || ii >= c.nx || jj < 0 || jj >= c.ny || kk < 0 || kk >= c.nz) continue;
+            ++deg;
+            if (ii == 0) bsum += 1000.0; else if (ii == c.nx - 1) bsum += 100.0; else v[s] = -1.0;
+        }
+        v[7] = (double)deg;
+        return;
+    }
+    double X[3], Y[3], Z[3];
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+        X[t] = -5.0 + 10.0 * (double)(i - 1 + t) / (double)(c.nx - 1);
+        Y[t] = -5.0 + 10.0 * (double)(j - 1 + t) / (double)(c.ny - 1);
+        Z[t] = -5.0 + 10.0 * (double)(k - 1 + t) / (double)(c.nz - 1);
+    }
+    const bool at_lo = i == 1, at_hi = i == c.nx - 2;
+    const bool jlo = j >= 1, jhi = j <= c.ny - 2, klo = k >= 1, khi = k <= c.nz - 2;   // cells at j-1 / j / k-1 / k exist
+    // ascending element id: cells by (ck, cj, ci); the x-cells i-1 and i always exist for 1 <= i <= nx-2
+    if (klo && jlo) { kuhn_cell_row<1, 1, 1>(X, Y, Z, at_lo, at_hi, v, bsum); kuhn_cell_row<0, 1, 1>(X, Y, Z, at_lo, at_hi, v, bsum); }
+    if (klo && jhi) { kuhn_cell_row<1, 0, 1>(X, Y, Z, at_lo, at_hi, v, bsum); kuhn_cell_row<0, 0, 1>(X, Y, Z, at_lo, at_hi, v, bsum); }
+    if (khi && jlo) { kuhn_cell_row<1, 1, 0>(X, Y, Z, at_lo, at_hi, v, bsum); kuhn_cell_row<0, 1, 0>(X, Y, Z, at_lo, at_hi, v, bsum); }
+    if (khi && jhi) { kuhn_cell_row<1, 0, 0>(X, Y, Z, at_lo, at_hi, v, bsum); kuhn_cell_row<0, 0, 0>(X, Y, Z, at_lo, at_hi, v, bsum); }
+}
+
+__device__ __forceinline__ bool cube_slot_stored(const CubeGeom &c, int s, int i, int j, int k, int &ii, int &jj, int &kk) {
+    int di, dj, dk;
+    slot_delta(s, di, dj, dk);
+    ii = i + di; jj = j + dj; kk = k + dk;
+    return ii >= 1 && ii <= c.nx - 2 && jj >= 0 && jj < c.ny && kk >= 0 && kk < c.nz;
+}
+
+// one warp per slice: slice_entries[s] = 64 * (longest row of the slice); *nnz_total += stored entries
+__global__ void __launch_bounds__(kBlock)
+cube_width_kernel(CubeGeom c, int64_t n_slices, int64_t *__restrict__ slice_entries, unsigned long long *nnz_total) {
+    const int lane = threadIdx.x & 31;
+    const int64_t s = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    int len_sum = 0;
+    if (s < n_slices) {
+        int wmax = 0;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int64_t l = s * kSellChunk + h * 32 + lane;
+            if (l >= c.n_owned) continue;
+            int i, j, k, ii, jj, kk, len = 0;
+            cube_row_ijk(c, l, i, j, k);
+#pragma unroll
+            for (int q = 0; q < 15; ++q) len += cube_slot_stored(c, q, i, j, k, ii, jj, kk) ? 1 : 0;
+            wmax = len > wmax ? len : wmax;
+            len_sum += len;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+        if (lane == 0) slice_entries[s] = (int64_t)wmax * kSellChunk;
+    }
+    __shared__ int blk;
+    if (threadIdx.x == 0) blk = 0;
+    __syncthreads();
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) len_sum += __shfl_xor_sync(0xffffffffu, len_sum, o);
+    if (lane == 0 && len_sum) atomicAdd(&blk, len_sum);
+    __syncthreads();
+    if (threadIdx.x == 0 && blk) atomicAdd(nnz_total, (unsigned long long)blk);
+}
+
+struct CubeSellArgs {
+    CubeGeom c; int mode;
+    const int64_t *slice_ptr; int64_t n_slices;
+    double *val;                     // [sell_padded]
+    int32_t *col;                    // [sell_padded]           (int32 column stream; null when byte-indexed)
+    uint8_t *idx8; int32_t *tab;     // [sell_padded], [n_slices][tpad]   (byte-indexed stream; null otherwise)
+    int tpad;
+    uint8_t *rowlen;                 // [n_owned] stored entries of every row
+    double *diag, *dinv, *b;         // [n_owned]
+    int32_t *is_boundary;            // [n_slices] (null on one GPU): slice references a ghost column
+    int *max_tab;                    // atomicMax of the table lengths (> tpad: the caller falls back to the CSR-first path)
+};
+
+template <bool C8>
+__global__ void __launch_bounds__(kCubeWarps * 32, 2) cube_sell_kernel(CubeSellArgs a) {
+    extern __shared__ __align__(128) unsigned char cube_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char *my = cube_smem + (size_t)warp * kCubeTileBytes;
+    double *tv = reinterpret_cast<double *>(my);
+    int32_t *tc = reinterpret_cast<int32_t *>(my + kCubeTileVal);
+    uint8_t *ti = my + kCubeTileVal + kCubeTileCol;
+    int32_t *tab = reinterpret_cast<int32_t *>(my + kCubeTileVal + kCubeTileCol + kCubeTileIdx);
+    const CubeGeom &c = a.c;
+    for (int64_t s = (int64_t)blockIdx.x * kCubeWarps + warp; s < a.n_slices; s += (int64_t)gridDim.x * kCubeWarps) {
+        const int64_t base = a.slice_ptr[s];
+        const int w = (int)((a.slice_ptr[s + 1] - base) >> 6);
+        int ghost = 0;
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+            const int rl = h * 32 + lane;
+            const int64_t l = s * kSellChunk + rl;
+            int cnt = 0;
+            // padding: (value 0, column = own row); rows past the end point 64 rows back (constant offset, sell.cu)
+            int32_t padcol = l < c.n_owned ? (int32_t)l : (l >= kSellChunk ? (int32_t)(l - kSellChunk) : 0);
+            if (l < c.n_owned) {
+                int i, j, k;
+                cube_row_ijk(c, l, i, j, k);
+                double v[15], bsum;
+                cube_row_values(c, a.mode, i, j, k, v, bsum);
+#pragma unroll
+                for (int q = 0; q < 15; ++q) {
+                    int ii, jj, kk;
+                    if (cube_slot_stored(c, q, i, j, k, ii, jj, kk)) {
+                        const int32_t cc = cube_local_col(c, ii, jj, kk);
+                        ghost |= cc >= c.n_owned;
+                        tv[cnt * kSellChunk + rl] = v[q];
+                        tc[cnt * kSellChunk + rl] = cc;
+                        ++cnt;
+                    }
+                }
+                a.diag[l] = v[7];
+                a.dinv[l] = 1.0 / v[7];
+                a.b[l] = bsum;
+                a.rowlen[l] = (uint8_t)cnt;
+            }
+            for (; cnt < w; ++cnt) { tv[cnt * kSellChunk + rl] = 0.0; tc[cnt * kSellChunk + rl] = padcol; }
+        }
+        __syncwarp();
+        if (C8) {
+            const int row0 = (int)(s * kSellChunk) + 2 * lane;
+            int T = 0;
+            bool ok = true;
+            for (int k = 0; k < w && ok; ++k) {
+                const int2 cc = *reinterpret_cast<const int2 *>(tc + k * kSellChunk + 2 * lane);
+                const int off[2] = {cc.x - row0, cc.y - (row0 + 1)};
+                int id[2];
+                ok = sell_dict_step(tab, T, off, id);
+                if (ok) *reinterpret_cast<uchar2 *>(ti + k * kSellChunk + 2 * lane) = make_uchar2((unsigned char)id[0], (unsigned char)id[1]);
+            }
+            if (!ok) T = kSellDictCap + 1;
+            if (lane == 0 && T > a.tpad) atomicMax(a.max_tab, T);
+            __syncwarp();
+            for (int t = lane; t < a.tpad; t += 32) a.tab[s * a.tpad + t] = t < T ? tab[t] : 0;
+        }
+        if (a.is_boundary) {
+            ghost = __any_sync(0xffffffffu, ghost);
+            if (lane == 0) a.is_boundary[s] = ghost;
+        }
+        // the staged slice goes out as bulk stores: make the generic-proxy writes visible to the async proxy first
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0 && w > 0) {
+            const uint32_t sv = (uint32_t)__cvta_generic_to_shared(tv);
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                         ::"l"(a.val + base), "r"(sv), "r"((uint32_t)w * kSellChunk * 8) : "memory");
+            if (C8) {
+                const uint32_t si = (uint32_t)__cvta_generic_to_shared(ti);
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                             ::"l"(a.idx8 + base), "r"(si), "r"((uint32_t)w * kSellChunk) : "memory");
+            } else {
+                const uint32_t sc = (uint32_t)__cvta_generic_to_shared(tc);
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                             ::"l"(a.col + base), "r"(sc), "r"((uint32_t)w * kSellChunk * 4) : "memory");
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");       // the tile is reused by the next slice
+        }
+        __syncwarp();
+    }
+}
+
+// Direct-to-SELL assembly of one GPU's slab.  Fills A's SELL arrays, slice tables, row lengths, diagonal and
+// right-hand side; leaves the CSR unbuilt (sell.cu: sell_to_csr builds it on demand for exports / ILU).
+// Returns 0 with *done = false when the slice tables do not fit the analytic bound (the caller then takes the
+// CSR-first path) — cannot happen for slab partitions, kept as a guard.
+int cube_assemble_sell(const CubeGeom &c, int mode, bool byte_index, heat_matrix *A, double *d_b, cudaStream_t st, bool *done) {
+    *done = false;
+    const int64_t n = c.n_owned;
+    const int64_t ns = (n + kSellChunk - 1) / kSellChunk;
+    if (ns == 0) return 0;
+    cudaEvent_t e0, e1;
+    HEAT_CUDA(cudaEventCreate(&e0)); HEAT_CUDA(cudaEventCreate(&e1));
+    A->n_slices = ns;
+    HEAT_TRY(A->slice_ptr.alloc((size_t)ns + 1));
+    HEAT_TRY(A->diag.alloc((size_t)n)); HEAT_TRY(A->dinv.alloc((size_t)n)); HEAT_TRY(A->sell_rowlen.alloc((size_t)n));
+    DevBuf<int64_t> entries; HEAT_TRY(entries.alloc((size_t)ns));
+    DevBuf<unsigned long long> d_nnz; HEAT_TRY(d_nnz.alloc(1));
+    DevBuf<int> d_maxtab; HEAT_TRY(d_maxtab.alloc(1));
+    HEAT_CUDA(cudaMemsetAsync(d_nnz.p, 0, sizeof(unsigned long long), st));
+    HEAT_CUDA(cudaMemsetAsync(d_maxtab.p, 0, sizeof(int), st));
+    HEAT_CUDA(cudaMemsetAsync(A->slice_ptr.p, 0, sizeof(int64_t), st));
+    cube_width_kernel<<<(unsigned)((ns + kWarpsPerBlock - 1) / kWarpsPerBlock), kBlock, 0, st>>>(c, ns, entries.p, d_nnz.p);
+    HEAT_LAUNCHED();
+    size_t tb = 0;
+    HEAT_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tb, entries.p, A->slice_ptr.p + 1, ns, st));
+    DevBuf<char> tmp; HEAT_TRY(tmp.alloc(tb));
+    HEAT_CUDA(cub::DeviceScan::InclusiveSum(tmp.p, tb, entries.p, A->slice_ptr.p + 1, ns, st));
+    unsigned long long h_nnz = 0;
+    HEAT_CUDA(cudaMemcpyAsync(&A->sell_padded, A->slice_ptr.p + ns, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    HEAT_CUDA(cudaMemcpyAsync(&h_nnz, d_nnz.p, sizeof(h_nnz), cudaMemcpyDeviceToHost, st));
+    HEAT_CUDA(cudaStreamSynchronize(st));
+    A->nnz = (int64_t)h_nnz;
+    A->max_row_len = (int32_t)(A->sell_padded > 0 ? 15 : 0);
+    // offsets a slice can see: the 15 stencil offsets, 4 more per ghost plane (the dk = -1 / +1 slots of the rows
+    // next to it), the tail rows' -64
+    const int tpad = (c.ghost_lo || c.ghost_hi) ? 24 : 16;
+    CubeSellArgs a;
+    a.c = c; a.mode = mode; a.slice_ptr = A->slice_ptr.p; a.n_slices = ns;
+    HEAT_TRY(A->sell_val.alloc((size_t)A->sell_padded));
+    a.val = A->sell_val.p; a.col = nullptr; a.idx8 = nullptr; a.tab = nullptr; a.tpad = 0;
+    if (byte_index) {
+        HEAT_TRY(A->sell_idx8.alloc((size_t)A->sell_padded));
+        HEAT_TRY(A->sell_tab.alloc((size_t)ns * (size_t)tpad));
+        a.idx8 = A->sell_idx8.p; a.tab = A->sell_tab.p; a.tpad = tpad;
+    } else {
+        HEAT_TRY(A->sell_col.alloc((size_t)A->sell_padded));
+        a.col = A->sell_col.p;
+    }
+    a.rowlen = A->sell_rowlen.p; a.diag = A->diag.p; a.dinv = A->dinv.p; a.b = d_b;
+    DevBuf<int32_t> flags;
+    const bool need_split = A->n_ghost > 0;
+    if (need_split) HEAT_TRY(flags.alloc((size_t)ns));
+    a.is_boundary = need_split ? flags.p : nullptr;
+    a.max_tab = d_maxtab.p;
+    const size_t smem = (size_t)kCubeWarps * kCubeTileBytes;
+    int dev = 0, sms = 148;
+    HEAT_CUDA(cudaGetDevice(&dev));
+    HEAT_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    int64_t blocks = (ns + kCubeWarps - 1) / kCubeWarps;
+    if (blocks > (int64_t)sms * 2 * 8) blocks = (int64_t)sms * 2 * 8;       // persistent-ish: 8 waves of 2 CTAs per SM
+    HEAT_CUDA(cudaEventRecord(e0, st));
+    if (byte_index) {
+        HEAT_CUDA(cudaFuncSetAttribute(cube_sell_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cube_sell_kernel<true><<<(unsigned)blocks, kCubeWarps * 32, smem, st>>>(a);
+    } else {
+        HEAT_CUDA(cudaFuncSetAttribute(cube_sell_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cube_sell_kernel<false><<<(unsigned)blocks, kCubeWarps * 32, smem, st>>>(a);
+    }
+    HEAT_LAUNCHED();
+    HEAT_CUDA(cudaEventRecord(e1, st));
+    int h_maxtab = 0;
+    HEAT_CUDA(cudaMemcpyAsync(&h_maxtab, d_maxtab.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    std::vector<int32_t> h_flags;
+    if (need_split) {
+        h_flags.resize((size_t)ns);
+        HEAT_CUDA(cudaMemcpyAsync(h_flags.data(), flags.p, sizeof(int32_t) * (size_t)ns, cudaMemcpyDeviceToHost, st));
+    }
+    HEAT_CUDA(cudaStreamSynchronize(st));
+    float fill_ms = 0.f;
+    HEAT_CUDA(cudaEventElapsedTime(&fill_ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    A->assemble_fill_ms = fill_ms;
+    if (h_maxtab > tpad) {          // guard: a slice saw more distinct offsets than the analytic bound
+        A->sell_val.release(); A->sell_idx8.release(); A->sell_tab.release(); A->sell_col.release(); A->sell_rowlen.release();
+        A->slice_ptr.release(); A->diag.release(); A->dinv.release();
+        A->n_slices = 0; A->sell_padded = 0; A->nnz = 0;
+        return 0;
+    }
+    A->sell_tpad = byte_index ? tpad : 0;
+    HEAT_TRY(sell_finish_lists(A, need_split ? h_flags.data() : nullptr, st));
+    *done = true;
+    return 0;
 }
 
 int cube_assemble(const CubeGeom &c, int mode, heat_matrix *A, double *d_b, cudaStream_t st) {

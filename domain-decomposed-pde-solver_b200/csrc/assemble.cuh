@@ -21,6 +21,9 @@ struct GeneralAssembler {
     DevBuf<double> x, y, z, bc;
     DevBuf<int32_t> conn, red, n2e, gcol;
     DevBuf<int64_t> red2orig, n2e_ptr, grow_ptr;
+    // device time by phase (CUDA events on the assembly stream): node->element radix sort, pattern count,
+    // pattern fill, values — what bench.py --assemble explicit reports
+    float phase_ms[4] = {0.f, 0.f, 0.f, 0.f};
 
     int upload(const HostMesh &m, const std::vector<double> &node_bc, cudaStream_t st);
     int make_cube(int nx, int ny, int nz, cudaStream_t st);
@@ -32,6 +35,9 @@ struct GeneralAssembler {
                     const int64_t *d_lrow_ptr, int32_t *d_lcol, double *d_lval, double *d_b, cudaStream_t st);
 };
 
+// CSR-first path (one thread per row; kept as the fallback and for HEAT_CUBE_ASSEMBLY=csr)
 int cube_assemble(const CubeGeom &c, int mode, heat_matrix *A, double *d_b, cudaStream_t st);
+// default: one warp per slice straight into the SELL arrays (+ byte indices, tables, diagonal, row lengths)
+int cube_assemble_sell(const CubeGeom &c, int mode, bool byte_index, heat_matrix *A, double *d_b, cudaStream_t st, bool *done);
 
 }  // namespace heat

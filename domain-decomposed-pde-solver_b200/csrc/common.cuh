@@ -81,7 +81,8 @@ struct DevBuf {
 constexpr int kSellRowsPerLane = 2;                      // R
 constexpr int kSellChunk = 32 * kSellRowsPerLane;        // C: rows per SELL slice (one warp)
 constexpr int kSellDictCap = 64;                         // most distinct col-row offsets a slice may have to be byte-indexed
-constexpr int kMaxPartials = 4096;                       // per-launch block partials capacity
+constexpr int kMaxPartials = 4096;
+constexpr int kMaxDevices = 64;                          // per-device caches (function attributes, SM counts)                       // per-launch block partials capacity
 
 // one entry per slice in SpMV processing order (interior slices first, then boundary slices; natural
 // order on one GPU): everything a warp needs to start streaming the slice, in ONE 16-byte load
@@ -138,6 +139,8 @@ struct heat_matrix {
     heat::DevBuf<double> sell_val;
     // byte-indexed column stream (built when EVERY slice has <= kSellDictCap distinct col-row offsets):
     // col = row + sell_tab[slice][sell_idx8[entry]]; 1 byte per entry instead of 4
+    heat::DevBuf<uint8_t> sell_rowlen;   // stored entries per row — only for matrices assembled straight into SELL (no CSR
+                                         // until sell_to_csr rebuilds one for an export or ILU)
     heat::DevBuf<uint8_t> sell_idx8;
     heat::DevBuf<int32_t> sell_tab;
     int sell_tpad = 0;
@@ -162,7 +165,10 @@ struct heat_matrix {
     heat::DevBuf<double> partials;       // [2 * kMaxPartials * 4]
     heat::DevBuf<double> scal;           // [S_COUNT]
     heat::DevBuf<int> iscal;             // [I_COUNT]
+    double cheb_lmax_est = 0.0;          // lambda_max(D^-1 A) estimated by 10 power iterations, once per matrix
     double assemble_ms = 0.0;
+    double assemble_fill_ms = 0.0;       // the matrix-fill kernel alone (cube_sell_kernel / values_kernel), CUDA events
+    double asm_phase_ms[4] = {0, 0, 0, 0};   // explicit-mesh path: node->element sort, pattern count, pattern fill, values
 };
 
 struct ExoFile;   // exodus.hpp

@@ -106,7 +106,10 @@ int gmres_device(heat_ctx *ctx, heat_matrix *A, double *x, const double *b, cons
     if (!A->w_u.p) HEAT_TRY(A->w_u.alloc(nv));
     if (o.prec == HEAT_PREC_ILU0) HEAT_TRY(ilu0_setup(ctx, A));
     double lmax = o.cheb_lambda_max;
-    if (o.prec == HEAT_PREC_CHEBYSHEV && !(lmax > 0.0)) HEAT_TRY(estimate_lambda_max(ctx, A, &lmax));
+    if (o.prec == HEAT_PREC_CHEBYSHEV && !(lmax > 0.0)) {
+        if (!(A->cheb_lmax_est > 0.0)) HEAT_TRY(estimate_lambda_max(ctx, A, &A->cheb_lmax_est));
+        lmax = A->cheb_lmax_est;
+    }
 
     const int64_t stride = (n + 1) & ~(int64_t)1;
     if ((double)stride * (double)(m + 1) * 8.0 > 150e9)

@@ -88,6 +88,7 @@ int ilu0_setup(heat_ctx *ctx, heat_matrix *A) {
     if (A->ilu) return 0;
     const int64_t n = A->n_owned, nnz = A->nnz;
     cudaStream_t st = ctx->stream;
+    HEAT_TRY(sell_to_csr(A, st));                     // matrices assembled straight into SELL have no CSR yet
     std::vector<int64_t> rp((size_t)n + 1);
     std::vector<int32_t> col((size_t)nnz);
     HEAT_CUDA(cudaStreamSynchronize(st));

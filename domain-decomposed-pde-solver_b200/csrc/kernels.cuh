@@ -43,6 +43,8 @@ int trace_set_spmv(TraceBuf *buf);
 #endif
 // ---- sell.cu ----
 int sell_from_csr(heat_matrix *A, cudaStream_t st);
+int sell_finish_lists(heat_matrix *A, const int32_t *h_flags, cudaStream_t st);   // interior/boundary lists + slice_meta
+int sell_to_csr(heat_matrix *A, cudaStream_t st);      // builds row_ptr/col/val from the SELL arrays if absent
 // ---- spmv.cu ----
 // y = A x over entries [first, first + n_list) of A->slice_meta (processing order: interior slices, then
 // boundary slices).  gate.H == nullptr disables the CG stopping test; dot.out == nullptr disables the

@@ -7,6 +7,7 @@
 
 #include "device_utils.cuh"
 #include "kernels.cuh"
+#include "sell_dict.cuh"
 
 namespace heat {
 
@@ -94,23 +95,7 @@ sell_dict_kernel(const int64_t *__restrict__ slice_ptr, const int32_t *__restric
         const int2 c = *reinterpret_cast<const int2 *>(scol + base + (int64_t)k * kSellChunk + 2 * lane);
         const int off[2] = {c.x - row0, c.y - (row0 + 1)};
         int id[2];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            int found = -1;
-            for (int t = 0; t < T; ++t)
-                if (tab[t] == off[h]) { found = t; break; }
-            unsigned miss = __ballot_sync(0xffffffffu, found < 0);
-            while (miss && !overflow) {
-                const int v = __shfl_sync(0xffffffffu, off[h], __ffs(miss) - 1);
-                if (T >= kSellDictCap) { overflow = true; break; }
-                if (lane == 0) tab[T] = v;
-                __syncwarp();
-                if (found < 0 && off[h] == v) found = T;
-                ++T;
-                miss = __ballot_sync(0xffffffffu, found < 0);
-            }
-            id[h] = found;
-        }
+        overflow = !sell_dict_step(tab, T, off, id);
         if (WRITE && !overflow)
             *reinterpret_cast<uchar2 *>(idx8 + base + (int64_t)k * kSellChunk + 2 * lane) =
                 make_uchar2((unsigned char)id[0], (unsigned char)id[1]);
@@ -175,6 +160,92 @@ int launch_extract_diag(const heat_matrix *A, cudaStream_t st) {
     return 0;
 }
 
+// interior / boundary slice lists (h_flags[s] != 0: slice s references a ghost column; null: no ghosts) and the
+// packed per-slice metadata in processing order
+int sell_finish_lists(heat_matrix *A, const int32_t *h_flags, cudaStream_t st) {
+    const int64_t ns = A->n_slices;
+    A->n_int_slices = ns;
+    A->n_bnd_slices = 0;
+    if (h_flags && ns > 0) {
+        std::vector<int32_t> li, lb;
+        for (int64_t s = 0; s < ns; ++s) (h_flags[(size_t)s] ? lb : li).push_back((int32_t)s);
+        A->n_int_slices = (int64_t)li.size();
+        A->n_bnd_slices = (int64_t)lb.size();
+        HEAT_TRY(A->slices_interior.alloc(li.size()));
+        HEAT_TRY(A->slices_boundary.alloc(lb.size()));
+        std::vector<int32_t> all(li);
+        all.insert(all.end(), lb.begin(), lb.end());
+        HEAT_TRY(A->slices_all.alloc(all.size()));
+        if (!all.empty())
+            HEAT_CUDA(cudaMemcpyAsync(A->slices_all.p, all.data(), sizeof(int32_t) * all.size(), cudaMemcpyHostToDevice, st));
+        if (!li.empty())
+            HEAT_CUDA(cudaMemcpyAsync(A->slices_interior.p, li.data(), sizeof(int32_t) * li.size(), cudaMemcpyHostToDevice, st));
+        if (!lb.empty())
+            HEAT_CUDA(cudaMemcpyAsync(A->slices_boundary.p, lb.data(), sizeof(int32_t) * lb.size(), cudaMemcpyHostToDevice, st));
+        HEAT_CUDA(cudaStreamSynchronize(st));          // the host vectors die here
+    }
+    HEAT_TRY(A->slice_meta.alloc((size_t)ns));
+    if (ns > 0) {
+        slice_meta_kernel<<<(unsigned)((ns + 255) / 256), 256, 0, st>>>(A->slice_ptr.p, A->n_ghost > 0 ? A->slices_all.p : nullptr, ns,
+                                                                      A->slice_meta.p);
+        HEAT_LAUNCHED();
+    }
+    return 0;
+}
+
+// ---- SELL -> CSR (export / ILU only): matrices assembled straight into the SpMV format have no CSR until asked ----
+__global__ void rowlen_widen_kernel(const uint8_t *__restrict__ len8, int64_t n, int64_t *__restrict__ len64) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r <= n) len64[r] = r < n ? (int64_t)len8[r] : 0;
+}
+__global__ void __launch_bounds__(kBlock)
+sell_to_csr_kernel(const int64_t *__restrict__ slice_ptr, const double *__restrict__ sval, const int32_t *__restrict__ scol,
+                   const uint8_t *__restrict__ idx8, const int32_t *__restrict__ tabs, int tpad, const uint8_t *__restrict__ rowlen,
+                   int64_t n_rows, int64_t n_slices, const int64_t *__restrict__ row_ptr, int32_t *__restrict__ col,
+                   double *__restrict__ val) {
+    const int lane = threadIdx.x & 31;
+    const int64_t s = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    if (s >= n_slices) return;
+    const int64_t base = slice_ptr[s];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int64_t row = s * kSellChunk + 2 * lane + h;
+        if (row >= n_rows) continue;
+        const int len = rowlen[row];
+        const int64_t o = row_ptr[row];
+        for (int k = 0; k < len; ++k) {
+            const int64_t e = base + (int64_t)k * kSellChunk + 2 * lane + h;
+            col[o + k] = idx8 ? (int32_t)row + tabs[s * tpad + idx8[e]] : scol[e];
+            val[o + k] = sval[e];
+        }
+    }
+}
+int sell_to_csr(heat_matrix *A, cudaStream_t st) {
+    if (A->row_ptr.p) return 0;
+    if (!A->sell_rowlen.p || !A->sell_val.p) HEAT_FAIL(60, "matrix has neither a CSR nor row lengths to rebuild it from");
+    const int64_t n = A->n_owned, ns = A->n_slices;
+    HEAT_TRY(A->row_ptr.alloc((size_t)n + 1));
+    {
+        DevBuf<int64_t> len64; HEAT_TRY(len64.alloc((size_t)n + 1));
+        rowlen_widen_kernel<<<(unsigned)((n + 256) / 256), 256, 0, st>>>(A->sell_rowlen.p, n, len64.p);
+        HEAT_LAUNCHED();
+        size_t tb = 0;
+        HEAT_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, len64.p, A->row_ptr.p, n + 1, st));
+        DevBuf<char> tmp; HEAT_TRY(tmp.alloc(tb));
+        HEAT_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, len64.p, A->row_ptr.p, n + 1, st));
+        HEAT_CUDA(cudaStreamSynchronize(st));
+    }
+    HEAT_TRY(A->col.alloc((size_t)A->nnz)); HEAT_TRY(A->val.alloc((size_t)A->nnz));
+    if (ns > 0) {
+        sell_to_csr_kernel<<<(unsigned)((ns + kWarpsPerBlock - 1) / kWarpsPerBlock), kBlock, 0, st>>>(
+            A->slice_ptr.p, A->sell_val.p, A->sell_col.p, A->sell_idx8.p, A->sell_tab.p, A->sell_tpad, A->sell_rowlen.p, n, ns,
+            A->row_ptr.p, A->col.p, A->val.p);
+        HEAT_LAUNCHED();
+    }
+    HEAT_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
 int sell_from_csr(heat_matrix *A, cudaStream_t st) {
     const int64_t n = A->n_owned;
     A->n_slices = (n + kSellChunk - 1) / kSellChunk;
@@ -204,38 +275,15 @@ int sell_from_csr(heat_matrix *A, cudaStream_t st) {
             A->row_ptr.p, A->col.p, A->val.p, n, A->n_owned, ns, A->slice_ptr.p, A->sell_col.p, A->sell_val.p,
             need_split ? flags.p : nullptr);
         HEAT_LAUNCHED();
-        A->n_int_slices = ns;
-        A->n_bnd_slices = 0;
+        std::vector<int32_t> h;
         if (need_split) {
-            std::vector<int32_t> h((size_t)ns);
+            h.resize((size_t)ns);
             HEAT_CUDA(cudaMemcpyAsync(h.data(), flags.p, sizeof(int32_t) * (size_t)ns, cudaMemcpyDeviceToHost, st));
             HEAT_CUDA(cudaStreamSynchronize(st));
-            std::vector<int32_t> li, lb;
-            for (int64_t s = 0; s < ns; ++s) (h[(size_t)s] ? lb : li).push_back((int32_t)s);
-            A->n_int_slices = (int64_t)li.size();
-            A->n_bnd_slices = (int64_t)lb.size();
-            HEAT_TRY(A->slices_interior.alloc(li.size()));
-            HEAT_TRY(A->slices_boundary.alloc(lb.size()));
-            {
-                std::vector<int32_t> all(li);
-                all.insert(all.end(), lb.begin(), lb.end());
-                HEAT_TRY(A->slices_all.alloc(all.size()));
-                if (!all.empty())
-                    HEAT_CUDA(cudaMemcpyAsync(A->slices_all.p, all.data(), sizeof(int32_t) * all.size(), cudaMemcpyHostToDevice, st));
-                HEAT_CUDA(cudaStreamSynchronize(st));
-            }
-            if (!li.empty())
-                HEAT_CUDA(cudaMemcpyAsync(A->slices_interior.p, li.data(), sizeof(int32_t) * li.size(), cudaMemcpyHostToDevice, st));
-            if (!lb.empty())
-                HEAT_CUDA(cudaMemcpyAsync(A->slices_boundary.p, lb.data(), sizeof(int32_t) * lb.size(), cudaMemcpyHostToDevice, st));
-            HEAT_CUDA(cudaStreamSynchronize(st));
         }
-    }
-    HEAT_TRY(A->slice_meta.alloc((size_t)ns));
-    if (ns > 0) {
-        slice_meta_kernel<<<(unsigned)((ns + 255) / 256), 256, 0, st>>>(A->slice_ptr.p, A->n_ghost > 0 ? A->slices_all.p : nullptr, ns,
-                                                                      A->slice_meta.p);
-        HEAT_LAUNCHED();
+        HEAT_TRY(sell_finish_lists(A, need_split ? h.data() : nullptr, st));
+    } else {
+        HEAT_TRY(sell_finish_lists(A, nullptr, st));
     }
     HEAT_TRY(sell_build_dict(A, st));
     HEAT_TRY(launch_extract_diag(A, st));

@@ -13,14 +13,15 @@
 
 namespace heat {
 
-static int g_sm_count = 0;
 int sm_count(int device) {
-    if (g_sm_count == 0) {
-        cudaDeviceProp prop;
-        if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return 148;
-        g_sm_count = prop.multiProcessorCount;
+    static int cached[kMaxDevices] = {};                 // per device: a process may hold contexts on several GPUs
+    if (device < 0 || device >= kMaxDevices) return 148;
+    if (cached[device] == 0) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || v <= 0) return 148;
+        cached[device] = v;
     }
-    return g_sm_count;
+    return cached[device];
 }
 
 // y = A x with the halo exchange of x overlapped with the interior slices
@@ -42,6 +43,58 @@ int spmv_halo(heat_ctx *ctx, heat_matrix *A, double *x, double *y, CgGate gate, 
     HEAT_TRY(halo_end(ctx, A));
     d.part_offset = g1c;
     HEAT_TRY(launch_spmv(A, x, y, A->n_int_slices, A->n_bnd_slices, gate, d, g2, ctx->stream));
+    return 0;
+}
+
+// y = A x through the PEER-MEMORY halo path — the very launch the multi-GPU CG loop makes (halo pushed into the
+// neighbours' ghost segments by peer stores, ONE SpMV launch over [interior | boundary] slices, the boundary slices
+// waiting on the neighbours' epoch flags) — as a stand-alone collective: parity and measurement hook (heat_spmv
+// itself goes through the NCCL halo).  The kernel is launched `repeat` times on the same input; *kernel_ms is the
+// average device time of one launch, *xy_global the all-reduced sum_i x_i y_i.
+int spmv_peer_once(heat_ctx *ctx, heat_matrix *A, const double *x, double *y, int repeat, double *xy_global, double *kernel_ms) {
+    HEAT_CUDA(cudaSetDevice(ctx->device));
+    if (ctx->nranks < 2 || !ctx->peer_enabled) HEAT_FAIL(52, "heat_spmv_peer: the peer-memory path is not available (one rank, HEAT_COMM=nccl, or no CUDA IPC)");
+    HEAT_TRY(ensure_workspace(A, false, false));
+    if (!A->peer) HEAT_TRY(peer_matrix_setup(ctx, A));
+    if (!A->peer) HEAT_FAIL(52, "heat_spmv_peer: peer-memory set-up failed for this matrix");
+    if (repeat < 1) repeat = 1;
+    cudaStream_t st = ctx->stream;
+    const int which = (int)(ctx->peer_halo_epoch & 1);                 // alternate the two IPC-mapped input buffers
+    double *pin = which ? A->w_p2.p : A->w_p.p;
+    double *S = A->scal.p;
+    int *I = A->iscal.p;
+    HEAT_CUDA(cudaMemsetAsync(I, 0, sizeof(int) * I_COUNT, st));
+    HEAT_CUDA(cudaMemcpyAsync(pin, x, sizeof(double) * (size_t)A->n_owned, cudaMemcpyDeviceToDevice, st));
+    PeerPush pp = A->peer->push[which];
+    pp.epoch = ctx->peer_halo_epoch + 1;
+    HEAT_TRY(launch_halo_push(pin, pp, st));
+    SpmvPeer sp;
+    sp.on = true; sp.n_interior = A->n_int_slices; sp.halo = A->peer->halo;
+    sp.halo.epoch = ctx->peer_halo_epoch + 1;
+    sp.red = peer_red_of(ctx); sp.seq_out = ctx->peer_red_seq + 1; sp.I = I;
+    const int g = spmv_grid(A->n_slices, sm_count(ctx->device));
+    DotOut d{A->partials.p, 0, g, I + I_COUNTER, S + S_TMP2};
+    CgGate nogate{nullptr, nullptr, nullptr, 0};
+    HEAT_TRY(launch_spmv_peer(A, pin, y, nogate, d, sp, g, st));       // first launch: includes the wait for the halo
+    HEAT_CUDA(cudaEventRecord(ctx->ev_a, st));
+    for (int q = 1; q < repeat; ++q) HEAT_TRY(launch_spmv_peer(A, pin, y, nogate, d, sp, g, st));
+    HEAT_CUDA(cudaEventRecord(ctx->ev_b, st));
+    // the all-reduce doubles as the cross-rank fence: once it completes here, every rank's SpMV has read its
+    // ghosts, so the next call may push into the same buffers
+    HEAT_TRY(comm_allreduce_sum(ctx, S + S_TMP2, 1));
+    double h_xy = 0.0;
+    int hI[2] = {0, 0};
+    HEAT_CUDA(cudaMemcpyAsync(&h_xy, S + S_TMP2, sizeof(double), cudaMemcpyDeviceToHost, st));
+    HEAT_CUDA(cudaMemcpyAsync(hI, I, sizeof(hI), cudaMemcpyDeviceToHost, st));
+    HEAT_CUDA(cudaStreamSynchronize(st));
+    ctx->peer_halo_epoch += 4; ctx->peer_red_seq += 4;                 // identical on every rank
+    if (hI[I_STATUS] == 3) HEAT_FAIL(51, "heat_spmv_peer: peer-memory halo timed out");
+    if (xy_global) *xy_global = h_xy;
+    if (kernel_ms) {
+        float ms = 0.f;
+        if (repeat > 1) HEAT_CUDA(cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b));
+        *kernel_ms = repeat > 1 ? ms / (repeat - 1) : 0.0;
+    }
     return 0;
 }
 
@@ -220,7 +273,10 @@ int solve_device(heat_ctx *ctx, heat_matrix *A, double *x, const double *b, cons
     CgGate nogate{nullptr, nullptr, nullptr, 0};
 
     double lmax = o.cheb_lambda_max;
-    if (is_cheb && !(lmax > 0.0)) HEAT_TRY(estimate_lambda_max(ctx, A, &lmax));
+    if (is_cheb && !(lmax > 0.0)) {                  // Ifpack2 estimates lambda_max once, at set-up: cached with the matrix
+        if (!(A->cheb_lmax_est > 0.0)) HEAT_TRY(estimate_lambda_max(ctx, A, &A->cheb_lmax_est));
+        lmax = A->cheb_lmax_est;
+    }
 
     HEAT_CUDA(cudaEventRecord(ctx->ev_a, st));
     // ---- r0 = b - A x0 ; z0 ; p0 (or u0, w0) ; H[0] ----

@@ -8,6 +8,7 @@
 namespace heat {
 int sm_count(int device);
 int spmv_halo(heat_ctx *ctx, heat_matrix *A, double *x, double *y, CgGate gate, double *dot_out, bool with_yy = false);
+int spmv_peer_once(heat_ctx *ctx, heat_matrix *A, const double *x, double *y, int repeat, double *xy_global, double *kernel_ms);
 int power_method_device(heat_ctx *ctx, heat_matrix *A, int niters, double tol, uint64_t seed, heat_power_info *info);
 int ensure_workspace(heat_matrix *A, bool single_reduce, bool cheb);
 // on_poll (optional) is called with the iteration count after every host poll (every check_every

@@ -365,10 +365,11 @@ static int launch_tma(const heat_matrix *A, const double *x, double *y, int64_t 
                       CgGate gate, DotOut dot, int grid, cudaStream_t st) {
     auto kern = sell_spmv_tma_kernel<DOT, KC, NSTAGE, NWARPS, false, C8, MINB>;
     const size_t smem = TmaSmem<KC, NSTAGE, C8>::total(NWARPS);
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[kMaxDevices] = {};            // function attributes are per DEVICE, not per process
+    const int dev = A->ctx->device;
+    if (dev < 0 || dev >= kMaxDevices || !configured[dev]) {
         HEAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
+        if (dev >= 0 && dev < kMaxDevices) configured[dev] = true;
     }
     kern<<<grid, NWARPS * 32, smem, st>>>(A->slice_meta.p + first, A->sell_col.p, A->sell_val.p, x, y, A->n_owned,
                                          n_list, gate, dot, SpmvPeer(), dict_of(A));
@@ -385,10 +386,11 @@ static int launch_spmv_peer_t(const heat_matrix *A, const double *x, double *y, 
     constexpr int NW = C8 ? kC8Warps : 8;
     auto kern = sell_spmv_tma_kernel<1, 8, 2, NW, true, C8, 2>;
     const size_t smem = TmaSmem<8, 2, C8>::total(NW);
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[kMaxDevices] = {};
+    const int dev = A->ctx->device;
+    if (dev < 0 || dev >= kMaxDevices || !configured[dev]) {
         HEAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
+        if (dev >= 0 && dev < kMaxDevices) configured[dev] = true;
     }
     const int64_t n_list = A->n_slices;                   // slice_meta order: interior slices, then boundary slices
     if (A->n_ghost == 0) peer.n_interior = n_list;

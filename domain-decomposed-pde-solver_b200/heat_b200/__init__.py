@@ -47,7 +47,9 @@ class MatrixInfo(C.Structure):
                 ("max_row_len", C.c_int32), ("npe", C.c_int32), ("num_dim", C.c_int32), ("num_node_sets", C.c_int32),
                 ("rank", C.c_int32), ("nranks", C.c_int32), ("n_neighbors", C.c_int32), ("sell_chunk", C.c_int32),
                 ("sell_padded_nnz", C.c_int64), ("n_boundary_slices", C.c_int64), ("n_slices", C.c_int64),
-                ("assemble_ms", C.c_double), ("peer_path", C.c_int32), ("col_index_bytes", C.c_int32)]
+                ("assemble_ms", C.c_double), ("peer_path", C.c_int32), ("col_index_bytes", C.c_int32),
+                ("assemble_fill_ms", C.c_double), ("asm_phase_ms", C.c_double * 4), ("csr_resident", C.c_int32),
+                ("reserved0", C.c_int32), ("matrix_bytes", C.c_int64)]
 
 
 class PowerInfo(C.Structure):
@@ -64,7 +66,7 @@ class PlanSizes(C.Structure):
 ABI_SYMBOLS = [
     "heat_last_error", "heat_version", "heat_device_count", "heat_kernel_launches", "heat_ctx_create", "heat_ctx_set_stream", "heat_ctx_set_output", "heat_open",
     "heat_create", "heat_close", "heat_mesh_set", "heat_mesh_cube", "heat_mesh_nodeset_ids", "heat_comm_unique_id", "heat_comm_init",
-    "heat_comm_rank", "heat_assemble", "heat_get_matrix", "heat_node_owners", "heat_matrix_owned_nodeset", "heat_power_method", "heat_solve_opts_default", "heat_solve", "heat_solve_trajectory", "heat_solve_host", "heat_spmv",
+    "heat_comm_rank", "heat_assemble", "heat_get_matrix", "heat_node_owners", "heat_matrix_owned_nodeset", "heat_power_method", "heat_solve_opts_default", "heat_solve", "heat_solve_trajectory", "heat_solve_host", "heat_spmv", "heat_spmv_peer",
     "heat_cg_iterations", "heat_decompose", "heat_write_solution", "heat_write_nodal_field", "heat_nodal_field", "heat_scatter_nodal_field", "heat_reference_view_csr", "heat_decompose_partition",
     "heat_matrix_get_info", "heat_matrix_export_csr", "heat_matrix_export_maps", "heat_matrix_export_plan",
     "heat_matrix_export_red2orig", "heat_matrix_export_ilu0", "heat_matrix_free", "heat_vector_create", "heat_vector_size",
@@ -111,6 +113,7 @@ def lib():
                                         C.POINTER(C.c_int)]
     L.heat_solve_host.argtypes = [vp, vp, vp, vp, C.POINTER(SolveOpts), C.POINTER(SolveInfo)]
     L.heat_spmv.argtypes = [vp, vp, vp, vp]
+    L.heat_spmv_peer.argtypes = [vp, vp, vp, vp, C.c_int, dp, dp]
     L.heat_cg_iterations.argtypes = [vp, vp, vp, vp, C.POINTER(SolveOpts), C.c_int, C.POINTER(SolveInfo)]
     L.heat_decompose.argtypes = [vp, C.c_int]
     L.heat_write_solution.argtypes = [vp, vp, C.c_int]
@@ -490,6 +493,13 @@ class IO:
     def spmv(self, A: Matrix, x: Vector, y: Vector):
         _check(lib().heat_spmv(self.h, A.h, x.h, y.h))
 
+    def spmv_peer(self, A: Matrix, x: Vector, y: Vector, repeat: int = 1):
+        """y = A x through the peer-memory halo path (the SpMV launch of the multi-GPU CG loop); collective.
+        Returns (global x.y, average kernel ms of launches 2..repeat)."""
+        xy, ms = C.c_double(0.0), C.c_double(0.0)
+        _check(lib().heat_spmv_peer(self.h, A.h, x.h, y.h, repeat, C.byref(xy), C.byref(ms)))
+        return xy.value, ms.value
+
     def close(self):
         if self.h:
             lib().heat_close(self.h)
@@ -514,6 +524,17 @@ def node_owners(conn, num_nodes: int, epart, nparts: int) -> np.ndarray:
     _check(lib().heat_node_owners(num_nodes, conn.shape[0], conn.shape[1], _ptr(conn, C.c_int32), _ptr(epart, C.c_int64),
                                   nparts, _ptr(out, C.c_int32)))
     return out[:num_nodes]
+
+
+def maps_digest(owned, ghost, ghost_owner, nbr, send_ptr, send_gids, recv_ptr) -> str:
+    """sha1 over one rank's owned / ghost / send maps (int64, little endian, in this order) — what bench.py's parity
+    block compares with the digests tests/golden/make_parity_golden.py derived on the oracle side."""
+    import hashlib
+    h = hashlib.sha1()
+    for a in (owned, ghost, ghost_owner, nbr, send_ptr, send_gids, recv_ptr):
+        h.update(np.ascontiguousarray(np.asarray(a).ravel(), dtype="<i8").tobytes())
+        h.update(b"|")
+    return h.hexdigest()
 
 
 def plan_build(row_ptr, col, part, nranks: int, rank: int) -> dict:

@@ -164,6 +164,14 @@ int  heat_solve_host(heat_ctx *ctx, heat_matrix *A, const double *b_host, double
 
 /* y = A x  (Tpetra::CrsMatrix::apply; explicit use at ExodusMatrixTest.cpp:101) incl. halo.      */
 int  heat_spmv(heat_ctx *ctx, heat_matrix *A, heat_vector *x, heat_vector *y);
+/* The same product through the PEER-MEMORY halo path, i.e. the very SpMV launch the multi-GPU CG loop makes
+ * (Tpetra's Import inside apply, replaced by NVLink peer stores + epoch flags, csrc/peer.cuh) — heat_spmv goes
+ * through the NCCL halo.  Collective; fails with code 52 where the peer path is unavailable (one rank,
+ * HEAT_COMM=nccl, no CUDA IPC).  The kernel is launched `repeat` (>= 1) times on the same input;
+ * *kernel_ms (may be NULL) = average device time of launches 2..repeat, *xy_global (may be NULL) = sum_i x_i y_i
+ * over all ranks.  Parity and measurement hook.                                                    */
+int  heat_spmv_peer(heat_ctx *ctx, heat_matrix *A, heat_vector *x, heat_vector *y, int repeat,
+                    double *xy_global, double *kernel_ms);
 /* fixed number of CG iterations with no convergence exit (bench hook; same kernels as solve)    */
 int  heat_cg_iterations(heat_ctx *ctx, heat_matrix *A, heat_vector *X, const heat_vector *B,
                         const heat_solve_opts *opts, int iters, heat_solve_info *info);
@@ -208,6 +216,14 @@ typedef struct {
     int32_t peer_path;        /* 1 once the NVLink peer-memory halo/all-reduce path is set up      */
     int32_t col_index_bytes;  /* bytes per stored entry of the SpMV column stream: 4 (int32 ids), or 1
                                  (index into the slice's table of distinct col-row offsets)        */
+    double  assemble_fill_ms; /* the matrix-fill kernel alone (analytic cubes: cube_sell_kernel, straight into the
+                                 SpMV format; explicit meshes: values_kernel), CUDA events               */
+    double  asm_phase_ms[4];  /* explicit-mesh assembly by phase: node->element radix sort, pattern count,
+                                 pattern fill, values (0 for the analytic cube path)                     */
+    int32_t csr_resident;     /* 1 if a CSR copy is resident (always for explicit meshes; analytic cubes are
+                                 assembled straight into SELL and build the CSR only for an export / ILU)  */
+    int32_t reserved0;
+    int64_t matrix_bytes;     /* device bytes held by the matrix arrays (CSR + SELL + tables + diagonal)  */
 } heat_matrix_info;
 int  heat_matrix_get_info(const heat_matrix *A, heat_matrix_info *info);
 /* local CSR: row_ptr[n_owned+1] (int64), col[nnz_local] LOCAL column ids (int32), val.           */

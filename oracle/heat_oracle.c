@@ -22,6 +22,15 @@ int oracle_num_threads(void) {
 #endif
 }
 
+/* bench.py sets the thread count explicitly: a launcher (torchrun) may have exported OMP_NUM_THREADS=1 */
+void oracle_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 /* ---------------------------------------------------------------------------------------------
  * P1 element rows.  K_ab = vol * grad(phi_a).grad(phi_b), written as (G_a.G_b) * s with
  * G = det * grad(phi) (cross products of edges) and s = 1/(6|det|) (tets) or 1/(2|det|) (tris).
@@ -238,6 +247,131 @@ void oracle_cube_mesh(int nx, int ny, int nz, double *x, double *y, double *z, i
             }
 }
 
+/* ---------------------------------------------------------------------------------------------
+ * oracle_assemble(oracle_cube_mesh(nx,ny,nz)) WITHOUT materialising the mesh: the same system, bit for
+ * bit (tests/test_oracle_golden.py::test_cube_analytic_equals_explicit), built row by row from the
+ * closed form of the Kuhn cube's connectivity.  It exists so that the CPU baseline of bench.py can be
+ * timed on the 512^3 headline configuration itself (the explicit mesh + node->element lists of that
+ * size need ~100 GB of host memory; this needs the 24.5 GB CSR only).
+ *   DOF row r <-> node (i,j,k), 1 <= i <= nx-2:  r = (i-1) + (nx-2)*(j + ny*k)
+ *   neighbours = +-(di,dj,dk), (di,dj,dk) in {0,1}^3 \ 0  (the 7 edge classes of the Kuhn split);
+ *   slot 7 +- (di + 2 dj + 4 dk) enumerates them in ascending node id (slot 7 = diagonal)
+ *   incident elements in ascending element id: cells (ck,cj,ci) ascending, then the 6 permutations;
+ *   the node is vertex a of permutation pm iff its offset inside the cell lies on pm's path.
+ * Same restated lines as oracle_assemble: ExodusIO.hpp:216-252, :340-386, :591-608, :671-687.
+ * ------------------------------------------------------------------------------------------- */
+static int cube_row_slots(int nx, int ny, int nz, int i, int j, int k, int valid[15]) {
+    int len = 0;
+    for (int s = 0; s < 15; ++s) {
+        int code = s > 7 ? s - 7 : 7 - s, sg = s > 7 ? 1 : -1;
+        int ii = i + sg * (code & 1), jj = j + sg * ((code >> 1) & 1), kk = k + sg * ((code >> 2) & 1);
+        /* stored column: the neighbour exists and is a DOF (slot 7, the diagonal, always is) */
+        valid[s] = (ii >= 1 && ii <= nx - 2 && jj >= 0 && jj < ny && kk >= 0 && kk < nz);
+        len += valid[s];
+    }
+    return len;
+}
+
+int oracle_cube_assemble(int nx, int ny, int nz, int mode, oracle_system *out) {
+    static const int perms[6][3] = {{0, 1, 2}, {0, 2, 1}, {1, 0, 2}, {1, 2, 0}, {2, 0, 1}, {2, 1, 0}};
+    memset(out, 0, sizeof(*out));
+    if (nx < 3 || ny < 2 || nz < 2) return 2;
+    const int64_t w = nx - 2, n = w * ny * (int64_t)nz, N = (int64_t)nx * ny * nz;
+    int64_t *row_ptr = (int64_t *)calloc((size_t)n + 1, sizeof(int64_t));
+    int64_t *red2orig = (int64_t *)malloc(sizeof(int64_t) * (size_t)n);
+    if (!row_ptr || !red2orig) { free(row_ptr); free(red2orig); return 4; }
+#pragma omp parallel for schedule(static)
+    for (int64_t r = 0; r < n; ++r) {
+        const int i = (int)(r % w) + 1, j = (int)((r / w) % ny), k = (int)(r / (w * ny));
+        int valid[15];
+        row_ptr[r + 1] = cube_row_slots(nx, ny, nz, i, j, k, valid);
+        red2orig[r] = i + (int64_t)nx * (j + (int64_t)ny * k);
+    }
+    int32_t max_row = 0;
+    for (int64_t r = 0; r < n; ++r) {
+        if (row_ptr[r + 1] > max_row) max_row = (int32_t)row_ptr[r + 1];
+        row_ptr[r + 1] += row_ptr[r];
+    }
+    const int64_t nnz = row_ptr[n];
+    int32_t *col = (int32_t *)malloc(sizeof(int32_t) * (size_t)nnz);
+    double *val = (double *)malloc(sizeof(double) * (size_t)nnz);
+    double *b = (double *)malloc(sizeof(double) * (size_t)n);
+    if (!col || !val || !b) { free(row_ptr); free(red2orig); free(col); free(val); free(b); return 4; }
+#pragma omp parallel for schedule(static)
+    for (int64_t r = 0; r < n; ++r) {
+        const int i = (int)(r % w) + 1, j = (int)((r / w) % ny), k = (int)(r / (w * ny));
+        int valid[15];
+        cube_row_slots(nx, ny, nz, i, j, k, valid);
+        double v[15], bsum = 0.0;
+        for (int s = 0; s < 15; ++s) v[s] = 0.0;
+        if (mode == ORACLE_GRAPH_LAPLACIAN) {
+            int deg = 0;
+            for (int s = 0; s < 15; ++s) {
+                if (s == 7) continue;
+                int code = s > 7 ? s - 7 : 7 - s, sg = s > 7 ? 1 : -1;
+                int ii = i + sg * (code & 1), jj = j + sg * ((code >> 1) & 1), kk = k + sg * ((code >> 2) & 1);
+                if (ii < 0 || ii >= nx || jj < 0 || jj >= ny || kk < 0 || kk >= nz) continue;
+                ++deg;
+                if (ii == 0) bsum += 1000.0; else if (ii == nx - 1) bsum += 100.0; else v[s] = -1.0;
+            }
+            v[7] = (double)deg;
+        } else {
+            for (int ck = k - 1; ck <= k; ++ck) {
+                if (ck < 0 || ck >= nz - 1) continue;
+                for (int cj = j - 1; cj <= j; ++cj) {
+                    if (cj < 0 || cj >= ny - 1) continue;
+                    for (int ci = i - 1; ci <= i; ++ci) {
+                        if (ci < 0 || ci >= nx - 1) continue;
+                        const int o[3] = {i - ci, j - cj, k - ck};
+                        for (int pm = 0; pm < 6; ++pm) {
+                            int V[4][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+                            int a = (o[0] | o[1] | o[2]) == 0 ? 0 : -1;
+                            for (int q = 0; q < 3; ++q) {
+                                for (int d = 0; d < 3; ++d) V[q + 1][d] = V[q][d];
+                                V[q + 1][perms[pm][q]] += 1;
+                                if (V[q + 1][0] == o[0] && V[q + 1][1] == o[1] && V[q + 1][2] == o[2]) a = q + 1;
+                            }
+                            if (a < 0) continue;
+                            double p[4][3], G[4][3], sc;
+                            for (int q = 0; q < 4; ++q) {
+                                p[q][0] = -5.0 + 10.0 * (double)(ci + V[q][0]) / (double)(nx - 1);
+                                p[q][1] = -5.0 + 10.0 * (double)(cj + V[q][1]) / (double)(ny - 1);
+                                p[q][2] = -5.0 + 10.0 * (double)(ck + V[q][2]) / (double)(nz - 1);
+                            }
+                            tet_G(p, G, &sc);
+                            for (int q = 0; q < 4; ++q) {
+                                double kab = ((G[a][0] * G[q][0] + G[a][1] * G[q][1]) + G[a][2] * G[q][2]) * sc;
+                                int di = V[q][0] - o[0], dj = V[q][1] - o[1], dk = V[q][2] - o[2];
+                                int code = (di != 0) + 2 * (dj != 0) + 4 * (dk != 0);
+                                int slot = (di + dj + dk) > 0 ? 7 + code : 7 - code;
+                                int ii = i + di;
+                                if (ii == 0) { double t2 = kab * 1000.0; bsum = bsum - t2; }
+                                else if (ii == nx - 1) { double t2 = kab * 100.0; bsum = bsum - t2; }
+                                else v[slot] += kab;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        int32_t *c = col + row_ptr[r];
+        double *vv = val + row_ptr[r];
+        int len = 0;
+        for (int s = 0; s < 15; ++s) {
+            if (!valid[s]) continue;
+            int code = s > 7 ? s - 7 : 7 - s, sg = s > 7 ? 1 : -1;
+            int64_t off = sg * ((code & 1) + w * ((code >> 1) & 1) + w * ny * (int64_t)((code >> 2) & 1));
+            c[len] = (int32_t)(r + off);
+            vv[len] = v[s];
+            ++len;
+        }
+        b[r] = bsum;
+    }
+    out->num_nodes = N; out->n = n; out->nnz = nnz; out->row_ptr = row_ptr; out->col = col;
+    out->val = val; out->b = b; out->red2orig = red2orig; out->max_row = max_row;
+    return 0;
+}
+
 void oracle_spmv(int64_t n, const int64_t *row_ptr, const int32_t *col, const double *val,
                  const double *x, double *y) {
 #pragma omp parallel for schedule(static)
@@ -280,6 +414,18 @@ static void cheb_apply(int64_t n, const int64_t *rp, const int32_t *col, const d
 int oracle_ilu0(int64_t n, const int64_t *rp, const int32_t *col, const double *val, double *lu);
 void oracle_ilu0_apply(int64_t n, const int64_t *rp, const int32_t *col, const double *lu, const double *v, double *z);
 
+static double g_pcg_loop_seconds = 0.0;
+/* wall seconds the iteration loop of the last oracle_pcg call took (set-up excluded): what bench.py's CPU arm
+ * divides the iteration count by, so a short bounded sample is not dominated by allocation and r0 = b - A x0 */
+double oracle_pcg_loop_seconds(void) { return g_pcg_loop_seconds; }
+static double wall_now(void) {
+#ifdef _OPENMP
+    return omp_get_wtime();
+#else
+    return 0.0;
+#endif
+}
+
 int oracle_pcg(int64_t n, const int64_t *rp, const int32_t *col, const double *val,
                const double *b, double *x, int prec, int cheb_degree, double lmax, double ratio,
                int max_iters, double tol, double *achieved_tol, double *res_hist) {
@@ -315,6 +461,7 @@ int oracle_pcg(int64_t n, const int64_t *rp, const int32_t *col, const double *v
     double rz = dot(n, r, z), rr = dot(n, r, r), rr0 = rr;
     int it = 0, status = 0;
     if (res_hist) res_hist[0] = 1.0;
+    const double t_loop = wall_now();
     while (1) {
         double rel = (rr0 > 0.0) ? sqrt(rr / rr0) : 0.0;
         if (rel <= tol || it >= max_iters) break;
@@ -339,6 +486,7 @@ int oracle_pcg(int64_t n, const int64_t *rp, const int32_t *col, const double *v
         ++it;
         if (res_hist) res_hist[it] = sqrt(rr / rr0);
     }
+    g_pcg_loop_seconds = wall_now() - t_loop;
     if (achieved_tol) *achieved_tol = (rr0 > 0.0) ? sqrt(rr / rr0) : 0.0;
     free(r); free(z); free(p); free(Ap); free(dinv); free(w); free(t); free(lu);
     return status < 0 ? -1 : it;

@@ -100,7 +100,14 @@ int  oracle_gmres(int64_t n, const int64_t *row_ptr, const int32_t *col, const d
                   double *x, int prec, int cheb_degree, double cheb_lambda_max, double cheb_ratio, int restart,
                   int max_iters, double tol, double *achieved_tol, int *converged);
 
+/* The system oracle_assemble builds on oracle_cube_mesh(nx,ny,nz), bit for bit, without the explicit mesh
+ * (closed-form Kuhn connectivity; 15-slot rows).  For the CPU baseline at sizes whose explicit mesh does
+ * not fit the host.  n < 2^31 rows.                                                             */
+int oracle_cube_assemble(int nx, int ny, int nz, int mode, oracle_system *out);
+
+double oracle_pcg_loop_seconds(void);   /* wall seconds of the last oracle_pcg iteration loop (set-up excluded) */
 int oracle_num_threads(void);
+void oracle_set_num_threads(int n);
 
 #ifdef __cplusplus
 }

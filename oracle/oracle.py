@@ -64,6 +64,10 @@ def lib():
         _lib.oracle_pcg.restype = C.c_int
         _lib.oracle_scatter_field.argtypes = [C.c_int64, dp, C.c_int64, lp, dp, dp]
         _lib.oracle_num_threads.restype = C.c_int
+        _lib.oracle_set_num_threads.argtypes = [C.c_int]
+        _lib.oracle_pcg_loop_seconds.restype = C.c_double
+        _lib.oracle_cube_assemble.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_System)]
+        _lib.oracle_cube_assemble.restype = C.c_int
         _lib.oracle_ilu0.argtypes = [C.c_int64, lp, ip, dp, dp]
         _lib.oracle_ilu0.restype = C.c_int
         _lib.oracle_ilu0_apply.argtypes = [C.c_int64, lp, ip, dp, dp, dp]
@@ -187,6 +191,14 @@ class System:
         import scipy.sparse as sp
         return sp.csr_matrix((self.val, self.col, self.row_ptr), shape=(self.n, self.n))
 
+    def free(self):
+        """release the C arrays of a cube_assemble(copy=False) system (the numpy views die with them)"""
+        c = getattr(self, "_c", None)
+        if c is not None:
+            self.row_ptr = self.col = self.val = self.b = self.red2orig = None
+            lib().oracle_system_free(C.byref(c))
+            self._c = None
+
 
 def assemble(mesh: Mesh, mode: int = GRAPH_LAPLACIAN, node_bc: np.ndarray | None = None) -> System:
     """C oracle of IO::assemble (FIXED semantics)."""
@@ -212,6 +224,32 @@ def assemble(mesh: Mesh, mode: int = GRAPH_LAPLACIAN, node_bc: np.ndarray | None
         node_bc=bc,
     )
     lib().oracle_system_free(C.byref(s))
+    return out
+
+
+def cube_assemble(nx: int, ny: int, nz: int, mode: int = P1_FEM, copy: bool = True) -> System:
+    """The system assemble(cube_mesh(nx, ny, nz), mode) builds, bit for bit, from the closed form of the Kuhn
+    cube's connectivity (oracle_cube_assemble) — no explicit mesh, so the 512^3 headline size fits the host.
+    copy=False wraps the C arrays without duplicating them (24.5 GB at 512^3); call .free() when done."""
+    s = _System()
+    rc = lib().oracle_cube_assemble(nx, ny, nz, mode, C.byref(s))
+    if rc:
+        raise RuntimeError(f"oracle_cube_assemble failed rc={rc}")
+    n, nnz = s.n, s.nnz
+    wrap = (lambda a: a.copy()) if copy else (lambda a: a)
+    out = System(
+        n=n,
+        row_ptr=wrap(np.ctypeslib.as_array(s.row_ptr, (n + 1,))),
+        col=wrap(np.ctypeslib.as_array(s.col, (nnz,))),
+        val=wrap(np.ctypeslib.as_array(s.val, (nnz,))),
+        b=wrap(np.ctypeslib.as_array(s.b, (n,))),
+        red2orig=wrap(np.ctypeslib.as_array(s.red2orig, (n,))),
+        node_bc=np.zeros(0),
+    )
+    if copy:
+        lib().oracle_system_free(C.byref(s))
+    else:
+        out._c = s                    # keeps the C arrays alive until free()
     return out
 
 
@@ -443,6 +481,16 @@ def get_matrix_owners(conn: np.ndarray, epart: np.ndarray, nparts: int, num_node
 
 def num_threads() -> int:
     return int(lib().oracle_num_threads())
+
+
+def pcg_loop_seconds() -> float:
+    """wall seconds the iteration loop of the last pcg() call took, set-up excluded"""
+    return float(lib().oracle_pcg_loop_seconds())
+
+
+def set_num_threads(n: int) -> None:
+    """OpenMP threads of the C oracle (bench.py: all cores of the affinity mask, whatever the launcher exported)"""
+    lib().oracle_set_num_threads(int(n))
 
 
 # ------------------------------------------------------------------------------------------

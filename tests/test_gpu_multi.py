@@ -15,7 +15,7 @@ def _gpu_count():
     return torch.cuda.device_count()
 
 
-@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("world", [2, 4, 8])
 def test_multi_gpu_parity(world):
     n = _gpu_count()
     if n < world:
@@ -23,6 +23,6 @@ def test_multi_gpu_parity(world):
                     "tests/test_dist_cpu.py with gloo)")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(29500 + 11 * world), os.path.join(ROOT, "tests", "mgpu_worker.py")]
-    p = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=1500)
     assert p.returncode == 0, p.stdout[-4000:] + "\n" + p.stderr[-4000:]
     assert '"mgpu_ok": true' in p.stdout

@@ -183,6 +183,49 @@ def test_cube_analytic_and_explicit_match_oracle(hb, oracle, dims, mode):
         io.close()
 
 
+@pytest.mark.parametrize("dims", [(9, 9, 9), (40, 33, 29), (66, 3, 2), (130, 5, 4), (12, 9, 11)])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_cube_direct_sell_assembly(hb, oracle, dims, mode):
+    """Analytic cubes are assembled STRAIGHT into the SpMV format (cube_sell_kernel: SELL values + byte indices +
+    tables + diagonal + row lengths, no CSR).  The CSR a parity export asks for is rebuilt from those arrays
+    (sell_to_csr) and must be the oracle's, bit for bit; so must the SpMV that streams them; and the CSR-first path
+    (HEAT_CUBE_ASSEMBLY=csr) and the int32 column stream (HEAT_SPMV_CIDX=0) must give the same bits."""
+    ref = oracle.assemble(oracle.cube_mesh(*dims), mode)
+    xg = oracle.hash_vector(np.arange(ref.n), 31)
+    y_ref = oracle.spmv(ref, xg)
+    seen = {}
+    for tag, env in (("direct", {}), ("direct-int32", {"HEAT_SPMV_CIDX": "0"}), ("csr-first", {"HEAT_CUBE_ASSEMBLY": "csr"})):
+        old = {k: os.environ.get(k) for k in env}
+        os.environ.update(env)
+        try:
+            io = hb.IO(0)
+            io.mesh_cube(*dims)
+            A, X, B = io.assemble(mode)
+        finally:
+            for k, v in old.items():
+                os.environ.pop(k, None) if v is None else os.environ.__setitem__(k, v)
+        mi = A.info
+        assert bool(mi.csr_resident) == (tag == "csr-first"), tag               # direct: no CSR until asked
+        assert mi.col_index_bytes == (4 if tag == "direct-int32" else 1), tag
+        x, y = A.hash_vector(31), A.new_vector()
+        np.testing.assert_array_equal(x.numpy(), xg)
+        io.spmv(A, x, y)                                                       # before any export: streams what the kernel wrote
+        np.testing.assert_array_equal(y.numpy(), y_ref, err_msg=tag)
+        np.testing.assert_array_equal(B.numpy(), ref.b, err_msg=tag)
+        bytes_before = mi.matrix_bytes
+        rp, col, val = A.csr()
+        np.testing.assert_array_equal(rp, ref.row_ptr, err_msg=tag)
+        np.testing.assert_array_equal(col, ref.col, err_msg=tag)
+        assert val.tobytes() == ref.val.tobytes(), tag                         # zero signs included
+        assert A.info.csr_resident == 1 and A.info.nnz_local == ref.nnz
+        if tag == "direct":
+            assert A.info.matrix_bytes > bytes_before                          # the export built the CSR
+        res = io.solve(A, X, B, max_iters=2000, tol=RES_TOL)
+        seen[tag] = (res.iters, X.numpy().tobytes())
+        io.close()
+    assert seen["direct"] == seen["direct-int32"] == seen["csr-first"]
+
+
 @pytest.mark.parametrize("mode,solver", [(0, 0), (1, 0), (1, 1)])
 def test_cube_solve_matches_oracle(hb, oracle, mode, solver):
     n = 17

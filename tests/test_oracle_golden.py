@@ -252,3 +252,19 @@ def test_get_matrix_matches_golden(oracle, golden, name):
     assert (s.n, s.nnz) == (g["n"], g["nnz"]) and s.csr().diagonal().sum() == g["trace"]
     lam, res, it, conv = oracle.power_method(s, oracle.hash_vector(np.arange(s.n), 12345), 2000, 1e-6)
     assert -1e-12 * lam <= g["lambda_max"] - lam <= 1e-5 * g["lambda_max"], (lam, g["lambda_max"], it)
+
+
+@pytest.mark.parametrize("dims", [(3, 2, 2), (5, 4, 3), (9, 7, 5), (12, 9, 11), (17, 17, 17), (33, 17, 16)])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_cube_analytic_equals_explicit(oracle, dims, mode):
+    """oracle_cube_assemble (closed-form Kuhn connectivity: the CPU baseline's assembler at sizes whose explicit
+    mesh does not fit the host) is the SAME system as oracle_assemble on the explicit cube mesh, to the last bit
+    (zero signs included) — so it inherits every pin of oracle_assemble."""
+    a = oracle.assemble(oracle.cube_mesh(*dims), mode)
+    b = oracle.cube_assemble(*dims, mode)
+    assert (a.n, a.nnz) == (b.n, b.nnz)
+    for f in ("row_ptr", "col", "val", "b", "red2orig"):
+        assert getattr(a, f).tobytes() == getattr(b, f).tobytes(), f
+    c = oracle.cube_assemble(*dims, mode, copy=False)        # the zero-copy wrapper bench.py uses
+    assert np.array_equal(c.val, a.val)
+    c.free()
