@@ -238,9 +238,11 @@ __device__ __forceinline__ void peer_push_phase(const PeerPush &push, F value_of
 
 // classical update_p: beta needs the GLOBAL r.z (reduction `seq_in`); block 0 records the global
 // {r.z, r.r} in H[it+1]; p_out = D^-1 r + beta p_in (ping-pong buffers) and the halo push of p_out.
+// z == nullptr: Jacobi fused (z = D^-1 r); else z holds M^-1 r of a general preconditioner (Chebyshev)
 __global__ void __launch_bounds__(kBlock) cg_update_p_peer_kernel(int64_t n, double *p_out, const double *p_in,
                                                                   const double *__restrict__ r,
-                                                                  const double *__restrict__ dinv, CgGate g,
+                                                                  const double *__restrict__ dinv,
+                                                                  const double *__restrict__ z, CgGate g,
                                                                   CgRec *H, int *I, PeerRed pr,
                                                                   unsigned long long seq_in, PeerPush push) {
     if (cg_done(g)) return;
@@ -261,8 +263,19 @@ __global__ void __launch_bounds__(kBlock) cg_update_p_peer_kernel(int64_t n, dou
     }
     if (!(rr_new > g.S[S_TOL2] * g.H[0].rr)) return;        // converged: p is never used again
     const double beta = rz_new / g.H[g.it].rz;
-    peer_push_phase(push, [&](int32_t i) { return fma(beta, p_in[i], dinv[i] * r[i]); });
     const int64_t n2 = n >> 1, stride = (int64_t)gridDim.x * kBlock;
+    if (z) {
+        peer_push_phase(push, [&](int32_t i) { return fma(beta, p_in[i], z[i]); });
+        for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n2; i += stride) {
+            double2 zv = ld_stream_f64x2(z + 2 * i);
+            double2 pv = *reinterpret_cast<const double2 *>(p_in + 2 * i);
+            pv.x = fma(beta, pv.x, zv.x); pv.y = fma(beta, pv.y, zv.y);
+            *reinterpret_cast<double2 *>(p_out + 2 * i) = pv;
+        }
+        if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) p_out[n - 1] = fma(beta, p_in[n - 1], z[n - 1]);
+        return;
+    }
+    peer_push_phase(push, [&](int32_t i) { return fma(beta, p_in[i], dinv[i] * r[i]); });
     for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n2; i += stride) {
         double2 rv = ld_stream_f64x2(r + 2 * i), dv = ld_stream_f64x2(dinv + 2 * i);
         double2 pv = *reinterpret_cast<const double2 *>(p_in + 2 * i);
@@ -276,6 +289,126 @@ __global__ void __launch_bounds__(kBlock) cg_update_p_peer_kernel(int64_t n, dou
     if (threadIdx.x == 0) HEAT_TRACE_MAX(g.it, 2, 2);
 }
 
+// -------------------------------------------------------------------------------------------------
+// Chebyshev-preconditioned CG on the peer-memory path (also the fused single-GPU path, P == 1): the Ifpack2
+// recurrences folded into the CG vector kernels.  Every kernel that PRODUCES an SpMV input
+// (z of the polynomial, p of CG) also stores its boundary entries into the neighbours' ghost segments, and the last
+// polynomial step carries the r.z / r.r reduction, so an iteration of degree k is k SpMV launches + k + 1 vector
+// launches and no NCCL call (the NCCL path: 3k + 5 launches, 2 all-reduces, k send/recv groups).
+//   xr_first : alpha = gamma / p.Ap (global, reduction seq_in) ; x += alpha p ; r -= alpha Ap ;
+//              W = D^-1 r / theta ; Z = W                            [k == 1: + r.Z, r.r -> reduction seq_out]
+//   step     : W = c1 W + c2 D^-1 (r - A Z) ; Z' = Z + W             [last step: + r.Z', r.r -> reduction seq_out]
+// Z is ping-ponged between two buffers for the same reason p is: a neighbour may already deliver the boundary of
+// the next polynomial iterate while this GPU still gathers the previous one.
+// -------------------------------------------------------------------------------------------------
+template <bool LAST>
+__global__ void __launch_bounds__(kBlock)
+cheb_xr_first_peer_kernel(int64_t n, double *__restrict__ x, double *__restrict__ r, const double *__restrict__ p,
+                          const double *__restrict__ ap, const double *__restrict__ dinv, double inv_theta,
+                          double *__restrict__ w, double *z_out, CgGate g, CgRec *H, double *S, int *I, double *partials,
+                          int *counter, PeerRed pr, unsigned long long seq_in, unsigned long long seq_out, PeerPush push) {
+    if (cg_done(g)) return;
+    __shared__ double sh[2];
+    if (threadIdx.x < 32) {
+        double o[3];
+        const bool ok = peer_red_wait_warp(pr, seq_in, o, I);
+        if (threadIdx.x == 0) { sh[0] = o[0]; sh[1] = ok ? 1.0 : 0.0; }
+    }
+    __syncthreads();
+    if (sh[1] == 0.0) return;                              // communication timeout: I_STATUS = 3
+    const double pap = sh[0];
+    if (!(pap > 0.0)) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) I[I_STATUS] = 2;
+        return;
+    }
+    const double alpha = H[g.it].rz / pap;
+    if (!LAST) peer_push_phase(push, [&](int32_t i) { return dinv[i] * fma(-alpha, ap[i], r[i]) * inv_theta; });
+    double acc[2] = {0.0, 0.0};
+    const int64_t n2 = n >> 1, stride = (int64_t)gridDim.x * kBlock;
+    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n2; i += stride) {
+        double2 pv = ld_stream_f64x2(p + 2 * i), av = ld_stream_f64x2(ap + 2 * i), dv = ld_stream_f64x2(dinv + 2 * i);
+        double2 xv = *reinterpret_cast<const double2 *>(x + 2 * i);
+        double2 rv = *reinterpret_cast<const double2 *>(r + 2 * i);
+        xv.x = fma(alpha, pv.x, xv.x); xv.y = fma(alpha, pv.y, xv.y);
+        rv.x = fma(-alpha, av.x, rv.x); rv.y = fma(-alpha, av.y, rv.y);
+        const double2 wv = make_double2(dv.x * rv.x * inv_theta, dv.y * rv.y * inv_theta);
+        *reinterpret_cast<double2 *>(x + 2 * i) = xv;
+        *reinterpret_cast<double2 *>(r + 2 * i) = rv;
+        *reinterpret_cast<double2 *>(z_out + 2 * i) = wv;
+        if (!LAST) *reinterpret_cast<double2 *>(w + 2 * i) = wv;
+        if (LAST) { acc[0] += rv.x * wv.x + rv.y * wv.y; acc[1] += rv.x * rv.x + rv.y * rv.y; }
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        const int64_t i = n - 1;
+        const double xv = fma(alpha, p[i], x[i]), rv = fma(-alpha, ap[i], r[i]), wv = dinv[i] * rv * inv_theta;
+        x[i] = xv; r[i] = rv; z_out[i] = wv;
+        if (!LAST) w[i] = wv;
+        if (LAST) { acc[0] += rv * wv; acc[1] += rv * rv; }
+    }
+    if (LAST) {
+        double *const out[2] = {S + S_TMP0, S + S_TMP1};
+        if (grid_sum_block<2>(acc, partials, 0, gridDim.x, counter, out)) {
+            if (threadIdx.x == 0) H[g.it].alpha = alpha;
+            if (threadIdx.x < 32) peer_red_push_warp(pr, seq_out, S[S_TMP0], S[S_TMP1], 0.0);
+        }
+    } else if (blockIdx.x == 0 && threadIdx.x == 0) {
+        H[g.it].alpha = alpha;
+    }
+}
+
+template <bool LAST>
+__global__ void __launch_bounds__(kBlock)
+cheb_step_peer_kernel(int64_t n, const double *__restrict__ dinv, const double *__restrict__ r, const double *__restrict__ az,
+                      double c1, double c2, double *__restrict__ w, const double *z_in, double *z_out, CgGate g, double *S,
+                      double *partials, int *counter, PeerRed pr, unsigned long long seq_out, PeerPush push) {
+    if (cg_done(g)) return;
+    if (!LAST) peer_push_phase(push, [&](int32_t i) { return z_in[i] + (c1 * w[i] + c2 * (dinv[i] * (r[i] - az[i]))); });
+    double acc[2] = {0.0, 0.0};
+    const int64_t n2 = n >> 1, stride = (int64_t)gridDim.x * kBlock;
+    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n2; i += stride) {
+        const double2 dv = ld_stream_f64x2(dinv + 2 * i), rv = ld_stream_f64x2(r + 2 * i), tv = ld_stream_f64x2(az + 2 * i);
+        double2 wv = *reinterpret_cast<const double2 *>(w + 2 * i);
+        double2 zv = *reinterpret_cast<const double2 *>(z_in + 2 * i);
+        wv.x = c1 * wv.x + c2 * (dv.x * (rv.x - tv.x)); wv.y = c1 * wv.y + c2 * (dv.y * (rv.y - tv.y));
+        zv.x += wv.x; zv.y += wv.y;
+        if (!LAST) *reinterpret_cast<double2 *>(w + 2 * i) = wv;
+        *reinterpret_cast<double2 *>(z_out + 2 * i) = zv;
+        if (LAST) { acc[0] += rv.x * zv.x + rv.y * zv.y; acc[1] += rv.x * rv.x + rv.y * rv.y; }
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        const int64_t i = n - 1;
+        const double wv = c1 * w[i] + c2 * (dinv[i] * (r[i] - az[i])), zv = z_in[i] + wv;
+        if (!LAST) w[i] = wv;
+        z_out[i] = zv;
+        if (LAST) { acc[0] += r[i] * zv; acc[1] += r[i] * r[i]; }
+    }
+    if (LAST) {
+        double *const out[2] = {S + S_TMP0, S + S_TMP1};
+        if (grid_sum_block<2>(acc, partials, 0, gridDim.x, counter, out) && threadIdx.x < 32)
+            peer_red_push_warp(pr, seq_out, S[S_TMP0], S[S_TMP1], 0.0);
+    }
+}
+
+int launch_cheb_xr_first_peer(bool last, int64_t n, double *x, double *r, const double *p, const double *ap, const double *dinv,
+                              double inv_theta, double *w, double *z_out, CgGate gate, CgRec *H, double *S, int *I, double *partials,
+                              int *counter, PeerRed pr, unsigned long long seq_in, unsigned long long seq_out, PeerPush push,
+                              int grid, cudaStream_t st) {
+    if (push.n_blocks > grid) push.n_blocks = grid;
+    if (last) cheb_xr_first_peer_kernel<true><<<grid, kBlock, 0, st>>>(n, x, r, p, ap, dinv, inv_theta, w, z_out, gate, H, S, I, partials, counter, pr, seq_in, seq_out, push);
+    else cheb_xr_first_peer_kernel<false><<<grid, kBlock, 0, st>>>(n, x, r, p, ap, dinv, inv_theta, w, z_out, gate, H, S, I, partials, counter, pr, seq_in, seq_out, push);
+    HEAT_LAUNCHED();
+    return 0;
+}
+int launch_cheb_step_peer(bool last, int64_t n, const double *dinv, const double *r, const double *az, double c1, double c2, double *w,
+                          const double *z_in, double *z_out, CgGate gate, double *S, double *partials, int *counter, PeerRed pr,
+                          unsigned long long seq_out, PeerPush push, int grid, cudaStream_t st) {
+    if (push.n_blocks > grid) push.n_blocks = grid;
+    if (last) cheb_step_peer_kernel<true><<<grid, kBlock, 0, st>>>(n, dinv, r, az, c1, c2, w, z_in, z_out, gate, S, partials, counter, pr, seq_out, push);
+    else cheb_step_peer_kernel<false><<<grid, kBlock, 0, st>>>(n, dinv, r, az, c1, c2, w, z_in, z_out, gate, S, partials, counter, pr, seq_out, push);
+    HEAT_LAUNCHED();
+    return 0;
+}
+
 #ifdef HEAT_PEER_TRACE
 int trace_set_cg(TraceBuf *buf) {
     HEAT_CUDA(cudaMemcpyToSymbol(g_trace, &buf, sizeof(buf)));
@@ -283,11 +416,11 @@ int trace_set_cg(TraceBuf *buf) {
 }
 #endif
 
-int launch_cg_update_p_peer(int64_t n, double *p_out, const double *p_in, const double *r, const double *dinv,
+int launch_cg_update_p_peer(int64_t n, double *p_out, const double *p_in, const double *r, const double *dinv, const double *z,
                             CgGate gate, CgRec *H, int *I, PeerRed pr, unsigned long long seq_in, PeerPush push,
                             int grid, cudaStream_t st) {
     if (push.n_blocks > grid) push.n_blocks = grid;
-    cg_update_p_peer_kernel<<<grid, kBlock, 0, st>>>(n, p_out, p_in, r, dinv, gate, H, I, pr, seq_in, push);
+    cg_update_p_peer_kernel<<<grid, kBlock, 0, st>>>(n, p_out, p_in, r, dinv, z, gate, H, I, pr, seq_in, push);
     HEAT_LAUNCHED();
     return 0;
 }
@@ -297,6 +430,7 @@ __global__ void __launch_bounds__(kBlock) halo_push_kernel(const double *__restr
     peer_push_phase(push, [&](int32_t i) { return x[i]; });
 }
 int launch_halo_push(const double *x, PeerPush push, cudaStream_t st) {
+    if (push.n_nbr == 0) return 0;                 // single rank / no neighbour: nothing to deliver
     if (push.n_blocks < 1) push.n_blocks = 1;
     halo_push_kernel<<<push.n_blocks, kBlock, 0, st>>>(x, push);
     HEAT_LAUNCHED();

@@ -172,6 +172,10 @@ void peer_arena_teardown(heat_ctx *ctx) {
 
 PeerRed peer_red_of(const heat_ctx *ctx) {
     PeerRed pr;
+    if (ctx->nranks == 1 && ctx->peer_arena) {      // single GPU: the "all-reduce" is this GPU's own inbox
+        pr.P = 1; pr.rank = 0; pr.inbox[0] = ctx->peer_arena;
+        return pr;
+    }
     if (!ctx->peer_enabled) return pr;
     pr.P = ctx->nranks; pr.rank = ctx->rank;
     for (int q = 0; q < ctx->nranks; ++q) pr.inbox[q] = ctx->peer_arena_of[q];
@@ -179,7 +183,7 @@ PeerRed peer_red_of(const heat_ctx *ctx) {
 }
 
 struct PeerRecord {                   // what every rank tells the others about one matrix
-    cudaIpcMemHandle_t h_p[2];
+    cudaIpcMemHandle_t h_p[4];        // p ping-pong buffers, then the z ping-pong buffers (Chebyshev)
     long long n_owned;
     int n_nbr;
     int nbr_rank[kPeerMaxNbr];
@@ -188,18 +192,39 @@ struct PeerRecord {                   // what every rank tells the others about 
 
 // Collective.  Allocates the ping-pong SpMV-input buffers (w_p, w_p2), exchanges their IPC handles and
 // builds the two push plans.  On any failure on any rank the matrix silently stays on the NCCL path.
-int peer_matrix_setup(heat_ctx *ctx, heat_matrix *A) {
-    if (A->peer || !ctx->peer_enabled) return 0;
+int peer_matrix_setup(heat_ctx *ctx, heat_matrix *A, bool need_z) {
+    if (A->peer && (!need_z || A->peer->has_z)) return 0;
+    if (A->peer) peer_matrix_teardown(A);                            // same decision on every rank: redo with the z buffers
     const HaloPlan &h = A->halo;
     const size_t nv = (size_t)(A->n_owned + A->n_ghost);
+    const int nbuf = need_z ? 4 : 2;
+    DevBuf<double> *bufs[4] = {&A->w_p, &A->w_p2, &A->w_u, &A->w_u2};
+    if (ctx->nranks == 1) {
+        // degenerate state: no neighbour, the reductions go through this GPU's own inbox
+        if (!ctx->peer_arena) {
+            HEAT_CUDA(cudaMalloc((void **)&ctx->peer_arena, sizeof(unsigned long long) * kPeerArenaWords));
+            HEAT_CUDA(cudaMemset(ctx->peer_arena, 0, sizeof(unsigned long long) * kPeerArenaWords));
+            ctx->peer_arena_of[0] = ctx->peer_arena;
+        }
+        for (int b = 0; b < nbuf; ++b)
+            if (!bufs[b]->p) HEAT_TRY(bufs[b]->alloc(nv));
+        PeerMatrixState *st = new PeerMatrixState();
+        for (int b = 0; b < 4; ++b) { st->push[b].n_nbr = 0; st->push[b].n_blocks = 0; st->push[b].ticket = A->iscal.p + I_COUNTER + 2; }
+        st->halo.n_nbr = 0;
+        st->halo.flags = ctx->peer_arena + kPeerInboxWords;
+        st->has_z = need_z;
+        A->peer = st;
+        return 0;
+    }
+    if (!ctx->peer_enabled) return 0;
     int ok = (h.n_neighbors <= kPeerMaxNbr) && spmv_peer_supported() && (A->n_ghost == 0 || A->slices_all.p != nullptr);
     PeerRecord mine;
     memset(&mine, 0, sizeof(mine));
-    if (!A->w_p.p && A->w_p.alloc(nv)) ok = 0;
-    if (!A->w_p2.p && A->w_p2.alloc(nv)) ok = 0;
+    for (int b = 0; b < nbuf; ++b)
+        if (!bufs[b]->p && bufs[b]->alloc(nv)) ok = 0;
     if (ok) {
-        if (cudaIpcGetMemHandle(&mine.h_p[0], A->w_p.p) != cudaSuccess) ok = 0;
-        if (cudaIpcGetMemHandle(&mine.h_p[1], A->w_p2.p) != cudaSuccess) ok = 0;
+        for (int b = 0; b < nbuf; ++b)
+            if (cudaIpcGetMemHandle(&mine.h_p[b], bufs[b]->p) != cudaSuccess) ok = 0;
         cudaGetLastError();
         mine.n_owned = A->n_owned; mine.n_nbr = h.n_neighbors;
         for (int s = 0; s < h.n_neighbors && s < kPeerMaxNbr; ++s) { mine.nbr_rank[s] = h.nbr_rank[s]; mine.recv_ptr[s] = h.recv_ptr[s]; }
@@ -209,9 +234,9 @@ int peer_matrix_setup(heat_ctx *ctx, heat_matrix *A) {
     HEAT_TRY(allgather_bytes(ctx, &mine, sizeof(mine), all));
     PeerMatrixState *st = new PeerMatrixState();
     if (ok) {
-        for (int b = 0; b < 2; ++b) {
+        for (int b = 0; b < 4; ++b) {
             PeerPush &pp = st->push[b];
-            pp.n_nbr = h.n_neighbors;
+            pp.n_nbr = b < nbuf ? h.n_neighbors : 0;
             pp.send_idx = h.d_send_idx.p;
             pp.ticket = A->iscal.p + I_COUNTER + 2;                   // I[4]: push ticket
             for (int s = 0; s <= h.n_neighbors; ++s) pp.send_ptr[s] = h.n_neighbors ? h.send_ptr[s] : 0;
@@ -223,7 +248,7 @@ int peer_matrix_setup(heat_ctx *ctx, heat_matrix *A) {
             int sp = -1;
             for (int t = 0; t < rec.n_nbr && t < kPeerMaxNbr; ++t) if (rec.nbr_rank[t] == ctx->rank) sp = t;
             if (sp < 0 || rec.recv_ptr[sp + 1] - rec.recv_ptr[sp] != h.send_ptr[s + 1] - h.send_ptr[s]) { ok = 0; break; }
-            for (int b = 0; b < 2; ++b) {
+            for (int b = 0; b < nbuf; ++b) {
                 void *mapped = nullptr;
                 if (cudaIpcOpenMemHandle(&mapped, rec.h_p[b], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); break; }
                 st->mapped.push_back(mapped);
@@ -242,9 +267,10 @@ int peer_matrix_setup(heat_ctx *ctx, heat_matrix *A) {
     const long long total = h.n_neighbors ? h.send_ptr[h.n_neighbors] : 0;
     int nb = (int)((total + 4 * 256 - 1) / (4 * 256));
     nb = nb < 1 ? 1 : nb > 64 ? 64 : nb;
-    st->push[0].n_blocks = st->push[1].n_blocks = nb;
+    for (int b = 0; b < 4; ++b) st->push[b].n_blocks = nb;
     st->halo.n_nbr = h.n_neighbors;
     st->halo.flags = ctx->peer_arena + kPeerInboxWords;
+    st->has_z = need_z;
     A->peer = st;
     return 0;
 }

@@ -12,12 +12,15 @@ int comm_gather_reduced(heat_ctx *ctx, const std::vector<double> &x_owned, int64
                         std::vector<double> &x_global_on_root);
 // peer-memory path (peer.cuh)
 PeerRed peer_red_of(const heat_ctx *ctx);
-int peer_matrix_setup(heat_ctx *ctx, heat_matrix *A);          // collective; leaves A->peer null on failure
+// collective; leaves A->peer null on failure.  need_z: also map the two polynomial-iterate buffers of the
+// Chebyshev path.  With ONE rank it builds the degenerate (no neighbour) state the fused kernels run on.
+int peer_matrix_setup(heat_ctx *ctx, heat_matrix *A, bool need_z = false);
 void peer_matrix_teardown(heat_matrix *A);
 }  // namespace heat
 
 struct PeerMatrixState {
-    heat::PeerPush push[2];            // push plan into the neighbours' buffer 0 / buffer 1
+    heat::PeerPush push[4];            // push plans into the neighbours' p buffers (0, 1) and z buffers (2, 3)
+    bool has_z = false;
     heat::PeerHalo halo;               // my flags
     std::vector<void *> mapped;        // cudaIpcOpenMemHandle mappings to close
 };

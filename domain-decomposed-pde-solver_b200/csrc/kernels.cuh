@@ -66,9 +66,17 @@ int launch_cg_update_p(int64_t n, double *p, const double *r, const double *dinv
 int launch_cg_update_xr_peer(int64_t n, double *x, double *r, const double *p, const double *ap, const double *dinv,
                              CgGate gate, CgRec *H, double *S, int *I, double *partials, int *counter, PeerRed pr,
                              unsigned long long seq_in, unsigned long long seq_out, int grid, cudaStream_t st);
-int launch_cg_update_p_peer(int64_t n, double *p_out, const double *p_in, const double *r, const double *dinv,
+int launch_cg_update_p_peer(int64_t n, double *p_out, const double *p_in, const double *r, const double *dinv, const double *z,
                             CgGate gate, CgRec *H, int *I, PeerRed pr, unsigned long long seq_in, PeerPush push,
                             int grid, cudaStream_t st);
+// Chebyshev-PCG on the peer-memory path (cg.cu): `last` = this launch carries the r.z / r.r reduction
+int launch_cheb_xr_first_peer(bool last, int64_t n, double *x, double *r, const double *p, const double *ap, const double *dinv,
+                              double inv_theta, double *w, double *z_out, CgGate gate, CgRec *H, double *S, int *I, double *partials,
+                              int *counter, PeerRed pr, unsigned long long seq_in, unsigned long long seq_out, PeerPush push,
+                              int grid, cudaStream_t st);
+int launch_cheb_step_peer(bool last, int64_t n, const double *dinv, const double *r, const double *az, double c1, double c2, double *w,
+                          const double *z_in, double *z_out, CgGate gate, double *S, double *partials, int *counter, PeerRed pr,
+                          unsigned long long seq_out, PeerPush push, int grid, cudaStream_t st);
 int launch_halo_push(const double *x, PeerPush push, cudaStream_t st);
 int launch_cg_fused_update(int64_t n, double *x, double *r, double *p, double *s, double *u,
                            const double *w, const double *dinv, CgGate gate, CgRec *H, int *I,

@@ -244,6 +244,17 @@ int solve_device(heat_ctx *ctx, heat_matrix *A, double *x, const double *b, cons
     // peer-memory path (peer.cuh): classical CG with the fused Jacobi/identity preconditioner
     if (!single && !cheb && ctx->nranks > 1 && ctx->peer_enabled && !A->peer) HEAT_TRY(peer_matrix_setup(ctx, A));
     const bool peer = !single && !cheb && ctx->nranks > 1 && A->peer != nullptr;
+    // Chebyshev-PCG with the polynomial folded into the CG kernels (cg.cu): over peer memory on >1 GPU, and the same
+    // kernels with a degenerate (no-neighbour) state on one GPU.  HEAT_CHEB_FUSED=0 / HEAT_COMM=nccl: the plain path.
+    bool cheb_fused = false;
+    if (is_cheb && !single && o.cheb_degree >= 1) {
+        const char *cf = getenv("HEAT_CHEB_FUSED"), *hc = getenv("HEAT_COMM");
+        const bool want = !(cf && atoi(cf) == 0) && !(hc && strcmp(hc, "nccl") == 0) && spmv_peer_supported();
+        if (want && (ctx->nranks == 1 || ctx->peer_enabled)) {
+            HEAT_TRY(peer_matrix_setup(ctx, A, true));
+            cheb_fused = A->peer != nullptr && A->peer->has_z;
+        }
+    }
     const int64_t n = A->n_owned;
     const int sms = sm_count(ctx->device);
     const int vgrid = vec_grid(n, sms);
@@ -304,6 +315,11 @@ int solve_device(heat_ctx *ctx, heat_matrix *A, double *x, const double *b, cons
         HEAT_TRY(launch_dot2(n, r, z, r, r, &H[0].rz, &H[0].rr, A->partials.p, I + I_COUNTER2, vgrid, st));
         HEAT_TRY(comm_allreduce_sum(ctx, &H[0].rz, 3));
         HEAT_TRY(launch_axpby(n, 1.0, z, 0.0, p, vgrid, st));
+        if (cheb_fused) {                             // ghosts of p0 go to the neighbours by peer stores
+            PeerPush pp = A->peer->push[0];
+            pp.epoch = ctx->peer_halo_epoch + 1;
+            HEAT_TRY(launch_halo_push(p, pp, st));
+        }
     }
 
 #ifdef HEAT_PEER_TRACE
@@ -346,7 +362,44 @@ int solve_device(heat_ctx *ctx, heat_matrix *A, double *x, const double *b, cons
                 HEAT_TRY(launch_cg_update_xr_peer(n, x, r, pin, ap, dinv, gate, H, S, I, A->partials.p, I + I_COUNTER2, pr, s1, s2, vgrid, st));
                 PeerPush pp = A->peer->push[(it + 1) & 1];
                 pp.epoch = ctx->peer_halo_epoch + 2 + (unsigned)it;
-                HEAT_TRY(launch_cg_update_p_peer(n, pout, pin, r, dinv, gate, H, I, pr, s2, pp, vgrid, st));
+                HEAT_TRY(launch_cg_update_p_peer(n, pout, pin, r, dinv, nullptr, gate, H, I, pr, s2, pp, vgrid, st));
+            } else if (cheb_fused) {
+                // degree k: k SpMV launches + k + 1 vector launches, no NCCL (cg.cu)
+                const int k = o.cheb_degree;
+                const double ratio = o.cheb_ratio > 0 ? o.cheb_ratio : 30.0;
+                const double c_alpha = lmax / ratio, c_beta = 1.1 * lmax;
+                const double delta = 2.0 / (c_beta - c_alpha), theta = 0.5 * (c_beta + c_alpha), s1c = theta * delta;
+                double *pbuf[2] = {A->w_p.p, A->w_p2.p}, *zbuf[2] = {A->w_u.p, A->w_u2.p};
+                double *pin = pbuf[it & 1], *pout = pbuf[(it + 1) & 1];
+                const unsigned long long s1 = ctx->peer_red_seq + 2ull * (unsigned)it + 1, s2 = s1 + 1;
+                const unsigned long long e0 = ctx->peer_halo_epoch + 1 + (unsigned long long)it * (unsigned)k;   // epoch of this iteration's first SpMV
+                const PeerRed pr = peer_red_of(ctx);
+                const int g = spmv_grid(A->n_slices, sms);
+                SpmvPeer sp;
+                sp.on = true; sp.n_interior = A->n_int_slices; sp.halo = A->peer->halo; sp.red = pr; sp.I = I;
+                sp.halo.epoch = e0; sp.seq_out = s1;
+                DotOut d{A->partials.p, 0, g, I + I_COUNTER, S + S_TMP2};
+                HEAT_TRY(launch_spmv_peer(A, pin, ap, gate, d, sp, g, st));
+                PeerPush pz = A->peer->push[2];
+                pz.epoch = e0 + 1;
+                HEAT_TRY(launch_cheb_xr_first_peer(k == 1, n, x, r, pin, ap, A->dinv.p, 1.0 / theta, A->w_w.p, zbuf[0], gate, H, S, I,
+                                                   A->partials.p, I + I_COUNTER2, pr, s1, s2, pz, vgrid, st));
+                double rho = 1.0 / s1c;
+                for (int j = 1; j < k; ++j) {
+                    const double rho_new = 1.0 / (2.0 * s1c - rho);
+                    double *zin = zbuf[(j - 1) & 1], *zout = zbuf[j & 1];
+                    sp.halo.epoch = e0 + (unsigned)j;
+                    DotOut nod{A->partials.p, 0, g, I + I_COUNTER, nullptr};
+                    HEAT_TRY(launch_spmv_peer(A, zin, A->w_t.p, gate, nod, sp, g, st));
+                    PeerPush pj = A->peer->push[2 + (j & 1)];
+                    pj.epoch = e0 + (unsigned)j + 1;
+                    HEAT_TRY(launch_cheb_step_peer(j == k - 1, n, A->dinv.p, r, A->w_t.p, rho_new * rho, 2.0 * rho_new * delta, A->w_w.p,
+                                                   zin, zout, gate, S, A->partials.p, I + I_COUNTER2, pr, s2, pj, vgrid, st));
+                    rho = rho_new;
+                }
+                PeerPush pp = A->peer->push[(it + 1) & 1];
+                pp.epoch = e0 + (unsigned)k;
+                HEAT_TRY(launch_cg_update_p_peer(n, pout, pin, r, A->dinv.p, zbuf[(k - 1) & 1], gate, H, I, pr, s2, pp, vgrid, st));
             } else if (!cheb) {
                 HEAT_TRY(spmv_halo(ctx, A, p, ap, gate, S + S_PAP0));
                 HEAT_TRY(comm_allreduce_sum(ctx, S + S_PAP0, 1));
@@ -376,6 +429,10 @@ int solve_device(heat_ctx *ctx, heat_matrix *A, double *x, const double *b, cons
     if (peer) {                                       // identical on every rank: same launches everywhere
         ctx->peer_red_seq += 2ull * (unsigned)o.max_iters + 4;
         ctx->peer_halo_epoch += (unsigned)o.max_iters + 4;
+    }
+    if (cheb_fused) {
+        ctx->peer_red_seq += 2ull * (unsigned)o.max_iters + 4;
+        ctx->peer_halo_epoch += (unsigned long long)o.max_iters * (unsigned)o.cheb_degree + 4;
     }
 #ifdef HEAT_PEER_TRACE
     if (trace.p) {

@@ -380,11 +380,11 @@ static int launch_tma(const heat_matrix *A, const double *x, double *y, int64_t 
 // peer-memory mode: ONE launch over [interior slices | boundary slices]; needs the default TMA config
 bool spmv_peer_supported() { return spmv_variant() == 5; }
 
-template <bool C8>
+template <bool C8, int DOT>
 static int launch_spmv_peer_t(const heat_matrix *A, const double *x, double *y, CgGate gate, DotOut dot, SpmvPeer peer,
                               int grid, cudaStream_t st) {
     constexpr int NW = C8 ? kC8Warps : 8;
-    auto kern = sell_spmv_tma_kernel<1, 8, 2, NW, true, C8, 2>;
+    auto kern = sell_spmv_tma_kernel<DOT, 8, 2, NW, true, C8, 2>;
     const size_t smem = TmaSmem<8, 2, C8>::total(NW);
     static bool configured[kMaxDevices] = {};
     const int dev = A->ctx->device;
@@ -401,8 +401,11 @@ static int launch_spmv_peer_t(const heat_matrix *A, const double *x, double *y, 
 }
 int launch_spmv_peer(const heat_matrix *A, const double *x, double *y, CgGate gate, DotOut dot, SpmvPeer peer,
                      int grid, cudaStream_t st) {
-    return A->sell_idx8.p ? launch_spmv_peer_t<true>(A, x, y, gate, dot, peer, grid, st)
-                          : launch_spmv_peer_t<false>(A, x, y, gate, dot, peer, grid, st);
+    if (dot.out)                                  // p.Ap of CG goes to every rank's inbox
+        return A->sell_idx8.p ? launch_spmv_peer_t<true, 1>(A, x, y, gate, dot, peer, grid, st)
+                              : launch_spmv_peer_t<false, 1>(A, x, y, gate, dot, peer, grid, st);
+    return A->sell_idx8.p ? launch_spmv_peer_t<true, 0>(A, x, y, gate, dot, peer, grid, st)      // polynomial steps: no dot
+                          : launch_spmv_peer_t<false, 0>(A, x, y, gate, dot, peer, grid, st);
 }
 
 int launch_spmv(const heat_matrix *A, const double *x, double *y, int64_t first,
