@@ -103,10 +103,10 @@ static int assemble_cube_analytic(heat_ctx *ctx, int mode, heat_matrix *A, heat_
     HEAT_TRY(new_vector(ctx, A, B));
     {
         const char *how = getenv("HEAT_CUBE_ASSEMBLY");                // "csr": the CSR-first path
-        const char *cidx = getenv("HEAT_SPMV_CIDX");                   // 0: int32 column stream
+        const bool byte_index = sell_cidx_mode() == 1 && spmv_compact_supported();   // else: int32 ids (or the CSR-first path decides)
         bool done = false;
-        if (!(how && strcmp(how, "csr") == 0))
-            HEAT_TRY(cube_assemble_sell(c, mode, !(cidx && atoi(cidx) == 0), A, (*B)->d.p, ctx->stream, &done));
+        if (!(how && strcmp(how, "csr") == 0) && sell_cidx_mode() != 2)
+            HEAT_TRY(cube_assemble_sell(c, mode, byte_index, A, (*B)->d.p, ctx->stream, &done));
         if (!done) HEAT_TRY(cube_assemble(c, mode, A, (*B)->d.p, ctx->stream));
     }
     // halo plan: rank-1 (lower plane) first, then rank+1 — ghosts grouped by owner ascending
@@ -560,13 +560,13 @@ extern "C" int heat_matrix_get_info(const heat_matrix *A, heat_matrix_info *info
     info->n_boundary_slices = A->n_bnd_slices; info->n_slices = A->n_slices;
     info->assemble_ms = A->assemble_ms;
     info->peer_path = A->peer ? 1 : 0;
-    info->col_index_bytes = A->sell_idx8.p ? 1 : 4;
+    info->col_index_bytes = A->sell_cmode;
     info->assemble_fill_ms = A->assemble_fill_ms;
     for (int q = 0; q < 4; ++q) info->asm_phase_ms[q] = A->asm_phase_ms[q];
     info->csr_resident = A->row_ptr.p ? 1 : 0;
     info->matrix_bytes = (int64_t)(A->row_ptr.n * 8 + A->col.n * 4 + A->val.n * 8 + A->sell_val.n * 8 + A->sell_col.n * 4 +
                                    A->sell_idx8.n + A->sell_tab.n * 4 + A->slice_ptr.n * 8 + A->slice_meta.n * 16 +
-                                   A->sell_rowlen.n + A->diag.n * 8 + A->dinv.n * 8);
+                                   A->sell_rowlen.n + A->diag.n * 8 + A->dinv.n * 8 + A->slice_cptr.n * 8 + A->slice_mode.n);
     return 0;
 }
 

@@ -143,15 +143,26 @@ pattern_fill_kernel(int64_t n, const int64_t *__restrict__ red2orig, const int32
 
 // values + right-hand side of the OWNED rows.  lrow l <-> global reduced row gi = owned ? owned[l] : l.
 // Local row l copies the global pattern row (ascending global ids), columns mapped through g2l.
-__global__ void __launch_bounds__(128)
+// One thread per row (owner computes: atomic-free, accumulation in ascending element id like the oracle).  The row's
+// entries are accumulated in SHARED memory ([entry][thread], conflict-free) and written once — the first version
+// read-modify-wrote them in global memory for each of the ~96 element contributions of a row, 16x the output in DRAM
+// writes (ncu: 32 GB written for a 2 GB matrix at 256^3).  Node coordinates come as one 32-byte (x, y, z, 0) record
+// per node — one sector per gathered node instead of three — and a tet's four node ids as one 16-byte load.
+constexpr int kAccCap = 32;            // row entries held in shared memory; longer rows accumulate in global memory
+constexpr int kValThreads = 128;
+// NPE: nodes per element known at compile time for the P1 operator (4: tets, 3: triangles) so that the element
+// arrays stay in registers; 0: graph Laplacian (any clique size)
+template <int NPE>
+__global__ void __launch_bounds__(kValThreads)
 values_kernel(int64_t n_owned, const int32_t *__restrict__ owned, const int32_t *__restrict__ g2l,
               const int64_t *__restrict__ red2orig, const int32_t *__restrict__ red,
               const int64_t *__restrict__ n2e_ptr, const int32_t *__restrict__ n2e, int npe,
-              const int32_t *__restrict__ conn, const double *__restrict__ X, const double *__restrict__ Y,
-              const double *__restrict__ Z, const double *__restrict__ bc,
+              const int32_t *__restrict__ conn, const double4 *__restrict__ xyz, const double *__restrict__ bc,
               const int64_t *__restrict__ grow_ptr, const int32_t *__restrict__ gcol,
               const int64_t *__restrict__ lrow_ptr, int32_t *__restrict__ lcol, double *__restrict__ lval,
               double *__restrict__ b, int mode, int *overflow) {
+    __shared__ double acc_s[kAccCap][kValThreads];
+    const int tid = threadIdx.x;
     const int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= n_owned) return;
     const int64_t gi = owned ? (int64_t)owned[l] : l;
@@ -167,7 +178,7 @@ values_kernel(int64_t n_owned, const int32_t *__restrict__ owned, const int32_t 
         if (lc) lc[t] = g2l ? g2l[c] : c;
     }
     double bsum = 0.0;
-    if (mode == HEAT_OP_GRAPH_LAPLACIAN) {
+    if constexpr (NPE == 0) {
         int32_t buf[kMaxNbr];
         const int u = collect_neighbours(g, n2e_ptr, n2e, npe, conn, buf, overflow);
         for (int t = 0; t < u; ++t)
@@ -175,35 +186,64 @@ values_kernel(int64_t n_owned, const int32_t *__restrict__ owned, const int32_t 
         for (int t = 0; t < len; ++t) lv[t] = -1.0;                // :601
         lv[dpos] = (double)u;                                      // :606 full degree
     } else {
-        for (int t = 0; t < len; ++t) lv[t] = 0.0;
+        const bool in_smem = len <= kAccCap;
+        if (in_smem) { for (int t = 0; t < len; ++t) acc_s[t][tid] = 0.0; }
+        else { for (int t = 0; t < len; ++t) lv[t] = 0.0; }
         for (int64_t q = n2e_ptr[g]; q < n2e_ptr[g + 1]; ++q) {
-            const int32_t *e = conn + (int64_t)n2e[q] * npe;
+            constexpr int kN = NPE == 3 ? 3 : 4;
+            const int32_t *e = conn + (int64_t)n2e[q] * kN;
+            int32_t ev[4];
+            if (kN == 4) {
+                const int4 e4 = __ldg(reinterpret_cast<const int4 *>(e));
+                ev[0] = e4.x; ev[1] = e4.y; ev[2] = e4.z; ev[3] = e4.w;
+            } else {
+                ev[0] = e[0]; ev[1] = e[1]; ev[2] = e[2]; ev[3] = 0;
+            }
             double p[4][3], G[4][3], s;
             int a = -1;
-            for (int k = 0; k < npe; ++k) {
-                const int32_t v = e[k];
-                p[k][0] = X[v]; p[k][1] = Y[v]; p[k][2] = Z ? Z[v] : 0.0;
-                if (v == g && a < 0) a = k;
+#pragma unroll
+            for (int k = 0; k < kN; ++k) {
+                const double2 *c2 = reinterpret_cast<const double2 *>(xyz + ev[k]);     // one 32-byte sector, two 16-byte loads
+                const double2 xy = __ldg(c2), zw = __ldg(c2 + 1);
+                p[k][0] = xy.x; p[k][1] = xy.y; p[k][2] = zw.x;
+                if (ev[k] == g && a < 0) a = k;
             }
-            if (npe == 4) tet_G(p, G, s); else tri_G(p, G, s);
-            for (int k = 0; k < npe; ++k) {
-                const double kab = ((G[a][0] * G[k][0] + G[a][1] * G[k][1]) + G[a][2] * G[k][2]) * s;
-                const int32_t j = e[k];
+            if (kN == 4) tet_G(p, G, s); else tri_G(p, G, s);
+            double Ga[3];                                       // G[a] without a dynamically indexed (local-memory) array
+#pragma unroll
+            for (int d = 0; d < 3; ++d) Ga[d] = a == 0 ? G[0][d] : a == 1 ? G[1][d] : a == 2 ? G[2][d] : G[3][d];
+#pragma unroll
+            for (int k = 0; k < kN; ++k) {
+                const double kab = ((Ga[0] * G[k][0] + Ga[1] * G[k][1]) + Ga[2] * G[k][2]) * s;
+                const int32_t j = ev[k];
+                int slot = -1;
                 if (j == g) {
-                    lv[dpos] += kab;
+                    slot = dpos;
                 } else if (red[j] >= 0) {
                     const int32_t r = red[j];
                     int lo = 0, hi = len - 1;
                     while (lo < hi) { int mid = (lo + hi) >> 1; if (gc[mid] < r) lo = mid + 1; else hi = mid; }
-                    lv[lo] += kab;
+                    slot = lo;
                 } else {
                     const double t2 = kab * bc[j];
                     bsum = bsum - t2;
                 }
+                if (slot >= 0) {
+                    if (in_smem) acc_s[slot][tid] += kab; else lv[slot] += kab;
+                }
             }
         }
+        if (in_smem)
+            for (int t = 0; t < len; ++t) lv[t] = acc_s[t][tid];
     }
     b[l] = bsum;
+}
+
+// (x, y, z, 0) records of the nodes: one 32-byte sector per gathered node
+__global__ void pack_xyz_kernel(int64_t N, const double *__restrict__ X, const double *__restrict__ Y, const double *__restrict__ Z,
+                                double4 *__restrict__ xyz) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < N) xyz[g] = make_double4(X[g], Y[g], Z ? Z[g] : 0.0, 0.0);
 }
 
 // elapsed device time between two points of a stream (both events are created and destroyed here)
@@ -371,10 +411,20 @@ int GeneralAssembler::fill_values(int mode, int64_t n_owned, const int32_t *d_ow
     if (n_owned == 0) return 0;
     DevBuf<int> ovf; HEAT_TRY(ovf.alloc(1));
     HEAT_CUDA(cudaMemsetAsync(ovf.p, 0, sizeof(int), st));
+    if (!xyz.p) {
+        HEAT_TRY(xyz.alloc((size_t)N * 4));
+        pack_xyz_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(N, x.p, y.p, has_z ? z.p : nullptr, reinterpret_cast<double4 *>(xyz.p));
+        HEAT_LAUNCHED();
+    }
     StreamTimer t_val(st);
-    values_kernel<<<(unsigned)((n_owned + 127) / 128), 128, 0, st>>>(
-        n_owned, d_owned, d_g2l, red2orig.p, red.p, n2e_ptr.p, n2e.p, npe, conn.p, x.p, y.p, has_z ? z.p : nullptr,
-        bc.p, grow_ptr.p, gcol.p, d_lrow_ptr, d_lcol, d_lval, d_b, mode, ovf.p);
+    const unsigned vgrid = (unsigned)((n_owned + kValThreads - 1) / kValThreads);
+    const double4 *xyz4 = reinterpret_cast<const double4 *>(xyz.p);
+#define HEAT_VALUES_ARGS n_owned, d_owned, d_g2l, red2orig.p, red.p, n2e_ptr.p, n2e.p, npe, conn.p, xyz4, bc.p, grow_ptr.p, gcol.p, \
+                         d_lrow_ptr, d_lcol, d_lval, d_b, mode, ovf.p
+    if (mode == HEAT_OP_GRAPH_LAPLACIAN) values_kernel<0><<<vgrid, kValThreads, 0, st>>>(HEAT_VALUES_ARGS);
+    else if (npe == 4) values_kernel<4><<<vgrid, kValThreads, 0, st>>>(HEAT_VALUES_ARGS);
+    else values_kernel<3><<<vgrid, kValThreads, 0, st>>>(HEAT_VALUES_ARGS);
+#undef HEAT_VALUES_ARGS
     HEAT_LAUNCHED();
     phase_ms[3] = t_val.stop();
     return 0;
@@ -719,7 +769,7 @@ __global__ void __launch_bounds__(kCubeWarps * 32, 2) cube_sell_kernel(CubeSellA
                 const int2 cc = *reinterpret_cast<const int2 *>(tc + k * kSellChunk + 2 * lane);
                 const int off[2] = {cc.x - row0, cc.y - (row0 + 1)};
                 int id[2];
-                ok = sell_dict_step(tab, T, off, id);
+                ok = sell_dict_step(tab, T, off, id, k);
                 if (ok) *reinterpret_cast<uchar2 *>(ti + k * kSellChunk + 2 * lane) = make_uchar2((unsigned char)id[0], (unsigned char)id[1]);
             }
             if (!ok) T = kSellDictCap + 1;
@@ -842,7 +892,9 @@ int cube_assemble_sell(const CubeGeom &c, int mode, bool byte_index, heat_matrix
         return 0;
     }
     A->sell_tpad = byte_index ? tpad : 0;
+    A->sell_cmode = byte_index ? 1 : 4;
     HEAT_TRY(sell_finish_lists(A, need_split ? h_flags.data() : nullptr, st));
+    HEAT_TRY(sell_build_meta(A, st));
     *done = true;
     return 0;
 }

@@ -18,7 +18,7 @@ struct GeneralAssembler {
     int npe = 0;
     bool has_z = false;
     int32_t max_row = 0;
-    DevBuf<double> x, y, z, bc;
+    DevBuf<double> x, y, z, bc, xyz;    // xyz: packed (x, y, z, 0) per node, built by fill_values
     DevBuf<int32_t> conn, red, n2e, gcol;
     DevBuf<int64_t> red2orig, n2e_ptr, grow_ptr;
     // device time by phase (CUDA events on the assembly stream): node->element radix sort, pattern count,

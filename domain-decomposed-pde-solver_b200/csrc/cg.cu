@@ -87,7 +87,9 @@ __global__ void __launch_bounds__(kBlock) cg_update_xr_kernel(int64_t n, double 
     const double alpha = H[g.it].rz / pap;
     double acc[2] = {0.0, 0.0};
     const int64_t n2 = n >> 1, stride = (int64_t)gridDim.x * kBlock;
-    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n2; i += stride) {
+    const bool back = xr_backward(g);
+    for (int64_t t = (int64_t)blockIdx.x * kBlock + threadIdx.x; t < n2; t += stride) {
+        const int64_t i = back ? n2 - 1 - t : t;
         double2 pv = ld_stream_f64x2(p + 2 * i), av = ld_stream_f64x2(ap + 2 * i), dv = ld_stream_f64x2(dinv + 2 * i);
         double2 xv = *reinterpret_cast<const double2 *>(x + 2 * i);
         double2 rv = *reinterpret_cast<const double2 *>(r + 2 * i);
@@ -128,7 +130,9 @@ __global__ void __launch_bounds__(kBlock) cg_update_p_kernel(int64_t n, double *
     if (cg_done(nxt)) return;                              // converged: p is never used again
     const double beta = g.H[g.it + 1].rz / g.H[g.it].rz;
     const int64_t n2 = n >> 1, stride = (int64_t)gridDim.x * kBlock;
-    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n2; i += stride) {
+    const bool back = p_backward(g);
+    for (int64_t t = (int64_t)blockIdx.x * kBlock + threadIdx.x; t < n2; t += stride) {
+        const int64_t i = back ? n2 - 1 - t : t;
         double2 rv = ld_stream_f64x2(r + 2 * i), dv = ld_stream_f64x2(dinv + 2 * i);
         double2 pv = *reinterpret_cast<const double2 *>(p + 2 * i);
         pv.x = fma(beta, pv.x, dv.x * rv.x); pv.y = fma(beta, pv.y, dv.y * rv.y);
@@ -180,7 +184,9 @@ __global__ void __launch_bounds__(kBlock) cg_update_xr_peer_kernel(int64_t n, do
     const double alpha = H[g.it].rz / pap;
     double acc[2] = {0.0, 0.0};
     const int64_t n2 = n >> 1, stride = (int64_t)gridDim.x * kBlock;
-    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n2; i += stride) {
+    const bool back = xr_backward(g);
+    for (int64_t t = (int64_t)blockIdx.x * kBlock + threadIdx.x; t < n2; t += stride) {
+        const int64_t i = back ? n2 - 1 - t : t;
         double2 pv = ld_stream_f64x2(p + 2 * i), av = ld_stream_f64x2(ap + 2 * i), dv = ld_stream_f64x2(dinv + 2 * i);
         double2 xv = *reinterpret_cast<const double2 *>(x + 2 * i);
         double2 rv = *reinterpret_cast<const double2 *>(r + 2 * i);
@@ -276,7 +282,9 @@ __global__ void __launch_bounds__(kBlock) cg_update_p_peer_kernel(int64_t n, dou
         return;
     }
     peer_push_phase(push, [&](int32_t i) { return fma(beta, p_in[i], dinv[i] * r[i]); });
-    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n2; i += stride) {
+    const bool back = p_backward(g);
+    for (int64_t t = (int64_t)blockIdx.x * kBlock + threadIdx.x; t < n2; t += stride) {
+        const int64_t i = back ? n2 - 1 - t : t;
         double2 rv = ld_stream_f64x2(r + 2 * i), dv = ld_stream_f64x2(dinv + 2 * i);
         double2 pv = *reinterpret_cast<const double2 *>(p_in + 2 * i);
         pv.x = fma(beta, pv.x, dv.x * rv.x); pv.y = fma(beta, pv.y, dv.y * rv.y);

@@ -86,7 +86,11 @@ constexpr int kMaxDevices = 64;                          // per-device caches (f
 
 // one entry per slice in SpMV processing order (interior slices first, then boundary slices; natural
 // order on one GPU): everything a warp needs to start streaming the slice, in ONE 16-byte load
-struct SliceMeta { int64_t base; int32_t w; int32_t s; };   // entry offset, entries per row, slice id
+// base64 = entry offset / 64 (values: 8 B per entry), cbase64 = byte offset of the slice's column data / 64 in the
+// column stream, w_mode = entries per row | column mode << 24 (0: 1-byte table index, 1: int16 col-row delta,
+// 2: int32 column id), s = slice id
+struct SliceMeta { uint32_t base64; uint32_t cbase64; int32_t w_mode; int32_t s; };
+enum { kColModeU8 = 0, kColModeI16 = 1, kColModeI32 = 2 };
 
 // scalar slots of the CG state (device doubles)
 enum {
@@ -137,8 +141,14 @@ struct heat_matrix {
     heat::DevBuf<int64_t> slice_ptr;     // [n_slices+1] entry offsets
     heat::DevBuf<int32_t> sell_col;
     heat::DevBuf<double> sell_val;
-    // byte-indexed column stream (built when EVERY slice has <= kSellDictCap distinct col-row offsets):
-    // col = row + sell_tab[slice][sell_idx8[entry]]; 1 byte per entry instead of 4
+    // compact column stream, chosen PER SLICE (sell.cu): a slice with <= kSellDictCap distinct col-row offsets stores
+    // a 1-byte index into its offset table (col = row + sell_tab[slice][idx]); any other slice whose offsets fit 16
+    // bits stores int16 deltas (col = row + delta) — every mesh of moderate bandwidth; if some slice fits neither the
+    // matrix keeps the int32 stream (sell_col).  sell_cmode = widest entry of the stream: 1 (all slices table-indexed),
+    // 2 (table-indexed and int16 slices mixed; slice_cptr / slice_mode say which and where), 4 (int32: sell_col)
+    int sell_cmode = 4;
+    heat::DevBuf<int64_t> slice_cptr;    // [n_slices+1] byte offsets into sell_idx8 (mixed streams only)
+    heat::DevBuf<uint8_t> slice_mode;    // [n_slices] kColMode* (mixed streams only)
     heat::DevBuf<uint8_t> sell_rowlen;   // stored entries per row — only for matrices assembled straight into SELL (no CSR
                                          // until sell_to_csr rebuilds one for an export or ILU)
     heat::DevBuf<uint8_t> sell_idx8;

@@ -15,16 +15,26 @@ struct CgGate {               // stopping test evaluated by every block of every
     const double *S;          // scalars (S_TOL2)
     const int *I;             // I_STATUS
     int it;                   // iteration this launch belongs to
+    // Traversal direction of the iteration's kernels (0: all forward).  Consecutive kernels of the loop sweep the
+    // vectors in OPPOSITE directions — SpMV forward, update_xr backward, update_p forward, next SpMV backward, ... —
+    // so each kernel starts on the ~100 MB its predecessor touched last, which are still in the 126 MB L2.  It is
+    // the last-level-cache blocking a stream of whole-vector sweeps allows; it matters when a GPU's share of the
+    // vectors is comparable to the L2 (strong scaling: 134 MB per vector on 8 GPUs), not at 1 GB per vector.
+    //   1: even iteration (SpMV forward, update_xr backward, update_p forward)   2: odd iteration (the mirror image)
+    int dir;
 };
+__host__ __device__ inline bool spmv_backward(const CgGate &g) { return g.dir == 2; }
+__host__ __device__ inline bool xr_backward(const CgGate &g) { return g.dir == 1; }
+__host__ __device__ inline bool p_backward(const CgGate &g) { return g.dir == 2; }
 
 struct DotOut {               // where a fused dot product is reduced to
     double *partials; int part_offset; int total_blocks; int *counter; double *out;
     bool with_yy = false;     // SpMV only: also reduce sum_i y_i^2 into out[1]
 };
 
-struct SellDict {             // byte-indexed column stream of the SELL matrix (sell.cu); idx8 == nullptr: not built
-    const uint8_t *idx8;      // [sell_padded] index into the slice's offset table
-    const int32_t *tab;       // [n_slices][tpad] distinct (col - row) offsets of each slice
+struct SellDict {             // column stream of the SELL matrix (sell.cu)
+    const uint8_t *cstream;   // per slice (SliceMeta::cbase64): 1-byte table indices, int16 deltas or int32 column ids
+    const int32_t *tab;       // [n_slices][tpad] distinct (col - row) offsets of each table-indexed slice
     int tpad;                 // table stride, a multiple of 4 entries (16 bytes: one TMA granule)
 };
 
@@ -43,7 +53,9 @@ int trace_set_spmv(TraceBuf *buf);
 #endif
 // ---- sell.cu ----
 int sell_from_csr(heat_matrix *A, cudaStream_t st);
-int sell_finish_lists(heat_matrix *A, const int32_t *h_flags, cudaStream_t st);   // interior/boundary lists + slice_meta
+int sell_finish_lists(heat_matrix *A, const int32_t *h_flags, cudaStream_t st);   // interior/boundary slice lists
+int sell_build_meta(heat_matrix *A, cudaStream_t st);  // packed SliceMeta in processing order (after the column stream is chosen)
+int sell_cidx_mode();                                  // HEAT_SPMV_CIDX: 0 int32 only, 1 compact (default), 2 prefer int16
 int sell_to_csr(heat_matrix *A, cudaStream_t st);      // builds row_ptr/col/val from the SELL arrays if absent
 // ---- spmv.cu ----
 // y = A x over entries [first, first + n_list) of A->slice_meta (processing order: interior slices, then
@@ -54,6 +66,7 @@ int launch_spmv(const heat_matrix *A, const double *x, double *y, int64_t first,
 int launch_spmv_peer(const heat_matrix *A, const double *x, double *y, CgGate gate, DotOut dot, SpmvPeer peer,
                      int grid, cudaStream_t st);
 bool spmv_peer_supported();
+bool spmv_compact_supported();                         // the selected SpMV variant can stream the compact column formats
 int spmv_grid(int64_t n_list, int sm_count);
 // ---- cg.cu ----
 int launch_cg_init(int64_t n, const double *b, const double *ax, const double *dinv, double *r,

@@ -60,27 +60,34 @@ sell_fill_kernel(const int64_t *__restrict__ row_ptr, const int32_t *__restrict_
     if (lane == 0 && slice_is_boundary) slice_is_boundary[s] = ghost;
 }
 
-// packed per-slice metadata in processing order (list == nullptr: natural order)
-__global__ void slice_meta_kernel(const int64_t *__restrict__ slice_ptr, const int32_t *__restrict__ list, int64_t n_list,
+// packed per-slice metadata in processing order (list == nullptr: natural order).  cptr / mode == nullptr: the column
+// stream has `cbytes` bytes per entry in every slice (1: all table-indexed, 4: int32 ids) at cbytes * entry offset.
+__global__ void slice_meta_kernel(const int64_t *__restrict__ slice_ptr, const int64_t *__restrict__ cptr,
+                                  const uint8_t *__restrict__ mode, int cbytes, const int32_t *__restrict__ list, int64_t n_list,
                                   SliceMeta *__restrict__ meta) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_list) return;
     const int64_t s = list ? (int64_t)list[t] : t;
     const int64_t b = slice_ptr[s];
-    meta[t] = SliceMeta{b, (int32_t)((slice_ptr[s + 1] - b) >> 6), (int32_t)s};
+    const int32_t w = (int32_t)((slice_ptr[s + 1] - b) >> 6);
+    const int m = mode ? mode[s] : (cbytes == 1 ? kColModeU8 : kColModeI32);
+    const int64_t cb = cptr ? cptr[s] : b * cbytes;
+    meta[t] = SliceMeta{(uint32_t)(b >> 6), (uint32_t)(cb >> 6), w | (m << 24), (int32_t)s};
 }
 
-// Byte-indexed column stream.  One warp per slice collects the distinct (col - row) offsets of the
-// slice's 64 x w entries (first-seen order: k ascending, then lane, then the lane's first row) in a
-// shared-memory table.  On a structured mesh a slice has as many distinct offsets as the stencil has
-// directions (15 on the Kuhn cube, a few more where ghost columns start), so the 4-byte column id of
-// every entry shrinks to a 1-byte table index: 12 -> 9 bytes per stored entry in the SpMV stream.
-// WRITE == false only measures the table length of every slice (the matrix is byte-indexed only if ALL
-// slices fit kSellDictCap); WRITE == true stores indices and tables (stride tpad).
-template <bool WRITE>
+// Compact column stream, chosen per slice.  One warp per slice collects the distinct (col - row) offsets of the
+// slice's 64 x w entries (first-seen order: k ascending, then lane, then the lane's first row) in a shared-memory
+// table.  On a structured mesh a slice has as many distinct offsets as the stencil has directions (15 on the Kuhn
+// cube, a few more where ghost columns start), so the 4-byte column id of every entry shrinks to a 1-byte table
+// index: 12 -> 9 bytes per stored entry.  A slice with more than kSellDictCap distinct offsets (any unstructured
+// numbering) stores int16 deltas col - row instead, 12 -> 10 bytes, whenever they fit — every mesh whose bandwidth is
+// below 32768; only if some slice fits neither does the matrix keep the int32 stream.
+// PASS 1 classifies: mode[s], table length, column bytes of the slice.  PASS 2 writes the stream and the tables.
+__device__ __forceinline__ bool fits_i16(int v) { return v >= -32768 && v <= 32767; }
+
 __global__ void __launch_bounds__(kBlock)
-sell_dict_kernel(const int64_t *__restrict__ slice_ptr, const int32_t *__restrict__ scol, int64_t n_slices,
-                 int tpad, uint8_t *__restrict__ idx8, int32_t *__restrict__ tabs, int *__restrict__ max_len) {
+sell_classify_kernel(const int64_t *__restrict__ slice_ptr, const int32_t *__restrict__ scol, int64_t n_slices, int force16,
+                     uint8_t *__restrict__ mode, int64_t *__restrict__ cbytes, int *__restrict__ max_tab, int *__restrict__ any_mode) {
     __shared__ int32_t tab_s[kWarpsPerBlock][kSellDictCap];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t s = (int64_t)blockIdx.x * kWarpsPerBlock + warp;
@@ -89,53 +96,108 @@ sell_dict_kernel(const int64_t *__restrict__ slice_ptr, const int32_t *__restric
     const int64_t base = slice_ptr[s];
     const int w = (int)((slice_ptr[s + 1] - base) >> 6);
     const int row0 = (int)(s * kSellChunk) + 2 * lane;
-    int T = 0;                                         // warp-uniform table length
-    bool overflow = false;
-    for (int k = 0; k < w && !overflow; ++k) {
+    int T = 0;
+    bool table_ok = true, i16_ok = true;
+    for (int k = 0; k < w; ++k) {
         const int2 c = *reinterpret_cast<const int2 *>(scol + base + (int64_t)k * kSellChunk + 2 * lane);
         const int off[2] = {c.x - row0, c.y - (row0 + 1)};
+        i16_ok = i16_ok && fits_i16(off[0]) && fits_i16(off[1]);
         int id[2];
-        overflow = !sell_dict_step(tab, T, off, id);
-        if (WRITE && !overflow)
-            *reinterpret_cast<uchar2 *>(idx8 + base + (int64_t)k * kSellChunk + 2 * lane) =
-                make_uchar2((unsigned char)id[0], (unsigned char)id[1]);
+        if (table_ok) table_ok = sell_dict_step(tab, T, off, id, k);
     }
-    if (overflow) T = kSellDictCap + 1;
-    if (!WRITE) {
-        if (lane == 0) atomicMax(max_len, T);
-    } else {
+    i16_ok = __all_sync(0xffffffffu, i16_ok);
+    const int m = (table_ok && !(force16 && i16_ok)) ? kColModeU8 : i16_ok ? kColModeI16 : kColModeI32;
+    if (lane == 0) {
+        mode[s] = (uint8_t)m;
+        cbytes[s] = (int64_t)w * kSellChunk * (m == kColModeU8 ? 1 : m == kColModeI16 ? 2 : 4);
+        if (m == kColModeU8) atomicMax(max_tab, T);
+        atomicOr(any_mode, 1 << m);
+    }
+}
+
+__global__ void __launch_bounds__(kBlock)
+sell_compact_kernel(const int64_t *__restrict__ slice_ptr, const int32_t *__restrict__ scol, int64_t n_slices,
+                    const uint8_t *__restrict__ mode, const int64_t *__restrict__ cptr, int tpad,
+                    uint8_t *__restrict__ cstream, int32_t *__restrict__ tabs) {
+    __shared__ int32_t tab_s[kWarpsPerBlock][kSellDictCap];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t s = (int64_t)blockIdx.x * kWarpsPerBlock + warp;
+    if (s >= n_slices) return;
+    int32_t *tab = tab_s[warp];
+    const int64_t base = slice_ptr[s];
+    const int w = (int)((slice_ptr[s + 1] - base) >> 6);
+    const int row0 = (int)(s * kSellChunk) + 2 * lane;
+    const int m = mode ? mode[s] : kColModeU8;
+    uint8_t *out = cstream + (cptr ? cptr[s] : base);
+    int T = 0;
+    for (int k = 0; k < w; ++k) {
+        const int2 c = *reinterpret_cast<const int2 *>(scol + base + (int64_t)k * kSellChunk + 2 * lane);
+        const int off[2] = {c.x - row0, c.y - (row0 + 1)};
+        if (m == kColModeU8) {
+            int id[2];
+            sell_dict_step(tab, T, off, id, k);
+            *reinterpret_cast<uchar2 *>(out + (int64_t)k * kSellChunk + 2 * lane) = make_uchar2((unsigned char)id[0], (unsigned char)id[1]);
+        } else {
+            *reinterpret_cast<short2 *>(out + 2 * ((int64_t)k * kSellChunk + 2 * lane)) = make_short2((short)off[0], (short)off[1]);
+        }
+    }
+    if (tabs) {
         __syncwarp();
-        for (int t = lane; t < tpad; t += 32) tabs[s * tpad + t] = t < T ? tab[t] : 0;
+        for (int t = lane; t < tpad; t += 32) tabs[s * tpad + t] = (m == kColModeU8 && t < T) ? tab[t] : 0;
     }
 }
 
-static bool want_byte_index() {
-    const char *e = getenv("HEAT_SPMV_CIDX");          // 0: keep int32 columns only
-    return !(e && atoi(e) == 0);
+// HEAT_SPMV_CIDX: 0 = keep int32 columns only; 1 (default) = compact where possible; 2 = prefer int16 deltas over
+// tables (tests / measurements of the int16 path on structured meshes)
+int sell_cidx_mode() {
+    const char *e = getenv("HEAT_SPMV_CIDX");
+    const int v = e ? atoi(e) : 1;
+    return v < 0 || v > 2 ? 1 : v;
 }
 
-// builds A->sell_idx8 / sell_tab when every slice qualifies; leaves them empty otherwise
+// builds the compact column stream (A->sell_idx8, sell_tab, slice_cptr, slice_mode, sell_cmode); leaves the int32
+// stream in charge (sell_cmode = 4) when some slice fits neither a table nor int16 deltas
 static int sell_build_dict(heat_matrix *A, cudaStream_t st) {
     const int64_t ns = A->n_slices;
-    A->sell_tpad = 0;
-    A->sell_idx8.release(); A->sell_tab.release();
-    if (ns == 0 || A->sell_padded == 0 || !want_byte_index()) return 0;
-    DevBuf<int> d_max;
-    HEAT_TRY(d_max.alloc(1));
-    HEAT_CUDA(cudaMemsetAsync(d_max.p, 0, sizeof(int), st));
+    A->sell_tpad = 0; A->sell_cmode = 4;
+    A->sell_idx8.release(); A->sell_tab.release(); A->slice_cptr.release(); A->slice_mode.release();
+    const int want = sell_cidx_mode();
+    if (ns == 0 || A->sell_padded == 0 || want == 0 || !spmv_compact_supported()) return 0;
+    DevBuf<int> d_flags;                              // [0] longest table, [1] bit m set: some slice has mode m
+    HEAT_TRY(d_flags.alloc(2));
+    HEAT_CUDA(cudaMemsetAsync(d_flags.p, 0, 2 * sizeof(int), st));
+    DevBuf<int64_t> cbytes;
+    HEAT_TRY(cbytes.alloc((size_t)ns));
+    HEAT_TRY(A->slice_mode.alloc((size_t)ns));
     const unsigned grid = (unsigned)((ns + kWarpsPerBlock - 1) / kWarpsPerBlock);
-    sell_dict_kernel<false><<<grid, kBlock, 0, st>>>(A->slice_ptr.p, A->sell_col.p, ns, 0, nullptr, nullptr, d_max.p);
+    sell_classify_kernel<<<grid, kBlock, 0, st>>>(A->slice_ptr.p, A->sell_col.p, ns, want == 2, A->slice_mode.p, cbytes.p, d_flags.p, d_flags.p + 1);
     HEAT_LAUNCHED();
-    int h_max = 0;
-    HEAT_CUDA(cudaMemcpyAsync(&h_max, d_max.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    int h[2] = {0, 0};
+    HEAT_CUDA(cudaMemcpyAsync(h, d_flags.p, sizeof(h), cudaMemcpyDeviceToHost, st));
     HEAT_CUDA(cudaStreamSynchronize(st));
-    if (h_max > kSellDictCap) return 0;                // some slice has too many distinct offsets: int32 columns
-    const int tpad = h_max < 4 ? 4 : (h_max + 3) & ~3; // 16-byte granules for the TMA copy of a table
-    HEAT_TRY(A->sell_idx8.alloc((size_t)A->sell_padded));
+    if (h[1] & (1 << kColModeI32)) { A->slice_mode.release(); return 0; }       // some slice needs int32 ids: keep sell_col
+    const bool mixed = (h[1] & (1 << kColModeI16)) != 0;
+    const int tpad = h[0] < 4 ? 4 : (h[0] + 3) & ~3;   // 16-byte granules for the TMA copy of a table
+    int64_t total = A->sell_padded;
+    if (mixed) {
+        HEAT_TRY(A->slice_cptr.alloc((size_t)ns + 1));
+        HEAT_CUDA(cudaMemsetAsync(A->slice_cptr.p, 0, sizeof(int64_t), st));
+        size_t tb = 0;
+        HEAT_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tb, cbytes.p, A->slice_cptr.p + 1, ns, st));
+        DevBuf<char> tmp; HEAT_TRY(tmp.alloc(tb));
+        HEAT_CUDA(cub::DeviceScan::InclusiveSum(tmp.p, tb, cbytes.p, A->slice_cptr.p + 1, ns, st));
+        HEAT_CUDA(cudaMemcpyAsync(&total, A->slice_cptr.p + ns, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        HEAT_CUDA(cudaStreamSynchronize(st));
+    } else {
+        A->slice_mode.release();                       // every slice is table-indexed: the stream is idx8[entry]
+    }
+    HEAT_TRY(A->sell_idx8.alloc((size_t)total));
     HEAT_TRY(A->sell_tab.alloc((size_t)ns * (size_t)tpad));
-    sell_dict_kernel<true><<<grid, kBlock, 0, st>>>(A->slice_ptr.p, A->sell_col.p, ns, tpad, A->sell_idx8.p, A->sell_tab.p, nullptr);
+    sell_compact_kernel<<<grid, kBlock, 0, st>>>(A->slice_ptr.p, A->sell_col.p, ns, mixed ? A->slice_mode.p : nullptr,
+                                                 mixed ? A->slice_cptr.p : nullptr, tpad, A->sell_idx8.p, A->sell_tab.p);
     HEAT_LAUNCHED();
     A->sell_tpad = tpad;
+    A->sell_cmode = mixed ? 2 : 1;
     return 0;
 }
 
@@ -184,10 +246,17 @@ int sell_finish_lists(heat_matrix *A, const int32_t *h_flags, cudaStream_t st) {
             HEAT_CUDA(cudaMemcpyAsync(A->slices_boundary.p, lb.data(), sizeof(int32_t) * lb.size(), cudaMemcpyHostToDevice, st));
         HEAT_CUDA(cudaStreamSynchronize(st));          // the host vectors die here
     }
+    return 0;
+}
+
+// packed per-slice metadata of the SpMV, in processing order; needs the column stream (sell_cmode, slice_cptr, slice_mode)
+int sell_build_meta(heat_matrix *A, cudaStream_t st) {
+    const int64_t ns = A->n_slices;
     HEAT_TRY(A->slice_meta.alloc((size_t)ns));
     if (ns > 0) {
-        slice_meta_kernel<<<(unsigned)((ns + 255) / 256), 256, 0, st>>>(A->slice_ptr.p, A->n_ghost > 0 ? A->slices_all.p : nullptr, ns,
-                                                                      A->slice_meta.p);
+        slice_meta_kernel<<<(unsigned)((ns + 255) / 256), 256, 0, st>>>(A->slice_ptr.p, A->slice_cptr.p, A->slice_mode.p,
+                                                                      A->sell_cmode == 1 ? 1 : 4, A->n_ghost > 0 ? A->slices_all.p : nullptr,
+                                                                      ns, A->slice_meta.p);
         HEAT_LAUNCHED();
     }
     return 0;
@@ -203,6 +272,7 @@ sell_to_csr_kernel(const int64_t *__restrict__ slice_ptr, const double *__restri
                    const uint8_t *__restrict__ idx8, const int32_t *__restrict__ tabs, int tpad, const uint8_t *__restrict__ rowlen,
                    int64_t n_rows, int64_t n_slices, const int64_t *__restrict__ row_ptr, int32_t *__restrict__ col,
                    double *__restrict__ val) {
+    // (only matrices assembled straight into SELL come here: their stream is all table-indexed or all int32)
     const int lane = threadIdx.x & 31;
     const int64_t s = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     if (s >= n_slices) return;
@@ -286,6 +356,7 @@ int sell_from_csr(heat_matrix *A, cudaStream_t st) {
         HEAT_TRY(sell_finish_lists(A, nullptr, st));
     }
     HEAT_TRY(sell_build_dict(A, st));
+    HEAT_TRY(sell_build_meta(A, st));
     HEAT_TRY(launch_extract_diag(A, st));
     return 0;
 }

@@ -334,13 +334,16 @@ int solve_device(heat_ctx *ctx, heat_matrix *A, double *x, const double *b, cons
     }
 #endif
     // ---- iterations, polled every check_every ----
+    // consecutive kernels sweep the vectors in opposite directions (kernels.cuh: CgGate::dir); HEAT_CG_ALTERNATE=0: all forward
+    const char *alt_env = getenv("HEAT_CG_ALTERNATE");
+    const bool alternate = !(alt_env && atoi(alt_env) == 0) && !single && !cheb;
     const int check = o.check_every > 0 ? o.check_every : 32;
     int launched = 0, h_iters = 0, h_status = 0;
     while (launched < o.max_iters) {
         const int batch = (o.max_iters - launched) < check ? (o.max_iters - launched) : check;
         for (int q = 0; q < batch; ++q) {
             const int it = launched + q;
-            CgGate gate{H, S, I, it};
+            CgGate gate{H, S, I, it, alternate ? 1 + (it & 1) : 0};
             if (single) {
                 double *u = A->w_u.p, *s = A->w_s.p, *w = ap;
                 HEAT_TRY(launch_cg_fused_update(n, x, r, p, s, u, w, dinv, gate, H, I, A->partials.p, I + I_COUNTER2, vgrid, st));

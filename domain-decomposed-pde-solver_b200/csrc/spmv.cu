@@ -121,22 +121,22 @@ __device__ __forceinline__ uint64_t l2_evict_first_policy() {
     return p;
 }
 
-// C8: the column stream is one byte per entry (index into the slice's table of distinct col-row
-// offsets, sell.cu) instead of an int32; each warp also keeps NSTAGE table buffers (the issue cursor
-// runs at most NSTAGE chunks, hence at most NSTAGE slices, ahead of the consume cursor).
-template <int KC, int NSTAGE, bool C8 = false>
+// CB = widest column entry of the matrix's stream in bytes: 1 (every slice table-indexed), 2 (table-indexed and int16
+// slices mixed), 4 (int32 ids).  With CB <= 2 each warp also keeps NSTAGE table buffers (the issue cursor runs at
+// most NSTAGE chunks, hence at most NSTAGE slices, ahead of the consume cursor).
+template <int KC, int NSTAGE, int CB = 4>
 struct TmaSmem {
     static constexpr int kValBytes = KC * kSellChunk * 8;
-    static constexpr int kColBytes = KC * kSellChunk * (C8 ? 1 : 4);
+    static constexpr int kColBytes = KC * kSellChunk * CB;
     static constexpr int kStageBytes = kValBytes + kColBytes;
-    static constexpr int kTabBytes = C8 ? kSellDictCap * 4 : 0;
+    static constexpr int kTabBytes = CB <= 2 ? kSellDictCap * 4 : 0;
     static constexpr int kRing = NSTAGE + 2;                       // slices the issue cursor can be ahead of the consumer, + 1
     static constexpr int kRingBytes = ((kRing * 8) + 15) & ~15;    // {slice id, width} per ring slot
     static constexpr int kWarpBytes = NSTAGE * (kStageBytes + kTabBytes) + kRingBytes;
     static constexpr size_t total(int nwarps) { return (size_t)nwarps * kWarpBytes + (size_t)nwarps * NSTAGE * 8; }
 };
 
-template <int DOT, int KC, int NSTAGE, int NWARPS, bool PEER = false, bool C8 = false,
+template <int DOT, int KC, int NSTAGE, int NWARPS, bool PEER = false, int CB = 4,
           int MINB = ((NWARPS <= 8 && KC <= 8) ? 2 : 1)>
 __global__ void __launch_bounds__(NWARPS * 32, MINB)
 sell_spmv_tma_kernel(const SliceMeta *__restrict__ meta, const int32_t *__restrict__ col,
@@ -144,7 +144,7 @@ sell_spmv_tma_kernel(const SliceMeta *__restrict__ meta, const int32_t *__restri
                      int64_t n_rows, int64_t n_list, CgGate gate, DotOut dot, SpmvPeer peer, SellDict dict) {
     if (gate_done(gate)) return;
     if (PEER && threadIdx.x == 0) HEAT_TRACE_MIN(gate.it, 0, 0);
-    using L = TmaSmem<KC, NSTAGE, C8>;
+    using L = TmaSmem<KC, NSTAGE, CB>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char *my = smem_raw + (size_t)warp * L::kWarpBytes;
@@ -167,13 +167,20 @@ sell_spmv_tma_kernel(const SliceMeta *__restrict__ meta, const int32_t *__restri
     // as long as a warp needs for one slice, and a stalled issue cursor is a bubble in the TMA pipeline.  The
     // consume cursor gets {id, width} through a small shared-memory ring written when the slice is first issued
     // (ordered by the mbarrier phase the consumer waits for anyway).
-    struct Meta { int64_t base; int s, w; };
+    // gate.dir: on odd iterations the (interior) slices are swept from the end of the list, so the kernel starts on
+    // the part of the input vector its predecessor wrote last (kernels.cuh: CgGate::dir); boundary slices stay last
+    const bool back = spmv_backward(gate);
+    const int64_t n_rev = PEER ? (peer.n_interior < n_list ? peer.n_interior : n_list) : n_list;
+    struct Meta { int64_t base, cb; int s, w, mode; };     // value offset (entries), column offset (bytes), id, width, column mode
     auto load_meta = [&](int64_t t) -> Meta {
-        Meta m{0, 0, 0};
+        Meta m{0, 0, 0, 0, 0};
         if (t < n_list) {
+            if (back && t < n_rev) t = n_rev - 1 - t;
             const int4 q = __ldg(reinterpret_cast<const int4 *>(meta + t));
-            m.base = ((int64_t)(unsigned)q.x) | ((int64_t)q.y << 32);
-            m.w = q.z; m.s = q.w;
+            m.base = (int64_t)(unsigned)q.x << 6;
+            m.cb = (int64_t)(unsigned)q.y << 6;
+            m.w = q.z & 0xffffff; m.s = q.w;
+            m.mode = CB == 1 ? kColModeU8 : CB == 4 ? kColModeI32 : (q.z >> 24);
         }
         return m;
     };
@@ -185,19 +192,16 @@ sell_spmv_tma_kernel(const SliceMeta *__restrict__ meta, const int32_t *__restri
     auto issue = [&](int stage) {
         const int kc = (mi.w - ki) < KC ? (mi.w - ki) : KC;
         if (lane == 0) {
-            if (ki == 0) ring[si % L::kRing] = make_int2(mi.s, mi.w);
+            if (ki == 0) ring[si % L::kRing] = make_int2(mi.s, mi.w | (mi.mode << 24));
             if (kc > 0) {
                 unsigned char *dst = my + stage * L::kStageBytes;
-                const uint32_t vb = (uint32_t)kc * kSellChunk * 8, cb = (uint32_t)kc * kSellChunk * (C8 ? 1 : 4);
-                const uint32_t tb = (C8 && ki == 0) ? (uint32_t)dict.tpad * 4 : 0;   // first chunk brings the table
+                const uint32_t ebytes = mi.mode == kColModeU8 ? 1u : mi.mode == kColModeI16 ? 2u : 4u;     // column bytes per entry
+                const uint32_t vb = (uint32_t)kc * kSellChunk * 8, cb = (uint32_t)kc * kSellChunk * ebytes;
+                const uint32_t tb = (mi.mode == kColModeU8 && ki == 0) ? (uint32_t)dict.tpad * 4 : 0;   // first chunk brings the table
                 mbar_arrive_expect_tx(bars + stage, vb + cb + tb);
                 tma_load_1d(dst, val + mi.base + (int64_t)ki * kSellChunk, vb, bars + stage, policy);
-                if (C8) {
-                    tma_load_1d(dst + L::kValBytes, dict.idx8 + mi.base + (int64_t)ki * kSellChunk, cb, bars + stage, policy);
-                    if (tb) tma_load_1d(my_tabs + (si % NSTAGE) * L::kTabBytes, dict.tab + (int64_t)mi.s * dict.tpad, tb, bars + stage, policy);
-                } else {
-                    tma_load_1d(dst + L::kValBytes, col + mi.base + (int64_t)ki * kSellChunk, cb, bars + stage, policy);
-                }
+                tma_load_1d(dst + L::kValBytes, dict.cstream + mi.cb + (int64_t)ki * kSellChunk * ebytes, cb, bars + stage, policy);
+                if (tb) tma_load_1d(my_tabs + (si % NSTAGE) * L::kTabBytes, dict.tab + (int64_t)mi.s * dict.tpad, tb, bars + stage, policy);
             } else {
                 mbar_arrive(bars + stage);                              // empty slice: complete the phase
             }
@@ -217,13 +221,18 @@ sell_spmv_tma_kernel(const SliceMeta *__restrict__ meta, const int32_t *__restri
     int64_t tc = first;
     int kc0 = 0, sc = 0;                                             // sc: ordinal of the slice being consumed
     int2 mc = make_int2(0, 0);                                       // {slice id, width}: read from the ring per slice
+    int cmode = CB == 1 ? kColModeU8 : kColModeI32;                  // column mode of the slice being consumed
     int stage = 0;
     uint32_t parity = 0;
     double acc0 = 0.0, acc1 = 0.0, dsum = 0.0, ysum = 0.0;
     bool halo_ready = !PEER;
     while (tc < n_list) {
         mbar_wait(bars + stage, parity);
-        if (kc0 == 0) mc = ring[sc % L::kRing];
+        if (kc0 == 0) {
+            mc = ring[sc % L::kRing];
+            if (CB == 2) cmode = mc.y >> 24;
+            mc.y &= 0xffffff;
+        }
         const int kc = (mc.y - kc0) < KC ? (mc.y - kc0) : KC;
         const double *vs = reinterpret_cast<const double *>(my + stage * L::kStageBytes) + 2 * lane;
         const int32_t *cs = reinterpret_cast<const int32_t *>(my + stage * L::kStageBytes + L::kValBytes) + 2 * lane;
@@ -232,9 +241,13 @@ sell_spmv_tma_kernel(const SliceMeta *__restrict__ meta, const int32_t *__restri
         const int row0 = mc.x * kSellChunk + 2 * lane;
         // the two column ids of this lane at entry k of the staged chunk
         auto cols_at = [&](int k) -> int2 {
-            if (C8) {
+            if (CB == 1 || (CB == 2 && cmode == kColModeU8)) {
                 const uchar2 ix = *reinterpret_cast<const uchar2 *>(is + k * kSellChunk);
                 return make_int2(row0 + tb[ix.x], row0 + 1 + tb[ix.y]);
+            }
+            if (CB == 2) {                                           // int16 deltas: col = row + delta
+                const short2 d = *reinterpret_cast<const short2 *>(is + 2 * (k * kSellChunk + 2 * lane) - 2 * lane);
+                return make_int2(row0 + d.x, row0 + 1 + d.y);
             }
             return *reinterpret_cast<const int2 *>(cs + k * kSellChunk);
         };
@@ -358,13 +371,17 @@ int spmv_grid(int64_t n_list, int sm_count) {
     return grid_for(blocks, sm_count, v == 5 ? 2 : 1);    // persistent: one (or two) CTA per SM
 }
 
-static SellDict dict_of(const heat_matrix *A) { return SellDict{A->sell_idx8.p, A->sell_tab.p, A->sell_tpad}; }
+// column stream the kernel reads: the compact one (table indices / int16 deltas) or the int32 ids themselves
+static SellDict dict_of(const heat_matrix *A) {
+    if (A->sell_cmode == 4) return SellDict{reinterpret_cast<const uint8_t *>(A->sell_col.p), nullptr, 0};
+    return SellDict{A->sell_idx8.p, A->sell_tab.p, A->sell_tpad};
+}
 
-template <int DOT, int KC, int NSTAGE, int NWARPS, bool C8 = false, int MINB = ((NWARPS <= 8 && KC <= 8) ? 2 : 1)>
+template <int DOT, int KC, int NSTAGE, int NWARPS, int CB = 4, int MINB = ((NWARPS <= 8 && KC <= 8) ? 2 : 1)>
 static int launch_tma(const heat_matrix *A, const double *x, double *y, int64_t first, int64_t n_list,
                       CgGate gate, DotOut dot, int grid, cudaStream_t st) {
-    auto kern = sell_spmv_tma_kernel<DOT, KC, NSTAGE, NWARPS, false, C8, MINB>;
-    const size_t smem = TmaSmem<KC, NSTAGE, C8>::total(NWARPS);
+    auto kern = sell_spmv_tma_kernel<DOT, KC, NSTAGE, NWARPS, false, CB, MINB>;
+    const size_t smem = TmaSmem<KC, NSTAGE, CB>::total(NWARPS);
     static bool configured[kMaxDevices] = {};            // function attributes are per DEVICE, not per process
     const int dev = A->ctx->device;
     if (dev < 0 || dev >= kMaxDevices || !configured[dev]) {
@@ -379,13 +396,14 @@ static int launch_tma(const heat_matrix *A, const double *x, double *y, int64_t 
 
 // peer-memory mode: ONE launch over [interior slices | boundary slices]; needs the default TMA config
 bool spmv_peer_supported() { return spmv_variant() == 5; }
+bool spmv_compact_supported() { return spmv_variant() == 5; }
 
-template <bool C8, int DOT>
+template <int CB, int DOT>
 static int launch_spmv_peer_t(const heat_matrix *A, const double *x, double *y, CgGate gate, DotOut dot, SpmvPeer peer,
                               int grid, cudaStream_t st) {
-    constexpr int NW = C8 ? kC8Warps : 8;
-    auto kern = sell_spmv_tma_kernel<DOT, 8, 2, NW, true, C8, 2>;
-    const size_t smem = TmaSmem<8, 2, C8>::total(NW);
+    constexpr int NW = CB <= 2 ? kC8Warps : 8;
+    auto kern = sell_spmv_tma_kernel<DOT, 8, 2, NW, true, CB, 2>;
+    const size_t smem = TmaSmem<8, 2, CB>::total(NW);
     static bool configured[kMaxDevices] = {};
     const int dev = A->ctx->device;
     if (dev < 0 || dev >= kMaxDevices || !configured[dev]) {
@@ -399,13 +417,19 @@ static int launch_spmv_peer_t(const heat_matrix *A, const double *x, double *y, 
     HEAT_LAUNCHED();
     return 0;
 }
+template <int DOT>
+static int launch_spmv_peer_d(const heat_matrix *A, const double *x, double *y, CgGate gate, DotOut dot, SpmvPeer peer,
+                              int grid, cudaStream_t st) {
+    switch (A->sell_cmode) {
+        case 1: return launch_spmv_peer_t<1, DOT>(A, x, y, gate, dot, peer, grid, st);
+        case 2: return launch_spmv_peer_t<2, DOT>(A, x, y, gate, dot, peer, grid, st);
+        default: return launch_spmv_peer_t<4, DOT>(A, x, y, gate, dot, peer, grid, st);
+    }
+}
 int launch_spmv_peer(const heat_matrix *A, const double *x, double *y, CgGate gate, DotOut dot, SpmvPeer peer,
                      int grid, cudaStream_t st) {
-    if (dot.out)                                  // p.Ap of CG goes to every rank's inbox
-        return A->sell_idx8.p ? launch_spmv_peer_t<true, 1>(A, x, y, gate, dot, peer, grid, st)
-                              : launch_spmv_peer_t<false, 1>(A, x, y, gate, dot, peer, grid, st);
-    return A->sell_idx8.p ? launch_spmv_peer_t<true, 0>(A, x, y, gate, dot, peer, grid, st)      // polynomial steps: no dot
-                          : launch_spmv_peer_t<false, 0>(A, x, y, gate, dot, peer, grid, st);
+    return dot.out ? launch_spmv_peer_d<1>(A, x, y, gate, dot, peer, grid, st)       // p.Ap of CG goes to every rank's inbox
+                   : launch_spmv_peer_d<0>(A, x, y, gate, dot, peer, grid, st);      // polynomial steps: no dot
 }
 
 int launch_spmv(const heat_matrix *A, const double *x, double *y, int64_t first,
@@ -414,23 +438,28 @@ int launch_spmv(const heat_matrix *A, const double *x, double *y, int64_t first,
     const int32_t *slice_list = A->n_ghost > 0 ? A->slices_all.p + first : nullptr;      // direct-load kernel only
     const int v = spmv_variant();
     const bool d = dot.out != nullptr;
-    if (A->sell_idx8.p && v == 5) {      // byte-indexed column stream (sell.cu: every slice has a small offset table)
-        if (d && dot.with_yy) return launch_tma<2, 8, 2, kC8Warps, true, 2>(A, x, y, first, n_list, gate, dot, grid, st);
+    if (A->sell_cmode == 2 && v == 5) {  // table-indexed and int16-delta slices mixed (sell.cu)
+        if (d && dot.with_yy) return launch_tma<2, 8, 2, kC8Warps, 2, 2>(A, x, y, first, n_list, gate, dot, grid, st);
+        return d ? launch_tma<1, 8, 2, kC8Warps, 2, 2>(A, x, y, first, n_list, gate, dot, grid, st)
+                 : launch_tma<0, 8, 2, kC8Warps, 2, 2>(A, x, y, first, n_list, gate, dot, grid, st);
+    }
+    if (A->sell_cmode == 1 && v == 5) {  // byte-indexed column stream (sell.cu: every slice has a small offset table)
+        if (d && dot.with_yy) return launch_tma<2, 8, 2, kC8Warps, 1, 2>(A, x, y, first, n_list, gate, dot, grid, st);
         switch (c8_cfg()) {
-            case 1: return d ? launch_tma<1, 8, 2, 8, true, 2>(A, x, y, first, n_list, gate, dot, grid, st)
-                             : launch_tma<0, 8, 2, 8, true, 2>(A, x, y, first, n_list, gate, dot, grid, st);
-            case 2: return d ? launch_tma<1, 8, 2, 11, true, 2>(A, x, y, first, n_list, gate, dot, grid, st)
-                             : launch_tma<0, 8, 2, 11, true, 2>(A, x, y, first, n_list, gate, dot, grid, st);
-            case 3: return d ? launch_tma<1, 6, 2, 12, true, 2>(A, x, y, first, n_list, gate, dot, grid, st)
-                             : launch_tma<0, 6, 2, 12, true, 2>(A, x, y, first, n_list, gate, dot, grid, st);
-            case 4: return d ? launch_tma<1, 6, 3, 10, true, 2>(A, x, y, first, n_list, gate, dot, grid, st)
-                             : launch_tma<0, 6, 3, 10, true, 2>(A, x, y, first, n_list, gate, dot, grid, st);
-            case 5: return d ? launch_tma<1, 4, 3, 10, true, 2>(A, x, y, first, n_list, gate, dot, grid, st)
-                             : launch_tma<0, 4, 3, 10, true, 2>(A, x, y, first, n_list, gate, dot, grid, st);
+            case 1: return d ? launch_tma<1, 8, 2, 8, 1, 2>(A, x, y, first, n_list, gate, dot, grid, st)
+                             : launch_tma<0, 8, 2, 8, 1, 2>(A, x, y, first, n_list, gate, dot, grid, st);
+            case 2: return d ? launch_tma<1, 8, 2, 11, 1, 2>(A, x, y, first, n_list, gate, dot, grid, st)
+                             : launch_tma<0, 8, 2, 11, 1, 2>(A, x, y, first, n_list, gate, dot, grid, st);
+            case 3: return d ? launch_tma<1, 6, 2, 12, 1, 2>(A, x, y, first, n_list, gate, dot, grid, st)
+                             : launch_tma<0, 6, 2, 12, 1, 2>(A, x, y, first, n_list, gate, dot, grid, st);
+            case 4: return d ? launch_tma<1, 6, 3, 10, 1, 2>(A, x, y, first, n_list, gate, dot, grid, st)
+                             : launch_tma<0, 6, 3, 10, 1, 2>(A, x, y, first, n_list, gate, dot, grid, st);
+            case 5: return d ? launch_tma<1, 4, 3, 10, 1, 2>(A, x, y, first, n_list, gate, dot, grid, st)
+                             : launch_tma<0, 4, 3, 10, 1, 2>(A, x, y, first, n_list, gate, dot, grid, st);
             default: break;
         }
-        return d ? launch_tma<1, 8, 2, kC8Warps, true, 2>(A, x, y, first, n_list, gate, dot, grid, st)
-                 : launch_tma<0, 8, 2, kC8Warps, true, 2>(A, x, y, first, n_list, gate, dot, grid, st);
+        return d ? launch_tma<1, 8, 2, kC8Warps, 1, 2>(A, x, y, first, n_list, gate, dot, grid, st)
+                 : launch_tma<0, 8, 2, kC8Warps, 1, 2>(A, x, y, first, n_list, gate, dot, grid, st);
     }
     if (d && dot.with_yy) {      // x.y and y.y in one pass (power method): default TMA config or direct loads
         if (v != 0) return launch_tma<2, 8, 2, 8>(A, x, y, first, n_list, gate, dot, grid, st);

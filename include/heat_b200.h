@@ -214,8 +214,10 @@ typedef struct {
     int64_t sell_padded_nnz, n_boundary_slices, n_slices;
     double  assemble_ms;      /* device time of pattern+values+SELL (CUDA events)                 */
     int32_t peer_path;        /* 1 once the NVLink peer-memory halo/all-reduce path is set up      */
-    int32_t col_index_bytes;  /* bytes per stored entry of the SpMV column stream: 4 (int32 ids), or 1
-                                 (index into the slice's table of distinct col-row offsets)        */
+    int32_t col_index_bytes;  /* widest entry of the SpMV column stream, chosen per 64-row slice: 1 (every slice stores a
+                                 1-byte index into its table of distinct col-row offsets: structured numberings), 2
+                                 (slices that fit no table store int16 col-row deltas: any mesh of bandwidth < 32768),
+                                 4 (int32 column ids)                                                  */
     double  assemble_fill_ms; /* the matrix-fill kernel alone (analytic cubes: cube_sell_kernel, straight into the
                                  SpMV format; explicit meshes: values_kernel), CUDA events               */
     double  asm_phase_ms[4];  /* explicit-mesh assembly by phase: node->element radix sort, pattern count,

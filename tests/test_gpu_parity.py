@@ -524,7 +524,7 @@ def test_spmv_variants_bit_identical(hb, oracle):
             "print(hashlib.sha1(y.numpy().tobytes()).hexdigest(), hashlib.sha1(X.numpy().tobytes()).hexdigest())")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     outs = set()
-    for v, cidx in [(v, "1") for v in range(6)] + [(5, "0")]:      # (5, "1") is the byte-indexed default
+    for v, cidx in [(v, "1") for v in range(6)] + [(5, "0"), (5, "2")]:      # (5, "1"): byte-indexed default; (5, "2"): int16 deltas
         env = dict(os.environ, HEAT_SPMV_VARIANT=str(v), HEAT_SPMV_CIDX=cidx)
         p = subprocess.run([sys.executable, "-c", code % root], capture_output=True, text=True, env=env, timeout=300)
         assert p.returncode == 0, p.stderr[-2000:]
@@ -541,8 +541,9 @@ def test_byte_indexed_column_stream(hb, oracle):
         io.mesh_cube(*dims)
         for mode in (0, 1):
             A, X, B = io.assemble(mode)
-            # (3,2,2): 4 rows in one 64-row slice, the 60 tail rows all point at column 0 -> int32 stream
-            assert A.info.col_index_bytes == (4 if dims == (3, 2, 2) else 1), dims
+            # (3,2,2): 4 rows in one 64-row slice, the 60 tail rows all point at column 0: 60 distinct offsets plus the
+            # stencil's do not fit a 64-entry table -> the slice stores int16 deltas
+            assert A.info.col_index_bytes == (2 if dims == (3, 2, 2) else 1), dims
             ref = oracle.assemble(oracle.cube_mesh(*dims), mode)
             x, y = A.hash_vector(11), A.new_vector()
             io.spmv(A, x, y)
@@ -557,8 +558,69 @@ def test_byte_indexed_column_stream(hb, oracle):
     io = hb.IO(0)
     io.open(mesh_path("tet-cube-heat"), True)                         # unstructured numbering: hundreds of offsets per slice
     A, X, B = io.assemble(0)
-    assert A.info.col_index_bytes == 4
+    assert A.info.col_index_bytes == 2                                # ... but every offset fits 16 bits: int16 deltas
     io.close()
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_int16_delta_and_mixed_column_streams(hb, oracle, mode):
+    """Per-slice choice of the column stream: unstructured numberings (the reference's meshes) stream int16 col-row
+    deltas, structured slices 1-byte table indices, and one matrix may mix both; a bandwidth beyond 16 bits keeps int32.
+    Whatever the stream, SpMV and assembled system are the oracle's, bit for bit."""
+    def check(io, ref, expect):
+        A, X, B = io.assemble(mode)
+        assert A.info.col_index_bytes == expect, (A.info.col_index_bytes, expect)
+        x, y = A.hash_vector(3), A.new_vector()
+        io.spmv(A, x, y)
+        np.testing.assert_array_equal(y.numpy(), oracle.spmv(ref, x.numpy()))
+        pr = io.power_method(A, 3, 0.0, 5)                               # the x.y / y.y variant of the same kernel
+        lam = oracle.power_method(ref, oracle.hash_vector(np.arange(ref.n), 5), 3, 0.0)[0]
+        assert abs(pr.lambda_ - lam) <= 1e-12 * abs(lam)
+        res = io.solve(A, X, B, max_iters=3000, tol=RES_TOL)
+        x_ref, it_ref, *_ = oracle.pcg(ref, tol=RES_TOL, max_iters=3000)
+        assert res.converged and abs(res.iters - it_ref) <= ITER_SLACK
+        assert np.abs(X.numpy() - x_ref).max() <= SOL_RTOL * np.abs(x_ref).max()
+        rp, col, val = A.csr()
+        np.testing.assert_array_equal(col, ref.col); np.testing.assert_array_equal(val, ref.val)
+
+    for name in ("tet-cube-heat", "bolted_bracket"):                     # all slices int16
+        io = hb.IO(0)
+        io.open(mesh_path(name), True)
+        check(io, oracle.assemble(oracle.read_exodus(mesh_path(name)), mode), 2)
+        io.close()
+    # a structured cube whose upper half is renumbered at random: table-indexed slices below, int16 slices above
+    m = oracle.cube_mesh(24, 20, 18)
+    N = m.num_nodes
+    perm = np.arange(N)
+    rng = np.random.default_rng(5)
+    hi = np.arange(N // 2, N)
+    perm[hi] = rng.permutation(hi)                                       # new id of old node g
+    inv = np.empty(N, dtype=np.int64); inv[perm] = np.arange(N)
+    m2 = oracle.Mesh(m.x[inv], m.y[inv], m.z[inv], perm[m.conn].astype(np.int32), {k: np.sort(perm[v]) for k, v in m.nodesets.items()})
+    io = hb.IO(0)
+    io.mesh_set(m2.x, m2.y, m2.z, m2.conn, m2.nodesets)
+    check(io, oracle.assemble(m2, mode), 2)
+    io.close()
+    # a numbering whose bandwidth exceeds 16 bits: int32 ids are kept
+    m = oracle.cube_mesh(48, 40, 40)
+    N = m.num_nodes
+    perm = np.random.default_rng(9).permutation(N)
+    inv = np.empty(N, dtype=np.int64); inv[perm] = np.arange(N)
+    m3 = oracle.Mesh(m.x[inv], m.y[inv], m.z[inv], perm[m.conn].astype(np.int32), {k: np.sort(perm[v]) for k, v in m.nodesets.items()})
+    io = hb.IO(0)
+    io.mesh_set(m3.x, m3.y, m3.z, m3.conn, m3.nodesets)
+    check(io, oracle.assemble(m3, mode), 4)
+    io.close()
+    # forced int16 on a structured cube (HEAT_SPMV_CIDX=2): same bits
+    old = os.environ.get("HEAT_SPMV_CIDX")
+    os.environ["HEAT_SPMV_CIDX"] = "2"
+    try:
+        io = hb.IO(0)
+        io.mesh_cube(40, 33, 29)
+        check(io, oracle.assemble(oracle.cube_mesh(40, 33, 29), mode), 2)
+        io.close()
+    finally:
+        os.environ.pop("HEAT_SPMV_CIDX") if old is None else os.environ.__setitem__("HEAT_SPMV_CIDX", old)
 
 
 def test_cli_driver_end_to_end(hb, oracle, tmp_path):
