@@ -465,6 +465,8 @@ extern "C" int heat_solve(heat_ctx *ctx, heat_matrix *A, heat_vector *X, const h
                           const heat_solve_opts *opts, heat_solve_info *info) {
     if (!ctx || !A || !X || !B || !opts) HEAT_FAIL(2, "heat_solve: null argument");
     if (X->n_owned != A->n_owned || B->n_owned != A->n_owned) HEAT_FAIL(2, "heat_solve: vector/matrix size mismatch");
+    if (X->n_ghost != A->n_ghost) HEAT_FAIL(2, "heat_solve: X holds %lld ghost entries, the matrix needs %lld (create it with heat_vector_create on this matrix)",
+                                            (long long)X->n_ghost, (long long)A->n_ghost);
     return solve_device(ctx, A, X->d.p, B->d.p, *opts, info);
 }
 
@@ -475,7 +477,7 @@ extern "C" int heat_solve_trajectory(heat_ctx *ctx, heat_matrix *A, heat_vector 
                                      const heat_solve_opts *opts, int write_every, int first_timestep,
                                      heat_solve_info *info, int *frames_written) {
     if (!ctx || !A || !X || !B || !opts) HEAT_FAIL(2, "heat_solve_trajectory: null argument");
-    if (X->n_owned != A->n_owned || B->n_owned != A->n_owned) HEAT_FAIL(2, "heat_solve_trajectory: vector/matrix size mismatch");
+    if (X->n_owned != A->n_owned || B->n_owned != A->n_owned || X->n_ghost != A->n_ghost) HEAT_FAIL(2, "heat_solve_trajectory: vector/matrix size mismatch");
     if (write_every < 1 || first_timestep < 0) HEAT_FAIL(2, "heat_solve_trajectory: write_every >= 1 and first_timestep >= 0 needed");
     heat_solve_opts o = *opts;
     o.check_every = write_every;
@@ -532,7 +534,7 @@ extern "C" int heat_solve_host(heat_ctx *ctx, heat_matrix *A, const double *b_ho
 
 extern "C" int heat_spmv(heat_ctx *ctx, heat_matrix *A, heat_vector *x, heat_vector *y) {
     if (!ctx || !A || !x || !y) HEAT_FAIL(2, "heat_spmv: null argument");
-    if (x->n_owned != A->n_owned || y->n_owned != A->n_owned || x == y) HEAT_FAIL(2, "heat_spmv: bad vectors");
+    if (x->n_owned != A->n_owned || y->n_owned != A->n_owned || x == y || x->n_ghost != A->n_ghost) HEAT_FAIL(2, "heat_spmv: bad vectors");
     HEAT_CUDA(cudaSetDevice(ctx->device));
     CgGate nogate{nullptr, nullptr, nullptr, 0};
     return spmv_halo(ctx, A, x->d.p, y->d.p, nogate, nullptr);

@@ -200,12 +200,14 @@ values_kernel(int64_t n_owned, const int32_t *__restrict__ owned, const int32_t 
                 ev[0] = e[0]; ev[1] = e[1]; ev[2] = e[2]; ev[3] = 0;
             }
             double p[4][3], G[4][3], s;
+            int32_t rv[4];                                      // reduced ids of the element's nodes (-1: Dirichlet)
             int a = -1;
 #pragma unroll
             for (int k = 0; k < kN; ++k) {
                 const double2 *c2 = reinterpret_cast<const double2 *>(xyz + ev[k]);     // one 32-byte sector, two 16-byte loads
                 const double2 xy = __ldg(c2), zw = __ldg(c2 + 1);
                 p[k][0] = xy.x; p[k][1] = xy.y; p[k][2] = zw.x;
+                rv[k] = (int32_t)__double_as_longlong(zw.y);
                 if (ev[k] == g && a < 0) a = k;
             }
             if (kN == 4) tet_G(p, G, s); else tri_G(p, G, s);
@@ -219,8 +221,8 @@ values_kernel(int64_t n_owned, const int32_t *__restrict__ owned, const int32_t 
                 int slot = -1;
                 if (j == g) {
                     slot = dpos;
-                } else if (red[j] >= 0) {
-                    const int32_t r = red[j];
+                } else if (rv[k] >= 0) {
+                    const int32_t r = rv[k];
                     int lo = 0, hi = len - 1;
                     while (lo < hi) { int mid = (lo + hi) >> 1; if (gc[mid] < r) lo = mid + 1; else hi = mid; }
                     slot = lo;
@@ -239,11 +241,12 @@ values_kernel(int64_t n_owned, const int32_t *__restrict__ owned, const int32_t 
     b[l] = bsum;
 }
 
-// (x, y, z, 0) records of the nodes: one 32-byte sector per gathered node
+// (x, y, z, reduced id) records of the nodes: one 32-byte sector per gathered node carries everything the element
+// loop needs to know about it (the reduced id, -1 for Dirichlet nodes, rides in the fourth slot as an integer)
 __global__ void pack_xyz_kernel(int64_t N, const double *__restrict__ X, const double *__restrict__ Y, const double *__restrict__ Z,
-                                double4 *__restrict__ xyz) {
+                                const int32_t *__restrict__ red, double4 *__restrict__ xyz) {
     const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g < N) xyz[g] = make_double4(X[g], Y[g], Z ? Z[g] : 0.0, 0.0);
+    if (g < N) xyz[g] = make_double4(X[g], Y[g], Z ? Z[g] : 0.0, __longlong_as_double((long long)red[g]));
 }
 
 // elapsed device time between two points of a stream (both events are created and destroyed here)
@@ -413,7 +416,7 @@ int GeneralAssembler::fill_values(int mode, int64_t n_owned, const int32_t *d_ow
     HEAT_CUDA(cudaMemsetAsync(ovf.p, 0, sizeof(int), st));
     if (!xyz.p) {
         HEAT_TRY(xyz.alloc((size_t)N * 4));
-        pack_xyz_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(N, x.p, y.p, has_z ? z.p : nullptr, reinterpret_cast<double4 *>(xyz.p));
+        pack_xyz_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(N, x.p, y.p, has_z ? z.p : nullptr, red.p, reinterpret_cast<double4 *>(xyz.p));
         HEAT_LAUNCHED();
     }
     StreamTimer t_val(st);

@@ -64,8 +64,10 @@ int read_atts(Reader &r, std::vector<NcAtt> &atts) {
         a.name = r.name();
         a.type = (int)r.u32();
         a.nelems = r.count();
-        size_t bytes = (size_t)a.nelems * nc_type_size(a.type);
-        if (!r.ok || r.pos + bytes > r.n) return 1;
+        const size_t esz = (size_t)nc_type_size(a.type);
+        // overflow-safe: nelems * esz and pos + bytes are file-controlled (CDF-5 counts are 64-bit)
+        if (!r.ok || a.nelems < 0 || esz == 0 || r.pos > r.n || (uint64_t)a.nelems > (uint64_t)(r.n - r.pos) / esz) return 1;
+        size_t bytes = (size_t)a.nelems * esz;
         a.raw.assign(r.p + r.pos, r.p + r.pos + bytes);
         r.pos += (bytes + 3) & ~(size_t)3;
         atts.push_back(std::move(a));
@@ -422,16 +424,22 @@ int exo_read_mesh(const ExoFile &f, HostMesh &m) {
     } else if (const NcVar *c = nc.var("coord")) {
         std::vector<double> all = nc.get_doubles(*c);
         const size_t N = (size_t)m.num_nodes;
+        if (m.num_dim < 1 || m.num_dim > 3 || all.size() < N * (size_t)m.num_dim)
+            HEAT_FAIL(65, "'%s': coord holds %zu values, %d x %zu expected", f.path.c_str(), all.size(), m.num_dim, N);
         m.x.assign(all.begin(), all.begin() + N);
         if (m.num_dim > 1) m.y.assign(all.begin() + N, all.begin() + 2 * N); else m.y.assign(N, 0.0);
         if (m.num_dim > 2) m.z.assign(all.begin() + 2 * N, all.begin() + 3 * N);
     } else if (m.num_nodes > 0) {
         HEAT_FAIL(65, "'%s' has no coordinates", f.path.c_str());
     }
+    if (m.num_nodes > 0 && ((int64_t)m.x.size() < m.num_nodes || (int64_t)m.y.size() < m.num_nodes ||
+                            (!m.z.empty() && (int64_t)m.z.size() < m.num_nodes)))
+        HEAT_FAIL(65, "'%s': coordinate arrays shorter than num_nodes = %lld", f.path.c_str(), (long long)m.num_nodes);
     m.npe = 0;
     for (int64_t b = 1; b <= nblk; ++b) {
         const NcVar *cv = nc.var("connect" + std::to_string(b));
         if (!cv) continue;                                   // NULL block (eb_status == 0)
+        if (cv->dimids.size() < 2) HEAT_FAIL(66, "'%s': connect%lld is not a [elements][nodes] table", f.path.c_str(), (long long)b);
         const int npe_b = (int)nc.dims[(size_t)cv->dimids[1]].len;
         if (m.npe == 0) m.npe = npe_b;
         if (npe_b != m.npe) HEAT_FAIL(66, "'%s': element blocks with %d and %d nodes per element; mixed meshes are not supported", f.path.c_str(), m.npe, npe_b);
@@ -447,6 +455,7 @@ int exo_read_mesh(const ExoFile &f, HostMesh &m) {
         const NcVar *ids = nc.var("ns_prop1");
         if (!ids) HEAT_FAIL(67, "'%s': nodesets without ns_prop1", f.path.c_str());
         std::vector<int64_t> idv = nc.get_ints(*ids);
+        if ((int64_t)idv.size() < nns) HEAT_FAIL(67, "'%s': ns_prop1 holds %zu ids for %lld nodesets", f.path.c_str(), idv.size(), (long long)nns);
         for (int64_t s = 1; s <= nns; ++s) {
             std::vector<int64_t> &dst = m.nodesets[idv[(size_t)s - 1]];     // ExodusIO.hpp:176-191
             if (const NcVar *nv = nc.var("node_ns" + std::to_string(s)))
@@ -683,7 +692,7 @@ extern "C" int heat_nodal_field(heat_ctx *ctx, const heat_vector *X, double *fie
 }
 
 // IO::writeSolution (ExodusIO.hpp:1972-2070): nodal variable "Steady-State Heat Solution",
-// step timestep+1, time (real_t)timestep; the first call also writes a BC-only frame at step 1.
+// step timestep+1, time (real_t)timestep; the first call also writes a BC-only frame at step 1, time 0.
 extern "C" int heat_write_solution(heat_ctx *ctx, const heat_vector *X, int timestep) {
     if (!ctx || !X) HEAT_FAIL(2, "heat_write_solution: null argument");
     if (timestep < 0) HEAT_FAIL(2, "heat_write_solution: negative timestep");
@@ -708,9 +717,9 @@ extern "C" int heat_write_nodal_field(heat_ctx *ctx, const double *field_host, i
     NcFile &nc = wf.nc;
     if (nc.dim_id("num_nodes") < 0) HEAT_FAIL(4, "heat_write_solution: output mesh not written (call heat_decompose)");
     const int64_t N = m.num_nodes;
-    bool layout_changed = false;
+    bool layout_changed = false, first_call = false;
     if (!ctx->printed_time_zero) {                              // :2034-2040
-        layout_changed = true;
+        layout_changed = true; first_call = true;
         nc.add_dim("num_nod_var", 1);
         if (nc.dim_id("len_name") < 0) nc.add_dim("len_name", 33);
         const int64_t len_name = nc.dim_len("len_name", 33);
@@ -736,6 +745,20 @@ extern "C" int heat_write_nodal_field(heat_ctx *ctx, const double *field_host, i
         tw->raw.resize((size_t)(step * ws), 0);
         vv->raw.resize((size_t)(step * N * ws), 0);
         nc.numrecs = step;
+    }
+    if (first_call && step > 1) {
+        // the reference's first call also writes a boundary-condition-only frame as step 1, time 0 (:2036-2039):
+        // nodeset nodes hold their id, unknowns 0 — it survives whenever the first timestep written is not 0
+        if ((int64_t)ctx->node_bc.size() != N && !m.is_cube) heat::build_node_bc(ctx);
+        const std::vector<double> &bcv = ctx->out_largest_id ? ctx->node_bc_hi : ctx->node_bc;
+        std::vector<double> frame((size_t)N, 0.0);
+        if ((int64_t)bcv.size() == N)
+            for (int64_t g = 0; g < N; ++g) frame[(size_t)g] = std::isnan(bcv[(size_t)g]) ? 0.0 : bcv[(size_t)g];
+        if (ws == 8) {
+            swap_copy(vv->raw.data(), frame.data(), (size_t)N, 8);
+        } else {
+            for (int64_t g = 0; g < N; ++g) { const float f = (float)frame[(size_t)g]; swap_copy(vv->raw.data() + 4 * g, &f, 1, 4); }
+        }
     }
     const double t = (double)timestep;
     if (ws == 8) {

@@ -425,7 +425,13 @@ int solve_device(heat_ctx *ctx, heat_matrix *A, double *x, const double *b, cons
         HEAT_CUDA(cudaMemcpyAsync(hI, I, sizeof(int) * 2, cudaMemcpyDeviceToHost, st));
         HEAT_CUDA(cudaStreamSynchronize(st));
         h_iters = hI[I_ITERS]; h_status = hI[I_STATUS];
-        if (on_poll && h_status == 0) HEAT_TRY((*on_poll)(h_iters));      // x holds iterate h_iters (trajectory output)
+        if (on_poll && h_status == 0) {
+            HEAT_TRY((*on_poll)(h_iters));          // x holds iterate h_iters (trajectory output)
+            // the callback may keep ONE rank busy for seconds (rank 0 gathers and writes the Exodus frame) while the
+            // others would launch the next batch and spin on its stamps until the peer-wait budget runs out: line the
+            // ranks up again first (a stream-ordered 1-double all-reduce; the NCCL path simply waits in its collectives)
+            if ((peer || cheb_fused) && ctx->nranks > 1) HEAT_TRY(comm_allreduce_sum(ctx, S + S_COUNT - 1, 1));
+        }
         if (h_iters < launched) break;              // the stopping test fired (or breakdown): frozen
     }
     HEAT_CUDA(cudaEventRecord(ctx->ev_b, st));

@@ -296,3 +296,26 @@ def test_write_nodal_field_records_in_place_float32(hb, host_io, tmp_path):
     np.testing.assert_array_equal(tw, [0, 1, 0, 3])
     nc.close()
 
+
+
+def test_first_write_at_a_later_timestep_keeps_the_boundary_frame(hb, host_io, tmp_path):
+    """IO::writeSolution's first call also writes a boundary-condition-only frame as step 1, time 0 (nodeset nodes hold
+    their id, unknowns 0; ExodusIO.hpp:2034-2040).  When the first timestep written is k > 0 that frame survives."""
+    from scipy.io import netcdf_file
+    import oracle as O
+    src = mesh_path("bolted_bracket")
+    out = str(tmp_path / "late.exo")
+    host_io.open(src, True)
+    host_io.create(out)
+    host_io.decompose(2)
+    N = 4098
+    f = np.random.default_rng(3).standard_normal(N)
+    host_io.write_nodal_field(f, 2)                             # first call: timestep 2 -> step 3
+    nc = netcdf_file(out, "r", mmap=False)
+    vals, tw = np.array(nc.variables["vals_nod_var1"].data), np.array(nc.variables["time_whole"].data)
+    bc = O.read_exodus(src).node_bc()                           # lowest nodeset id per node (the FIXED output rule), NaN for unknowns
+    np.testing.assert_array_equal(vals[0], np.where(np.isnan(bc), 0.0, bc))
+    assert not vals[1].any()
+    np.testing.assert_array_equal(vals[2], f)
+    np.testing.assert_array_equal(tw, [0, 0, 2])
+    nc.close()
