@@ -78,6 +78,7 @@ __global__ void __launch_bounds__(kBlock) cg_update_xr_kernel(int64_t n, double 
                                                               const double *__restrict__ dinv, CgGate g,
                                                               CgRec *H, double *S, int *I,
                                                               double *partials, int *counter) {
+    pdl_wait();
     if (cg_done(g)) return;
     const double pap = S[S_PAP0];
     if (!(pap > 0.0)) {                                   // Belos: "p.Ap <= 0" is a breakdown
@@ -106,6 +107,7 @@ __global__ void __launch_bounds__(kBlock) cg_update_xr_kernel(int64_t n, double 
         x[i] = xv; r[i] = rv;
         acc[0] += (dinv[i] * rv) * rv; acc[1] += rv * rv;
     }
+    pdl_launch_dependents();
     double *const out[2] = {&H[g.it + 1].rz, &H[g.it + 1].rr};
     if (grid_sum<2>(acc, partials, 0, gridDim.x, counter, out)) {
         H[g.it].alpha = alpha;
@@ -116,7 +118,7 @@ __global__ void __launch_bounds__(kBlock) cg_update_xr_kernel(int64_t n, double 
 int launch_cg_update_xr(int64_t n, double *x, double *r, const double *p, const double *ap,
                         const double *dinv, CgGate gate, CgRec *H, double *S, int *I,
                         double *partials, int *counter, int grid, cudaStream_t st) {
-    cg_update_xr_kernel<<<grid, kBlock, 0, st>>>(n, x, r, p, ap, dinv, gate, H, S, I, partials, counter);
+    HEAT_CUDA(launch_kernel(cg_update_xr_kernel, grid, kBlock, 0, st, gate.pdl != 0, n, x, r, p, ap, dinv, gate, H, S, I, partials, counter));
     HEAT_LAUNCHED();
     return 0;
 }
@@ -125,6 +127,7 @@ int launch_cg_update_xr(int64_t n, double *x, double *r, const double *p, const 
 __global__ void __launch_bounds__(kBlock) cg_update_p_kernel(int64_t n, double *__restrict__ p,
                                                              const double *__restrict__ r,
                                                              const double *__restrict__ dinv, CgGate g) {
+    pdl_wait();
     if (cg_done(g)) return;
     CgGate nxt = g; nxt.it = g.it + 1;
     if (cg_done(nxt)) return;                              // converged: p is never used again
@@ -146,7 +149,7 @@ __global__ void __launch_bounds__(kBlock) cg_update_p_kernel(int64_t n, double *
 
 int launch_cg_update_p(int64_t n, double *p, const double *r, const double *dinv, CgGate gate,
                        int grid, cudaStream_t st) {
-    cg_update_p_kernel<<<grid, kBlock, 0, st>>>(n, p, r, dinv, gate);
+    HEAT_CUDA(launch_kernel(cg_update_p_kernel, grid, kBlock, 0, st, gate.pdl != 0, n, p, (const double *)r, dinv, gate));
     HEAT_LAUNCHED();
     return 0;
 }
@@ -165,6 +168,7 @@ __global__ void __launch_bounds__(kBlock) cg_update_xr_peer_kernel(int64_t n, do
                                                                    int *counter, PeerRed pr,
                                                                    unsigned long long seq_in,
                                                                    unsigned long long seq_out) {
+    pdl_wait();
     if (cg_done(g)) return;
     if (threadIdx.x == 0) HEAT_TRACE_MIN(g.it, 1, 0);
     __shared__ double sh[2];
@@ -203,6 +207,7 @@ __global__ void __launch_bounds__(kBlock) cg_update_xr_peer_kernel(int64_t n, do
         x[i] = xv; r[i] = rv;
         acc[0] += (dinv[i] * rv) * rv; acc[1] += rv * rv;
     }
+    pdl_launch_dependents();
     double *const out[2] = {S + S_TMP0, S + S_TMP1};
     if (grid_sum_block<2>(acc, partials, 0, gridDim.x, counter, out)) {
         if (threadIdx.x == 0) H[g.it].alpha = alpha;
@@ -214,7 +219,8 @@ __global__ void __launch_bounds__(kBlock) cg_update_xr_peer_kernel(int64_t n, do
 int launch_cg_update_xr_peer(int64_t n, double *x, double *r, const double *p, const double *ap, const double *dinv,
                              CgGate gate, CgRec *H, double *S, int *I, double *partials, int *counter, PeerRed pr,
                              unsigned long long seq_in, unsigned long long seq_out, int grid, cudaStream_t st) {
-    cg_update_xr_peer_kernel<<<grid, kBlock, 0, st>>>(n, x, r, p, ap, dinv, gate, H, S, I, partials, counter, pr, seq_in, seq_out);
+    HEAT_CUDA(launch_kernel(cg_update_xr_peer_kernel, grid, kBlock, 0, st, gate.pdl != 0, n, x, r, p, ap, dinv, gate, H, S, I, partials, counter,
+                            pr, seq_in, seq_out));
     HEAT_LAUNCHED();
     return 0;
 }
@@ -251,6 +257,7 @@ __global__ void __launch_bounds__(kBlock) cg_update_p_peer_kernel(int64_t n, dou
                                                                   const double *__restrict__ z, CgGate g,
                                                                   CgRec *H, int *I, PeerRed pr,
                                                                   unsigned long long seq_in, PeerPush push) {
+    pdl_wait();
     if (cg_done(g)) return;
     if (threadIdx.x == 0) HEAT_TRACE_MIN(g.it, 2, 0);
     __shared__ double sh[3];
@@ -309,12 +316,16 @@ __global__ void __launch_bounds__(kBlock) cg_update_p_peer_kernel(int64_t n, dou
 // Z is ping-ponged between two buffers for the same reason p is: a neighbour may already deliver the boundary of
 // the next polynomial iterate while this GPU still gathers the previous one.
 // -------------------------------------------------------------------------------------------------
+// r and W are written OUT OF PLACE (r_in -> r_out, w_in -> w_out, ping-ponged by the host like p and Z): the blocks
+// that deliver the halo evaluate the boundary entries from the kernel's INPUTS while other blocks are already
+// writing its outputs, so no array may be both.
 template <bool LAST>
 __global__ void __launch_bounds__(kBlock)
-cheb_xr_first_peer_kernel(int64_t n, double *__restrict__ x, double *__restrict__ r, const double *__restrict__ p,
-                          const double *__restrict__ ap, const double *__restrict__ dinv, double inv_theta,
-                          double *__restrict__ w, double *z_out, CgGate g, CgRec *H, double *S, int *I, double *partials,
-                          int *counter, PeerRed pr, unsigned long long seq_in, unsigned long long seq_out, PeerPush push) {
+cheb_xr_first_peer_kernel(int64_t n, double *__restrict__ x, const double *__restrict__ r_in, double *__restrict__ r_out,
+                          const double *__restrict__ p, const double *__restrict__ ap, const double *__restrict__ dinv,
+                          double inv_theta, double *__restrict__ w, double *z_out, CgGate g, CgRec *H, double *S, int *I,
+                          double *partials, int *counter, PeerRed pr, unsigned long long seq_in, unsigned long long seq_out,
+                          PeerPush push) {
     if (cg_done(g)) return;
     __shared__ double sh[2];
     if (threadIdx.x < 32) {
@@ -330,26 +341,26 @@ cheb_xr_first_peer_kernel(int64_t n, double *__restrict__ x, double *__restrict_
         return;
     }
     const double alpha = H[g.it].rz / pap;
-    if (!LAST) peer_push_phase(push, [&](int32_t i) { return dinv[i] * fma(-alpha, ap[i], r[i]) * inv_theta; });
+    if (!LAST) peer_push_phase(push, [&](int32_t i) { return dinv[i] * fma(-alpha, ap[i], r_in[i]) * inv_theta; });
     double acc[2] = {0.0, 0.0};
     const int64_t n2 = n >> 1, stride = (int64_t)gridDim.x * kBlock;
     for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n2; i += stride) {
         double2 pv = ld_stream_f64x2(p + 2 * i), av = ld_stream_f64x2(ap + 2 * i), dv = ld_stream_f64x2(dinv + 2 * i);
         double2 xv = *reinterpret_cast<const double2 *>(x + 2 * i);
-        double2 rv = *reinterpret_cast<const double2 *>(r + 2 * i);
+        double2 rv = ld_stream_f64x2(r_in + 2 * i);
         xv.x = fma(alpha, pv.x, xv.x); xv.y = fma(alpha, pv.y, xv.y);
         rv.x = fma(-alpha, av.x, rv.x); rv.y = fma(-alpha, av.y, rv.y);
         const double2 wv = make_double2(dv.x * rv.x * inv_theta, dv.y * rv.y * inv_theta);
         *reinterpret_cast<double2 *>(x + 2 * i) = xv;
-        *reinterpret_cast<double2 *>(r + 2 * i) = rv;
+        *reinterpret_cast<double2 *>(r_out + 2 * i) = rv;
         *reinterpret_cast<double2 *>(z_out + 2 * i) = wv;
         if (!LAST) *reinterpret_cast<double2 *>(w + 2 * i) = wv;
         if (LAST) { acc[0] += rv.x * wv.x + rv.y * wv.y; acc[1] += rv.x * rv.x + rv.y * rv.y; }
     }
     if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
         const int64_t i = n - 1;
-        const double xv = fma(alpha, p[i], x[i]), rv = fma(-alpha, ap[i], r[i]), wv = dinv[i] * rv * inv_theta;
-        x[i] = xv; r[i] = rv; z_out[i] = wv;
+        const double xv = fma(alpha, p[i], x[i]), rv = fma(-alpha, ap[i], r_in[i]), wv = dinv[i] * rv * inv_theta;
+        x[i] = xv; r_out[i] = rv; z_out[i] = wv;
         if (!LAST) w[i] = wv;
         if (LAST) { acc[0] += rv * wv; acc[1] += rv * rv; }
     }
@@ -367,26 +378,27 @@ cheb_xr_first_peer_kernel(int64_t n, double *__restrict__ x, double *__restrict_
 template <bool LAST>
 __global__ void __launch_bounds__(kBlock)
 cheb_step_peer_kernel(int64_t n, const double *__restrict__ dinv, const double *__restrict__ r, const double *__restrict__ az,
-                      double c1, double c2, double *__restrict__ w, const double *z_in, double *z_out, CgGate g, double *S,
-                      double *partials, int *counter, PeerRed pr, unsigned long long seq_out, PeerPush push) {
+                      double c1, double c2, const double *__restrict__ w_in, double *__restrict__ w_out, const double *z_in,
+                      double *z_out, CgGate g, double *S, double *partials, int *counter, PeerRed pr, unsigned long long seq_out,
+                      PeerPush push) {
     if (cg_done(g)) return;
-    if (!LAST) peer_push_phase(push, [&](int32_t i) { return z_in[i] + (c1 * w[i] + c2 * (dinv[i] * (r[i] - az[i]))); });
+    if (!LAST) peer_push_phase(push, [&](int32_t i) { return z_in[i] + (c1 * w_in[i] + c2 * (dinv[i] * (r[i] - az[i]))); });
     double acc[2] = {0.0, 0.0};
     const int64_t n2 = n >> 1, stride = (int64_t)gridDim.x * kBlock;
     for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n2; i += stride) {
         const double2 dv = ld_stream_f64x2(dinv + 2 * i), rv = ld_stream_f64x2(r + 2 * i), tv = ld_stream_f64x2(az + 2 * i);
-        double2 wv = *reinterpret_cast<const double2 *>(w + 2 * i);
+        double2 wv = ld_stream_f64x2(w_in + 2 * i);
         double2 zv = *reinterpret_cast<const double2 *>(z_in + 2 * i);
         wv.x = c1 * wv.x + c2 * (dv.x * (rv.x - tv.x)); wv.y = c1 * wv.y + c2 * (dv.y * (rv.y - tv.y));
         zv.x += wv.x; zv.y += wv.y;
-        if (!LAST) *reinterpret_cast<double2 *>(w + 2 * i) = wv;
+        if (!LAST) *reinterpret_cast<double2 *>(w_out + 2 * i) = wv;
         *reinterpret_cast<double2 *>(z_out + 2 * i) = zv;
         if (LAST) { acc[0] += rv.x * zv.x + rv.y * zv.y; acc[1] += rv.x * rv.x + rv.y * rv.y; }
     }
     if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
         const int64_t i = n - 1;
-        const double wv = c1 * w[i] + c2 * (dinv[i] * (r[i] - az[i])), zv = z_in[i] + wv;
-        if (!LAST) w[i] = wv;
+        const double wv = c1 * w_in[i] + c2 * (dinv[i] * (r[i] - az[i])), zv = z_in[i] + wv;
+        if (!LAST) w_out[i] = wv;
         z_out[i] = zv;
         if (LAST) { acc[0] += r[i] * zv; acc[1] += r[i] * r[i]; }
     }
@@ -397,22 +409,22 @@ cheb_step_peer_kernel(int64_t n, const double *__restrict__ dinv, const double *
     }
 }
 
-int launch_cheb_xr_first_peer(bool last, int64_t n, double *x, double *r, const double *p, const double *ap, const double *dinv,
-                              double inv_theta, double *w, double *z_out, CgGate gate, CgRec *H, double *S, int *I, double *partials,
-                              int *counter, PeerRed pr, unsigned long long seq_in, unsigned long long seq_out, PeerPush push,
-                              int grid, cudaStream_t st) {
+int launch_cheb_xr_first_peer(bool last, int64_t n, double *x, const double *r_in, double *r_out, const double *p, const double *ap,
+                              const double *dinv, double inv_theta, double *w, double *z_out, CgGate gate, CgRec *H, double *S, int *I,
+                              double *partials, int *counter, PeerRed pr, unsigned long long seq_in, unsigned long long seq_out,
+                              PeerPush push, int grid, cudaStream_t st) {
     if (push.n_blocks > grid) push.n_blocks = grid;
-    if (last) cheb_xr_first_peer_kernel<true><<<grid, kBlock, 0, st>>>(n, x, r, p, ap, dinv, inv_theta, w, z_out, gate, H, S, I, partials, counter, pr, seq_in, seq_out, push);
-    else cheb_xr_first_peer_kernel<false><<<grid, kBlock, 0, st>>>(n, x, r, p, ap, dinv, inv_theta, w, z_out, gate, H, S, I, partials, counter, pr, seq_in, seq_out, push);
+    if (last) cheb_xr_first_peer_kernel<true><<<grid, kBlock, 0, st>>>(n, x, r_in, r_out, p, ap, dinv, inv_theta, w, z_out, gate, H, S, I, partials, counter, pr, seq_in, seq_out, push);
+    else cheb_xr_first_peer_kernel<false><<<grid, kBlock, 0, st>>>(n, x, r_in, r_out, p, ap, dinv, inv_theta, w, z_out, gate, H, S, I, partials, counter, pr, seq_in, seq_out, push);
     HEAT_LAUNCHED();
     return 0;
 }
-int launch_cheb_step_peer(bool last, int64_t n, const double *dinv, const double *r, const double *az, double c1, double c2, double *w,
-                          const double *z_in, double *z_out, CgGate gate, double *S, double *partials, int *counter, PeerRed pr,
-                          unsigned long long seq_out, PeerPush push, int grid, cudaStream_t st) {
+int launch_cheb_step_peer(bool last, int64_t n, const double *dinv, const double *r, const double *az, double c1, double c2,
+                          const double *w_in, double *w_out, const double *z_in, double *z_out, CgGate gate, double *S, double *partials,
+                          int *counter, PeerRed pr, unsigned long long seq_out, PeerPush push, int grid, cudaStream_t st) {
     if (push.n_blocks > grid) push.n_blocks = grid;
-    if (last) cheb_step_peer_kernel<true><<<grid, kBlock, 0, st>>>(n, dinv, r, az, c1, c2, w, z_in, z_out, gate, S, partials, counter, pr, seq_out, push);
-    else cheb_step_peer_kernel<false><<<grid, kBlock, 0, st>>>(n, dinv, r, az, c1, c2, w, z_in, z_out, gate, S, partials, counter, pr, seq_out, push);
+    if (last) cheb_step_peer_kernel<true><<<grid, kBlock, 0, st>>>(n, dinv, r, az, c1, c2, w_in, w_out, z_in, z_out, gate, S, partials, counter, pr, seq_out, push);
+    else cheb_step_peer_kernel<false><<<grid, kBlock, 0, st>>>(n, dinv, r, az, c1, c2, w_in, w_out, z_in, z_out, gate, S, partials, counter, pr, seq_out, push);
     HEAT_LAUNCHED();
     return 0;
 }
@@ -428,7 +440,7 @@ int launch_cg_update_p_peer(int64_t n, double *p_out, const double *p_in, const 
                             CgGate gate, CgRec *H, int *I, PeerRed pr, unsigned long long seq_in, PeerPush push,
                             int grid, cudaStream_t st) {
     if (push.n_blocks > grid) push.n_blocks = grid;
-    cg_update_p_peer_kernel<<<grid, kBlock, 0, st>>>(n, p_out, p_in, r, dinv, z, gate, H, I, pr, seq_in, push);
+    HEAT_CUDA(launch_kernel(cg_update_p_peer_kernel, grid, kBlock, 0, st, gate.pdl != 0, n, p_out, p_in, r, dinv, z, gate, H, I, pr, seq_in, push));
     HEAT_LAUNCHED();
     return 0;
 }

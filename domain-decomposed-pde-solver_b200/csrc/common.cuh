@@ -168,7 +168,7 @@ struct heat_matrix {
     heat::DevBuf<int64_t> d_owned_gids;  // only when !owned_contiguous
     HaloPlan halo;
     // solver workspace (lazily allocated)
-    heat::DevBuf<double> w_r, w_p, w_p2, w_ap, w_s, w_u, w_u2, w_t, w_w;
+    heat::DevBuf<double> w_r, w_r2, w_p, w_p2, w_ap, w_s, w_u, w_u2, w_t, w_w, w_w2;
     heat::DevBuf<double> h_x, h_b;       // staging of heat_solve_host (x with ghosts, b)
     PeerMatrixState *peer = nullptr;     // non-null once the peer-memory halo path is set up
     heat::IluState *ilu = nullptr;       // non-null once HEAT_PREC_ILU0 has been set up

@@ -1,5 +1,7 @@
 // device_utils.cuh — load/store and reduction helpers shared by the sm_100a kernels.
 #pragma once
+#include <utility>
+
 #include "common.cuh"
 
 namespace heat {
@@ -37,6 +39,26 @@ __device__ __forceinline__ int32_t ld_stream_s32(const int32_t *p) {
 // streaming store (written once, read by a later kernel)
 __device__ __forceinline__ void st_stream_f64x2(double *p, double2 v) {
     asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
+}
+
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------------
+// The kernels of the CG loop are launched with cudaLaunchAttributeProgrammaticStreamSerialization: a kernel's CTAs
+// may become resident while its predecessor in the stream drains (after every predecessor CTA has executed
+// pdl_launch_dependents or exited) and run their prologue — launch latency, barrier set-up, and for the SpMV the
+// first TMA loads of the (constant) matrix stream — before pdl_wait() blocks until the predecessor grid has
+// completed and its writes are visible.  Both are no-ops for a kernel launched the ordinary way.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kern)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, bool pdl, Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
 }
 
 // ---- reductions ----------------------------------------------------------------------------------

@@ -22,6 +22,7 @@ struct CgGate {               // stopping test evaluated by every block of every
     // vectors is comparable to the L2 (strong scaling: 134 MB per vector on 8 GPUs), not at 1 GB per vector.
     //   1: even iteration (SpMV forward, update_xr backward, update_p forward)   2: odd iteration (the mirror image)
     int dir;
+    int pdl;                  // host side: launch with programmatic stream serialization (device_utils.cuh)
 };
 __host__ __device__ inline bool spmv_backward(const CgGate &g) { return g.dir == 2; }
 __host__ __device__ inline bool xr_backward(const CgGate &g) { return g.dir == 1; }
@@ -83,13 +84,13 @@ int launch_cg_update_p_peer(int64_t n, double *p_out, const double *p_in, const 
                             CgGate gate, CgRec *H, int *I, PeerRed pr, unsigned long long seq_in, PeerPush push,
                             int grid, cudaStream_t st);
 // Chebyshev-PCG on the peer-memory path (cg.cu): `last` = this launch carries the r.z / r.r reduction
-int launch_cheb_xr_first_peer(bool last, int64_t n, double *x, double *r, const double *p, const double *ap, const double *dinv,
-                              double inv_theta, double *w, double *z_out, CgGate gate, CgRec *H, double *S, int *I, double *partials,
-                              int *counter, PeerRed pr, unsigned long long seq_in, unsigned long long seq_out, PeerPush push,
-                              int grid, cudaStream_t st);
-int launch_cheb_step_peer(bool last, int64_t n, const double *dinv, const double *r, const double *az, double c1, double c2, double *w,
-                          const double *z_in, double *z_out, CgGate gate, double *S, double *partials, int *counter, PeerRed pr,
-                          unsigned long long seq_out, PeerPush push, int grid, cudaStream_t st);
+int launch_cheb_xr_first_peer(bool last, int64_t n, double *x, const double *r_in, double *r_out, const double *p, const double *ap,
+                              const double *dinv, double inv_theta, double *w, double *z_out, CgGate gate, CgRec *H, double *S, int *I,
+                              double *partials, int *counter, PeerRed pr, unsigned long long seq_in, unsigned long long seq_out,
+                              PeerPush push, int grid, cudaStream_t st);
+int launch_cheb_step_peer(bool last, int64_t n, const double *dinv, const double *r, const double *az, double c1, double c2,
+                          const double *w_in, double *w_out, const double *z_in, double *z_out, CgGate gate, double *S, double *partials,
+                          int *counter, PeerRed pr, unsigned long long seq_out, PeerPush push, int grid, cudaStream_t st);
 int launch_halo_push(const double *x, PeerPush push, cudaStream_t st);
 int launch_cg_fused_update(int64_t n, double *x, double *r, double *p, double *s, double *u,
                            const double *w, const double *dinv, CgGate gate, CgRec *H, int *I,

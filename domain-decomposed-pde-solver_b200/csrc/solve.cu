@@ -253,6 +253,10 @@ int solve_device(heat_ctx *ctx, heat_matrix *A, double *x, const double *b, cons
         if (want && (ctx->nranks == 1 || ctx->peer_enabled)) {
             HEAT_TRY(peer_matrix_setup(ctx, A, true));
             cheb_fused = A->peer != nullptr && A->peer->has_z;
+            if (cheb_fused) {
+                if (!A->w_r2.p) HEAT_TRY(A->w_r2.alloc((size_t)A->n_owned));
+                if (!A->w_w2.p) HEAT_TRY(A->w_w2.alloc((size_t)A->n_owned));
+            }
         }
     }
     const int64_t n = A->n_owned;
@@ -337,13 +341,17 @@ int solve_device(heat_ctx *ctx, heat_matrix *A, double *x, const double *b, cons
     // consecutive kernels sweep the vectors in opposite directions (kernels.cuh: CgGate::dir); HEAT_CG_ALTERNATE=0: all forward
     const char *alt_env = getenv("HEAT_CG_ALTERNATE");
     const bool alternate = !(alt_env && atoi(alt_env) == 0) && !single && !cheb;
+    // programmatic dependent launch of the loop's kernels (device_utils.cuh); HEAT_PDL=0: ordinary launches.  Only where
+    // the loop is kernels of this library back to back (one GPU, or the peer-memory path): no NCCL launch in between.
+    const char *pdl_env = getenv("HEAT_PDL");
+    const bool pdl = !(pdl_env && atoi(pdl_env) == 0) && !single && !cheb && (ctx->nranks == 1 || peer);
     const int check = o.check_every > 0 ? o.check_every : 32;
     int launched = 0, h_iters = 0, h_status = 0;
     while (launched < o.max_iters) {
         const int batch = (o.max_iters - launched) < check ? (o.max_iters - launched) : check;
         for (int q = 0; q < batch; ++q) {
             const int it = launched + q;
-            CgGate gate{H, S, I, it, alternate ? 1 + (it & 1) : 0};
+            CgGate gate{H, S, I, it, alternate ? 1 + (it & 1) : 0, pdl ? 1 : 0};
             if (single) {
                 double *u = A->w_u.p, *s = A->w_s.p, *w = ap;
                 HEAT_TRY(launch_cg_fused_update(n, x, r, p, s, u, w, dinv, gate, H, I, A->partials.p, I + I_COUNTER2, vgrid, st));
@@ -373,7 +381,10 @@ int solve_device(heat_ctx *ctx, heat_matrix *A, double *x, const double *b, cons
                 const double c_alpha = lmax / ratio, c_beta = 1.1 * lmax;
                 const double delta = 2.0 / (c_beta - c_alpha), theta = 0.5 * (c_beta + c_alpha), s1c = theta * delta;
                 double *pbuf[2] = {A->w_p.p, A->w_p2.p}, *zbuf[2] = {A->w_u.p, A->w_u2.p};
+                double *rbuf[2] = {A->w_r.p, A->w_r2.p}, *wbuf[2] = {A->w_w.p, A->w_w2.p};     // out-of-place r and W (cg.cu)
                 double *pin = pbuf[it & 1], *pout = pbuf[(it + 1) & 1];
+                const double *r_in = rbuf[it & 1];
+                double *r_new = rbuf[(it + 1) & 1];
                 const unsigned long long s1 = ctx->peer_red_seq + 2ull * (unsigned)it + 1, s2 = s1 + 1;
                 const unsigned long long e0 = ctx->peer_halo_epoch + 1 + (unsigned long long)it * (unsigned)k;   // epoch of this iteration's first SpMV
                 const PeerRed pr = peer_red_of(ctx);
@@ -385,7 +396,7 @@ int solve_device(heat_ctx *ctx, heat_matrix *A, double *x, const double *b, cons
                 HEAT_TRY(launch_spmv_peer(A, pin, ap, gate, d, sp, g, st));
                 PeerPush pz = A->peer->push[2];
                 pz.epoch = e0 + 1;
-                HEAT_TRY(launch_cheb_xr_first_peer(k == 1, n, x, r, pin, ap, A->dinv.p, 1.0 / theta, A->w_w.p, zbuf[0], gate, H, S, I,
+                HEAT_TRY(launch_cheb_xr_first_peer(k == 1, n, x, r_in, r_new, pin, ap, A->dinv.p, 1.0 / theta, wbuf[0], zbuf[0], gate, H, S, I,
                                                    A->partials.p, I + I_COUNTER2, pr, s1, s2, pz, vgrid, st));
                 double rho = 1.0 / s1c;
                 for (int j = 1; j < k; ++j) {
@@ -396,13 +407,14 @@ int solve_device(heat_ctx *ctx, heat_matrix *A, double *x, const double *b, cons
                     HEAT_TRY(launch_spmv_peer(A, zin, A->w_t.p, gate, nod, sp, g, st));
                     PeerPush pj = A->peer->push[2 + (j & 1)];
                     pj.epoch = e0 + (unsigned)j + 1;
-                    HEAT_TRY(launch_cheb_step_peer(j == k - 1, n, A->dinv.p, r, A->w_t.p, rho_new * rho, 2.0 * rho_new * delta, A->w_w.p,
-                                                   zin, zout, gate, S, A->partials.p, I + I_COUNTER2, pr, s2, pj, vgrid, st));
+                    HEAT_TRY(launch_cheb_step_peer(j == k - 1, n, A->dinv.p, r_new, A->w_t.p, rho_new * rho, 2.0 * rho_new * delta,
+                                                   wbuf[(j - 1) & 1], wbuf[j & 1], zin, zout, gate, S, A->partials.p, I + I_COUNTER2, pr, s2, pj,
+                                                   vgrid, st));
                     rho = rho_new;
                 }
                 PeerPush pp = A->peer->push[(it + 1) & 1];
                 pp.epoch = e0 + (unsigned)k;
-                HEAT_TRY(launch_cg_update_p_peer(n, pout, pin, r, A->dinv.p, zbuf[(k - 1) & 1], gate, H, I, pr, s2, pp, vgrid, st));
+                HEAT_TRY(launch_cg_update_p_peer(n, pout, pin, r_new, A->dinv.p, zbuf[(k - 1) & 1], gate, H, I, pr, s2, pp, vgrid, st));
             } else if (!cheb) {
                 HEAT_TRY(spmv_halo(ctx, A, p, ap, gate, S + S_PAP0));
                 HEAT_TRY(comm_allreduce_sum(ctx, S + S_PAP0, 1));

@@ -142,7 +142,9 @@ __global__ void __launch_bounds__(NWARPS * 32, MINB)
 sell_spmv_tma_kernel(const SliceMeta *__restrict__ meta, const int32_t *__restrict__ col,
                      const double *__restrict__ val, const double *__restrict__ x, double *__restrict__ y,
                      int64_t n_rows, int64_t n_list, CgGate gate, DotOut dot, SpmvPeer peer, SellDict dict) {
-    if (gate_done(gate)) return;
+    // Everything up to pdl_wait() touches only the matrix (constant during a solve) and kernel parameters, so under
+    // programmatic dependent launch it overlaps the tail of the kernel that produces x: barriers are set up and the
+    // first NSTAGE chunks of every warp are already in flight when the input vector becomes valid.
     if (PEER && threadIdx.x == 0) HEAT_TRACE_MIN(gate.it, 0, 0);
     using L = TmaSmem<KC, NSTAGE, CB>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -213,9 +215,16 @@ sell_spmv_tma_kernel(const SliceMeta *__restrict__ meta, const int32_t *__restri
             mi_next2 = load_meta(ti + 2 * W);
         }
     };
+    int n_issued = 0;
 #pragma unroll
     for (int s = 0; s < NSTAGE; ++s)
-        if (ti < n_list) issue(s);
+        if (ti < n_list) { issue(s); ++n_issued; }
+
+    pdl_wait();                                                      // the producer of x (and of the gate's records) is complete
+    if (gate_done(gate)) {                                           // frozen solve: drain the loads in flight, then leave
+        for (int s = 0; s < n_issued; ++s) mbar_wait(bars + s, 0);
+        return;
+    }
 
     // consume cursor
     int64_t tc = first;
@@ -303,6 +312,7 @@ sell_spmv_tma_kernel(const SliceMeta *__restrict__ meta, const int32_t *__restri
         }
         if (++stage == NSTAGE) { stage = 0; parity ^= 1u; }
     }
+    pdl_launch_dependents();                                         // the next kernel's CTAs may move in as this grid drains
     if (DOT == 2) {
         double acc[2] = {dsum, ysum};
         double *const out[2] = {dot.out, dot.out + 1};
@@ -388,8 +398,9 @@ static int launch_tma(const heat_matrix *A, const double *x, double *y, int64_t 
         HEAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         if (dev >= 0 && dev < kMaxDevices) configured[dev] = true;
     }
-    kern<<<grid, NWARPS * 32, smem, st>>>(A->slice_meta.p + first, A->sell_col.p, A->sell_val.p, x, y, A->n_owned,
-                                         n_list, gate, dot, SpmvPeer(), dict_of(A));
+    HEAT_CUDA(launch_kernel(kern, grid, NWARPS * 32, smem, st, gate.pdl != 0, (const SliceMeta *)(A->slice_meta.p + first),
+                            (const int32_t *)A->sell_col.p, (const double *)A->sell_val.p, x, y, A->n_owned, n_list, gate, dot,
+                            SpmvPeer(), dict_of(A)));
     HEAT_LAUNCHED();
     return 0;
 }
@@ -412,8 +423,9 @@ static int launch_spmv_peer_t(const heat_matrix *A, const double *x, double *y, 
     }
     const int64_t n_list = A->n_slices;                   // slice_meta order: interior slices, then boundary slices
     if (A->n_ghost == 0) peer.n_interior = n_list;
-    kern<<<grid, NW * 32, smem, st>>>(A->slice_meta.p, A->sell_col.p, A->sell_val.p, x, y, A->n_owned, n_list, gate, dot,
-                                     peer, dict_of(A));
+    HEAT_CUDA(launch_kernel(kern, grid, NW * 32, smem, st, gate.pdl != 0, (const SliceMeta *)A->slice_meta.p,
+                            (const int32_t *)A->sell_col.p, (const double *)A->sell_val.p, x, y, A->n_owned, n_list, gate, dot, peer,
+                            dict_of(A)));
     HEAT_LAUNCHED();
     return 0;
 }
