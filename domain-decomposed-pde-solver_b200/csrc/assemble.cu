@@ -148,7 +148,7 @@ pattern_fill_kernel(int64_t n, const int64_t *__restrict__ red2orig, const int32
 // read-modify-wrote them in global memory for each of the ~96 element contributions of a row, 16x the output in DRAM
 // writes (ncu: 32 GB written for a 2 GB matrix at 256^3).  Node coordinates come as one 32-byte (x, y, z, 0) record
 // per node — one sector per gathered node instead of three — and a tet's four node ids as one 16-byte load.
-constexpr int kAccCap = 32;            // row entries held in shared memory; longer rows accumulate in global memory
+constexpr int kAccCap = 24;            // row entries (values AND column ids) held in shared memory; longer rows work in global memory
 constexpr int kValThreads = 128;
 // NPE: nodes per element known at compile time for the P1 operator (4: tets, 3: triangles) so that the element
 // arrays stay in registers; 0: graph Laplacian (any clique size)
@@ -162,6 +162,7 @@ values_kernel(int64_t n_owned, const int32_t *__restrict__ owned, const int32_t 
               const int64_t *__restrict__ lrow_ptr, int32_t *__restrict__ lcol, double *__restrict__ lval,
               double *__restrict__ b, int mode, int *overflow) {
     __shared__ double acc_s[kAccCap][kValThreads];
+    __shared__ int32_t col_s[kAccCap][kValThreads];        // the row's pattern: every element contribution is binary-searched in it
     const int tid = threadIdx.x;
     const int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= n_owned) return;
@@ -172,10 +173,12 @@ values_kernel(int64_t n_owned, const int32_t *__restrict__ owned, const int32_t 
     int32_t *lc = lcol ? lcol + lrow_ptr[l] : nullptr;
     double *lv = lval + lrow_ptr[l];
     int dpos = 0;
+    const bool in_smem = NPE != 0 && len <= kAccCap;
     for (int t = 0; t < len; ++t) {
         const int32_t c = gc[t];
         if (c == gi) dpos = t;
         if (lc) lc[t] = g2l ? g2l[c] : c;
+        if (in_smem) { col_s[t][tid] = c; acc_s[t][tid] = 0.0; }
     }
     double bsum = 0.0;
     if constexpr (NPE == 0) {
@@ -186,9 +189,7 @@ values_kernel(int64_t n_owned, const int32_t *__restrict__ owned, const int32_t 
         for (int t = 0; t < len; ++t) lv[t] = -1.0;                // :601
         lv[dpos] = (double)u;                                      // :606 full degree
     } else {
-        const bool in_smem = len <= kAccCap;
-        if (in_smem) { for (int t = 0; t < len; ++t) acc_s[t][tid] = 0.0; }
-        else { for (int t = 0; t < len; ++t) lv[t] = 0.0; }
+        if (!in_smem) { for (int t = 0; t < len; ++t) lv[t] = 0.0; }
         for (int64_t q = n2e_ptr[g]; q < n2e_ptr[g + 1]; ++q) {
             constexpr int kN = NPE == 3 ? 3 : 4;
             const int32_t *e = conn + (int64_t)n2e[q] * kN;
@@ -224,7 +225,8 @@ values_kernel(int64_t n_owned, const int32_t *__restrict__ owned, const int32_t 
                 } else if (rv[k] >= 0) {
                     const int32_t r = rv[k];
                     int lo = 0, hi = len - 1;
-                    while (lo < hi) { int mid = (lo + hi) >> 1; if (gc[mid] < r) lo = mid + 1; else hi = mid; }
+                    if (in_smem) { while (lo < hi) { int mid = (lo + hi) >> 1; if (col_s[mid][tid] < r) lo = mid + 1; else hi = mid; } }
+                    else { while (lo < hi) { int mid = (lo + hi) >> 1; if (gc[mid] < r) lo = mid + 1; else hi = mid; } }
                     slot = lo;
                 } else {
                     const double t2 = kab * bc[j];
@@ -772,7 +774,7 @@ __global__ void __launch_bounds__(kCubeWarps * 32, 2) cube_sell_kernel(CubeSellA
                 const int2 cc = *reinterpret_cast<const int2 *>(tc + k * kSellChunk + 2 * lane);
                 const int off[2] = {cc.x - row0, cc.y - (row0 + 1)};
                 int id[2];
-                ok = sell_dict_step(tab, T, off, id, k);
+                ok = sell_dict_step(tab, T, off, id);
                 if (ok) *reinterpret_cast<uchar2 *>(ti + k * kSellChunk + 2 * lane) = make_uchar2((unsigned char)id[0], (unsigned char)id[1]);
             }
             if (!ok) T = kSellDictCap + 1;

@@ -103,7 +103,7 @@ sell_classify_kernel(const int64_t *__restrict__ slice_ptr, const int32_t *__res
         const int off[2] = {c.x - row0, c.y - (row0 + 1)};
         i16_ok = i16_ok && fits_i16(off[0]) && fits_i16(off[1]);
         int id[2];
-        if (table_ok) table_ok = sell_dict_step(tab, T, off, id, k);
+        if (table_ok) table_ok = sell_dict_step(tab, T, off, id);
     }
     i16_ok = __all_sync(0xffffffffu, i16_ok);
     const int m = (table_ok && !(force16 && i16_ok)) ? kColModeU8 : i16_ok ? kColModeI16 : kColModeI32;
@@ -135,7 +135,7 @@ sell_compact_kernel(const int64_t *__restrict__ slice_ptr, const int32_t *__rest
         const int off[2] = {c.x - row0, c.y - (row0 + 1)};
         if (m == kColModeU8) {
             int id[2];
-            sell_dict_step(tab, T, off, id, k);
+            sell_dict_step(tab, T, off, id);
             *reinterpret_cast<uchar2 *>(out + (int64_t)k * kSellChunk + 2 * lane) = make_uchar2((unsigned char)id[0], (unsigned char)id[1]);
         } else {
             *reinterpret_cast<short2 *>(out + 2 * ((int64_t)k * kSellChunk + 2 * lane)) = make_short2((short)off[0], (short)off[1]);

@@ -17,7 +17,8 @@ from dataclasses import dataclass
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libheat_b200.so")
+# HEAT_B200_LIB: another build of the same library (tools/peer_trace.py uses the -DHEAT_PEER_TRACE build in lib_trace/)
+LIB_PATH = os.environ.get("HEAT_B200_LIB") or os.path.join(os.path.dirname(_HERE), "lib", "libheat_b200.so")
 
 OP_GRAPH_LAPLACIAN, OP_P1_FEM = 0, 1
 SOLVER_CG, SOLVER_CG_SINGLE_REDUCE, SOLVER_GMRES = 0, 1, 2

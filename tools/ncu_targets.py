@@ -14,6 +14,16 @@ import heat_b200 as hb
 what = sys.argv[1]
 nx = int(sys.argv[2]) if len(sys.argv) > 2 else 256
 iters = int(sys.argv[3]) if len(sys.argv) > 3 else 6
+if what == "assemble2":          # steady-state assembly: the same cube four times (byte-indexed x2, int32 x2)
+    for cidx in ("1", "1", "0", "0"):
+        os.environ["HEAT_SPMV_CIDX"] = cidx
+        io = hb.IO(0)
+        io.mesh_cube(nx, nx, nx, False)
+        A, X, B = io.assemble(hb.OP_P1_FEM)
+        mi = A.info
+        print("assemble", nx, "col_index_bytes", mi.col_index_bytes, "assemble_ms", round(mi.assemble_ms, 2), "fill_ms", round(mi.assemble_fill_ms, 2), flush=True)
+        io.close()
+    sys.exit(0)
 io = hb.IO(0)
 io.mesh_cube(nx, nx, nx, what == "explicit")
 A, X, B = io.assemble(hb.OP_P1_FEM)

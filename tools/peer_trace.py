@@ -30,6 +30,20 @@ def analyse(prefix, n):
         print("".join(out))
 
 
+def nvlink_kib(gpu):
+    """(tx KiB, rx KiB) summed over the links of `gpu` from the driver's NVLink data counters (`nvidia-smi nvlink -gt d`);
+    None where the counters are not available."""
+    import re
+    import subprocess
+    try:
+        out = subprocess.run(["nvidia-smi", "nvlink", "-gt", "d", "-i", str(gpu)], capture_output=True, text=True, timeout=20).stdout
+    except (OSError, subprocess.TimeoutExpired):
+        return None
+    tx = [int(v) for v in re.findall(r"Data Tx:\s*(\d+)\s*KiB", out)]
+    rx = [int(v) for v in re.findall(r"Data Rx:\s*(\d+)\s*KiB", out)]
+    return (sum(tx), sum(rx)) if tx and rx else None
+
+
 def main():
     if len(sys.argv) > 1 and sys.argv[1] == "--analyse":
         return analyse(sys.argv[2], int(sys.argv[3]))
@@ -48,13 +62,23 @@ def main():
     nx = int(os.environ.get("NX", "512"))
     io.mesh_cube(nx, nx, nx, False)
     A, X, B = io.assemble(hb.OP_P1_FEM, hb.PART_SLAB)
-    for _ in range(2):
-        X.fill(0.0)
-        r = io.cg_iterations(A, X, B, 300, check_every=300)
+    X.fill(0.0)
+    r = io.cg_iterations(A, X, B, 300, check_every=300)           # warm-up + peer set-up
     torch.cuda.synchronize()
     dist.barrier()
-    if rank == 0:
-        print("peer path:", A.info.peer_path, "ms per iteration:", r.solve_ms / 300)
+    c0 = nvlink_kib(local)
+    X.fill(0.0)
+    r = io.cg_iterations(A, X, B, 300, check_every=300)
+    torch.cuda.synchronize()
+    dist.barrier()
+    c1 = nvlink_kib(local)
+    mi = A.info
+    halo = 8 * mi.n_ghost                                          # bytes this rank RECEIVES per SpMV = its ghost entries
+    nv = None
+    if c0 and c1:
+        nv = {"tx_bytes_per_iteration": (c1[0] - c0[0]) * 1024 / 300, "rx_bytes_per_iteration": (c1[1] - c0[1]) * 1024 / 300}
+    print(f"rank {rank}: peer path {mi.peer_path}, {r.solve_ms / 300 * 1e3:.1f} us per iteration, ghosts {mi.n_ghost} "
+          f"(algorithmic halo in: {halo} B per iteration + {world} x 32 B of reduction stamps x 2), NVLink counters: {nv}", flush=True)
     io.close()
     dist.destroy_process_group()
 
