@@ -106,9 +106,12 @@ def check_system(io, A, X, B, ref, part, rank, world, tag, log):
     xg, itg, _, convg = O.gmres(ref, prec=O.PREC_JACOBI, restart=20, max_iters=5000, tol=1e-10)
     assert res.converged and convg and abs(res.iters - itg) <= max(2, itg // 100), (tag, res, itg)
     assert np.abs(X.numpy() - xg[owned]).max() <= 1e-8 * np.abs(xg).max(), tag
+    # (restarted GMRES on the block-preconditioned operator: a relative residual of 1e-10 leaves the ERROR a kappa
+    # above it — at 4 ranks on bolted_bracket P1 just over the 1e-8 bar — so this check converges two decades further)
     X.fill(0.0)
-    res = io.solve(A, X, B, solver=hb.SOLVER_GMRES, prec=hb.PREC_ILU0, gmres_restart=50, max_iters=5000, tol=1e-10)
-    assert res.converged and np.abs(X.numpy() - x_ref[owned]).max() <= 1e-8 * np.abs(x_ref).max(), (tag, res)
+    res = io.solve(A, X, B, solver=hb.SOLVER_GMRES, prec=hb.PREC_ILU0, gmres_restart=50, max_iters=20000, tol=1e-12)
+    err_ilu = np.abs(X.numpy() - x_ref[owned]).max() / np.abs(x_ref).max()
+    assert res.converged and err_ilu <= 1e-8, (tag, res, err_ilu)
     log.append(f"{tag} gmres(20)+jacobi iters={itg}, gmres(50)+block-ilu0 iters={res.iters}")
     return x_ref
 
