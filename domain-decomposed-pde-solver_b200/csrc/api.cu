@@ -300,6 +300,12 @@ extern "C" int heat_close(heat_ctx *ctx) {
     comm_destroy(ctx);
     if (ctx->comm_stream) cudaStreamDestroy(ctx->comm_stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->copy_out_stream) cudaStreamDestroy(ctx->copy_out_stream);
+    for (int q = 0; q < 2; ++q) {
+        if (ctx->ev_in[q]) cudaEventDestroy(ctx->ev_in[q]);
+        if (ctx->ev_done[q]) cudaEventDestroy(ctx->ev_done[q]);
+        if (ctx->ev_out[q]) cudaEventDestroy(ctx->ev_out[q]);
+    }
     if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
@@ -529,6 +535,64 @@ extern "C" int heat_solve_host(heat_ctx *ctx, heat_matrix *A, const double *b_ho
     if (rc) return rc;
     HEAT_CUDA(cudaMemcpyAsync(x_host, A->h_x.p, nb, cudaMemcpyDeviceToHost, ctx->stream));
     HEAT_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// A sequence of solves with ONE matrix through host buffers (time stepping, many right-hand sides): the role of a
+// loop around belosSolver with a new B per pass.  Two staging sets and two copy streams: while system k is solved the
+// inputs of system k+1 go up and the solution of system k-1 goes down (PCIe is full duplex), so a stream of solves
+// runs at the device-resident rate instead of paying 24 n bytes of serial copies per system.
+extern "C" int heat_solve_host_batch(heat_ctx *ctx, heat_matrix *A, int count, const double *const *b_hosts,
+                                     const double *const *x0_hosts, double *const *x_hosts, const heat_solve_opts *opts,
+                                     heat_solve_info *infos) {
+    if (!ctx || !A || count < 0 || (count > 0 && (!b_hosts || !x_hosts)) || !opts) HEAT_FAIL(2, "heat_solve_host_batch: bad arguments");
+    HEAT_NEED_GPU(ctx, "heat_solve_host_batch");
+    HEAT_CUDA(cudaSetDevice(ctx->device));
+    for (int k = 0; k < count; ++k)
+        if (!b_hosts[k] || !x_hosts[k]) HEAT_FAIL(2, "heat_solve_host_batch: null buffer for system %d", k);
+    const size_t nv = (size_t)(A->n_owned + A->n_ghost), nb = sizeof(double) * (size_t)A->n_owned;
+    DevBuf<double> *hx[2] = {&A->h_x, &A->h_x2}, *hb[2] = {&A->h_b, &A->h_b2};
+    for (int q = 0; q < 2; ++q) {
+        if (!hx[q]->p) HEAT_TRY(hx[q]->alloc(nv));
+        if (!hb[q]->p) HEAT_TRY(hb[q]->alloc((size_t)A->n_owned));
+    }
+    if (!ctx->copy_stream) {
+        HEAT_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        HEAT_CUDA(cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming));
+    }
+    if (!ctx->copy_out_stream) {
+        HEAT_CUDA(cudaStreamCreateWithFlags(&ctx->copy_out_stream, cudaStreamNonBlocking));
+        for (int q = 0; q < 2; ++q) {
+            HEAT_CUDA(cudaEventCreateWithFlags(&ctx->ev_in[q], cudaEventDisableTiming));
+            HEAT_CUDA(cudaEventCreateWithFlags(&ctx->ev_done[q], cudaEventDisableTiming));
+            HEAT_CUDA(cudaEventCreateWithFlags(&ctx->ev_out[q], cudaEventDisableTiming));
+        }
+    }
+    // whatever used the staging buffers before (an earlier heat_solve_host on ctx->stream) must be done
+    HEAT_CUDA(cudaEventRecord(ctx->ev_copy, ctx->stream));
+    HEAT_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_copy, 0));
+    auto upload = [&](int k) -> int {                   // inputs of system k into staging set k & 1 (copy-in stream)
+        const int q = k & 1;
+        if (k >= 2) HEAT_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_out[q], 0));    // system k-2 has left the set
+        if (x0_hosts && x0_hosts[k]) HEAT_CUDA(cudaMemcpyAsync(hx[q]->p, x0_hosts[k], nb, cudaMemcpyHostToDevice, ctx->copy_stream));
+        else HEAT_CUDA(cudaMemsetAsync(hx[q]->p, 0, nb, ctx->copy_stream));
+        HEAT_CUDA(cudaMemcpyAsync(hb[q]->p, b_hosts[k], nb, cudaMemcpyHostToDevice, ctx->copy_stream));
+        HEAT_CUDA(cudaEventRecord(ctx->ev_in[q], ctx->copy_stream));
+        return 0;
+    };
+    if (count > 0) HEAT_TRY(upload(0));
+    for (int k = 0; k < count; ++k) {
+        const int q = k & 1;
+        if (k + 1 < count) HEAT_TRY(upload(k + 1));                        // goes up while system k is solved
+        HEAT_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_in[q], 0));
+        HEAT_TRY(solve_device(ctx, A, hx[q]->p, hb[q]->p, *opts, infos ? infos + k : nullptr));
+        HEAT_CUDA(cudaEventRecord(ctx->ev_done[q], ctx->stream));
+        HEAT_CUDA(cudaStreamWaitEvent(ctx->copy_out_stream, ctx->ev_done[q], 0));
+        HEAT_CUDA(cudaMemcpyAsync(x_hosts[k], hx[q]->p, nb, cudaMemcpyDeviceToHost, ctx->copy_out_stream));   // goes down while k+1 is solved
+        HEAT_CUDA(cudaEventRecord(ctx->ev_out[q], ctx->copy_out_stream));
+    }
+    HEAT_CUDA(cudaStreamSynchronize(ctx->copy_out_stream));
+    HEAT_CUDA(cudaStreamSynchronize(ctx->copy_stream));
     return 0;
 }
 

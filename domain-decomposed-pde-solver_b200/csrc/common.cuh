@@ -170,6 +170,7 @@ struct heat_matrix {
     // solver workspace (lazily allocated)
     heat::DevBuf<double> w_r, w_r2, w_p, w_p2, w_ap, w_s, w_u, w_u2, w_t, w_w, w_w2;
     heat::DevBuf<double> h_x, h_b;       // staging of heat_solve_host (x with ghosts, b)
+    heat::DevBuf<double> h_x2, h_b2;     // second staging set of heat_solve_host_batch (copies overlap the neighbouring solves)
     PeerMatrixState *peer = nullptr;     // non-null once the peer-memory halo path is set up
     heat::IluState *ilu = nullptr;       // non-null once HEAT_PREC_ILU0 has been set up
     heat::DevBuf<double> partials;       // [2 * kMaxPartials * 4]
@@ -203,6 +204,8 @@ struct heat_ctx {
     cudaStream_t comm_stream = nullptr;
     cudaStream_t copy_stream = nullptr;  // heat_solve_host: b goes up beside the set-up SpMV
     cudaEvent_t ev_copy = nullptr;
+    cudaStream_t copy_out_stream = nullptr;              // heat_solve_host_batch: results go down while the next system is solved
+    cudaEvent_t ev_in[2] = {}, ev_done[2] = {}, ev_out[2] = {};   // per staging set: inputs up, solve done, result down
     cudaEvent_t wait_before_rhs = nullptr;   // if set, solve_device waits for it before it first reads b
     cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_halo = nullptr, ev_pack = nullptr;
     int rank = 0, nranks = 1;

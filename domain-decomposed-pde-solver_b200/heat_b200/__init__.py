@@ -67,7 +67,7 @@ class PlanSizes(C.Structure):
 ABI_SYMBOLS = [
     "heat_last_error", "heat_version", "heat_device_count", "heat_kernel_launches", "heat_ctx_create", "heat_ctx_set_stream", "heat_ctx_set_output", "heat_open",
     "heat_create", "heat_close", "heat_mesh_set", "heat_mesh_cube", "heat_mesh_nodeset_ids", "heat_comm_unique_id", "heat_comm_init",
-    "heat_comm_rank", "heat_assemble", "heat_get_matrix", "heat_node_owners", "heat_matrix_owned_nodeset", "heat_power_method", "heat_solve_opts_default", "heat_solve", "heat_solve_trajectory", "heat_solve_host", "heat_spmv", "heat_spmv_peer",
+    "heat_comm_rank", "heat_assemble", "heat_get_matrix", "heat_node_owners", "heat_matrix_owned_nodeset", "heat_power_method", "heat_solve_opts_default", "heat_solve", "heat_solve_trajectory", "heat_solve_host", "heat_solve_host_batch", "heat_spmv", "heat_spmv_peer",
     "heat_cg_iterations", "heat_decompose", "heat_write_solution", "heat_write_nodal_field", "heat_nodal_field", "heat_scatter_nodal_field", "heat_reference_view_csr", "heat_decompose_partition",
     "heat_matrix_get_info", "heat_matrix_export_csr", "heat_matrix_export_maps", "heat_matrix_export_plan",
     "heat_matrix_export_red2orig", "heat_matrix_export_ilu0", "heat_matrix_free", "heat_vector_create", "heat_vector_size",
@@ -113,6 +113,7 @@ def lib():
     L.heat_solve_trajectory.argtypes = [vp, vp, vp, vp, C.POINTER(SolveOpts), C.c_int, C.c_int, C.POINTER(SolveInfo),
                                         C.POINTER(C.c_int)]
     L.heat_solve_host.argtypes = [vp, vp, vp, vp, C.POINTER(SolveOpts), C.POINTER(SolveInfo)]
+    L.heat_solve_host_batch.argtypes = [vp, vp, C.c_int, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(SolveOpts), C.POINTER(SolveInfo)]
     L.heat_spmv.argtypes = [vp, vp, vp, vp]
     L.heat_spmv_peer.argtypes = [vp, vp, vp, vp, C.c_int, dp, dp]
     L.heat_cg_iterations.argtypes = [vp, vp, vp, vp, C.POINTER(SolveOpts), C.c_int, C.POINTER(SolveInfo)]
@@ -485,6 +486,18 @@ class IO:
         o, info = self.solve_opts(**kw), SolveInfo()
         _check(lib().heat_solve_host(self.h, A.h, _as_pointer(b_host), _as_pointer(x_host), C.byref(o), C.byref(info)))
         return SolveResult(info.iters, bool(info.converged), info.achieved_tol, info.r0_norm, info.solve_ms)
+
+    def solve_host_batch(self, A: Matrix, b_hosts, x0_hosts, x_hosts, **kw):
+        """A sequence of solves with one matrix through (pinned) host buffers; copies of neighbouring systems overlap
+        each solve.  b_hosts / x_hosts: lists of numpy arrays or pinned torch CPU tensors; x0_hosts: list (entries may be
+        None = zero start) or None.  Returns one SolveResult per system."""
+        n = len(b_hosts)
+        o, infos = self.solve_opts(**kw), (SolveInfo * max(n, 1))()
+        arr = lambda lst: (C.c_void_p * max(n, 1))(*[(_as_pointer(t).value if t is not None else None) for t in lst])
+        bp, xp = arr(b_hosts), arr(x_hosts)
+        x0p = arr(x0_hosts) if x0_hosts is not None else None
+        _check(lib().heat_solve_host_batch(self.h, A.h, n, bp, x0p, xp, C.byref(o), infos))
+        return [SolveResult(i.iters, bool(i.converged), i.achieved_tol, i.r0_norm, i.solve_ms) for i in infos[:n]]
 
     def cg_iterations(self, A: Matrix, X: Vector, B: Vector, iters: int, **kw) -> SolveResult:
         o, info = self.solve_opts(**kw), SolveInfo()

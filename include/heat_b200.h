@@ -162,6 +162,15 @@ int  heat_solve_trajectory(heat_ctx *ctx, heat_matrix *A, heat_vector *X, const 
 int  heat_solve_host(heat_ctx *ctx, heat_matrix *A, const double *b_host, double *x_host,
                      const heat_solve_opts *opts, heat_solve_info *info);
 
+/* A SEQUENCE of such solves with one matrix (a loop around belosSolver with a new B per pass: time stepping, many
+ * right-hand sides).  System k takes b_hosts[k], starts from x0_hosts[k] (x0_hosts or x0_hosts[k] NULL: zero) and
+ * leaves its solution in x_hosts[k]; infos (may be NULL) gets one record per system.  Two staging sets and two copy
+ * streams: the inputs of system k+1 go up and the solution of system k-1 goes down WHILE system k is solved, so the
+ * stream runs at the device-resident rate.  Pinned host buffers are needed for the overlap (pageable ones work, serially). */
+int  heat_solve_host_batch(heat_ctx *ctx, heat_matrix *A, int count, const double *const *b_hosts,
+                           const double *const *x0_hosts, double *const *x_hosts, const heat_solve_opts *opts,
+                           heat_solve_info *infos);
+
 /* y = A x  (Tpetra::CrsMatrix::apply; explicit use at ExodusMatrixTest.cpp:101) incl. halo.      */
 int  heat_spmv(heat_ctx *ctx, heat_matrix *A, heat_vector *x, heat_vector *y);
 /* The same product through the PEER-MEMORY halo path, i.e. the very SpMV launch the multi-GPU CG loop makes

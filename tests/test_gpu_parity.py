@@ -143,6 +143,26 @@ def test_solve_host_end_to_end(hb, io, oracle):
     assert res.converged and np.abs(xh - x_ref).max() <= SOL_RTOL * np.abs(x_ref).max()
 
 
+def test_solve_host_batch_equals_single_calls(hb, io, oracle):
+    """heat_solve_host_batch (copies of neighbouring systems overlapped with each solve) returns, for every system, the
+    bits of a heat_solve_host call on it; zero start where no x0 is given."""
+    A, X, B, ref = _assemble_exo(hb, io, oracle, "tet-cube-heat", 1)
+    rng = np.random.default_rng(4)
+    bs = [ref.b * (1.0 + 0.1 * k) + rng.standard_normal(ref.n) * (k % 2) for k in range(5)]
+    x0s = [None, rng.standard_normal(ref.n), None, np.zeros(ref.n), rng.standard_normal(ref.n)]
+    outs = [np.empty(ref.n) for _ in bs]
+    rs = io.solve_host_batch(A, bs, x0s, outs, max_iters=400, tol=RES_TOL)
+    for k, b in enumerate(bs):
+        x = np.zeros(ref.n) if x0s[k] is None else x0s[k].copy()
+        r1 = io.solve_host(A, b, x, max_iters=400, tol=RES_TOL)
+        assert (rs[k].iters, rs[k].converged) == (r1.iters, r1.converged)
+        np.testing.assert_array_equal(outs[k], x)
+        x_ref = oracle.pcg(type(ref)(ref.n, ref.row_ptr, ref.col, ref.val, b, ref.red2orig, ref.node_bc),
+                           x0=np.zeros(ref.n) if x0s[k] is None else x0s[k], tol=RES_TOL, max_iters=400)[0]
+        assert np.abs(outs[k] - x_ref).max() <= SOL_RTOL * np.abs(x_ref).max()
+    assert io.solve_host_batch(A, [], None, []) == []
+
+
 def test_chebyshev_matches_oracle(hb, io, oracle):
     A, X, B, ref = _assemble_exo(hb, io, oracle, "bolted_bracket", 0)
     res = io.solve(A, X, B, prec=hb.PREC_CHEBYSHEV, cheb_degree=3, cheb_lambda_max=2.0, max_iters=500, tol=RES_TOL)
