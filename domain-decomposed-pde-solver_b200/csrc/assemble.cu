@@ -20,6 +20,7 @@
 #include "device_utils.cuh"
 #include "kernels.cuh"
 #include "sell_dict.cuh"
+#include "kuhn_rows_generated.cuh"
 
 namespace heat {
 
@@ -446,11 +447,12 @@ __device__ __forceinline__ void slot_delta(int slot, int &di, int &dj, int &dk) 
 }
 
 __device__ __forceinline__ void cube_row_ijk(const CubeGeom &c, int64_t l, int &i, int &j, int &k) {
-    const int64_t plane = c.plane;
-    k = (int)(l / plane) + c.k0;
-    const int64_t rem = l % plane;
-    j = (int)(rem / (c.nx - 2));
-    i = (int)(rem % (c.nx - 2)) + 1;
+    // local row ids fit 31 bits (api.cu checks n_owned + ghosts < 2^31): 32-bit divisions
+    const uint32_t plane = (uint32_t)c.plane, w = (uint32_t)(c.nx - 2), lu = (uint32_t)l;
+    const uint32_t kk = lu / plane, rem = lu - kk * plane, jj = rem / w;
+    k = (int)kk + c.k0;
+    j = (int)jj;
+    i = (int)(rem - jj * w) + 1;
 }
 // local column id of DOF node (i,j,k): owned rows first, then the lower ghost plane, then the upper
 __device__ __forceinline__ int32_t cube_local_col(const CubeGeom &c, int i, int j, int k) {
@@ -661,6 +663,12 @@ __device__ __forceinline__ void cube_row_values(const CubeGeom &c, int mode, int
     }
     const bool at_lo = i == 1, at_hi = i == c.nx - 2;
     const bool jlo = j >= 1, jhi = j <= c.ny - 2, klo = k >= 1, khi = k <= c.nz - 2;   // cells at j-1 / j / k-1 / k exist
+#ifndef HEAT_KUHN_FULL_ARITHMETIC
+    // the same 24 tets with the exact-zero operands of tet_G / K_ab eliminated and common subexpressions shared
+    // (tools/gen_kuhn_rows.py: ~125 fp64 operations + 15 divisions per row instead of ~1500; bit-identical values)
+    kuhn_row_p1_generated(X, Y, Z, jlo, jhi, klo, khi, at_lo, at_hi, v, bsum);
+    return;
+#endif
     // ascending element id: cells by (ck, cj, ci); the x-cells i-1 and i always exist for 1 <= i <= nx-2
     if (klo && jlo) { kuhn_cell_row<1, 1, 1>(X, Y, Z, at_lo, at_hi, v, bsum); kuhn_cell_row<0, 1, 1>(X, Y, Z, at_lo, at_hi, v, bsum); }
     if (klo && jhi) { kuhn_cell_row<1, 0, 1>(X, Y, Z, at_lo, at_hi, v, bsum); kuhn_cell_row<0, 0, 1>(X, Y, Z, at_lo, at_hi, v, bsum); }
@@ -735,6 +743,7 @@ __global__ void __launch_bounds__(kCubeWarps * 32, 2) cube_sell_kernel(CubeSellA
         const int64_t base = a.slice_ptr[s];
         const int w = (int)((a.slice_ptr[s + 1] - base) >> 6);
         int ghost = 0;
+        bool full = true;                                // every row of the slice stores all 15 stencil slots
 #pragma unroll 1
         for (int h = 0; h < 2; ++h) {
             const int rl = h * 32 + lane;
@@ -747,15 +756,28 @@ __global__ void __launch_bounds__(kCubeWarps * 32, 2) cube_sell_kernel(CubeSellA
                 cube_row_ijk(c, l, i, j, k);
                 double v[15], bsum;
                 cube_row_values(c, a.mode, i, j, k, v, bsum);
+                if (i >= 2 && i <= c.nx - 3 && j >= 1 && j <= c.ny - 2 && k >= c.k0 + 1 && k <= c.k1 - 2) {
+                    // all 15 neighbours are owned unknowns: column = row + the slot's constant offset, no per-slot tests
+                    const int32_t wd = c.nx - 2, pl = (int32_t)c.plane;
 #pragma unroll
-                for (int q = 0; q < 15; ++q) {
-                    int ii, jj, kk;
-                    if (cube_slot_stored(c, q, i, j, k, ii, jj, kk)) {
-                        const int32_t cc = cube_local_col(c, ii, jj, kk);
-                        ghost |= cc >= c.n_owned;
-                        tv[cnt * kSellChunk + rl] = v[q];
-                        tc[cnt * kSellChunk + rl] = cc;
-                        ++cnt;
+                    for (int q = 0; q < 15; ++q) {
+                        const int code = q > 7 ? q - 7 : 7 - q;
+                        const int32_t off = (code & 1) + ((code >> 1) & 1) * wd + ((code >> 2) & 1) * pl;
+                        tv[q * kSellChunk + rl] = v[q];
+                        tc[q * kSellChunk + rl] = (int32_t)l + (q > 7 ? off : -off);
+                    }
+                    cnt = 15;
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 15; ++q) {
+                        int ii, jj, kk;
+                        if (cube_slot_stored(c, q, i, j, k, ii, jj, kk)) {
+                            const int32_t cc = cube_local_col(c, ii, jj, kk);
+                            ghost |= cc >= c.n_owned;
+                            tv[cnt * kSellChunk + rl] = v[q];
+                            tc[cnt * kSellChunk + rl] = cc;
+                            ++cnt;
+                        }
                     }
                 }
                 a.diag[l] = v[7];
@@ -763,10 +785,20 @@ __global__ void __launch_bounds__(kCubeWarps * 32, 2) cube_sell_kernel(CubeSellA
                 a.b[l] = bsum;
                 a.rowlen[l] = (uint8_t)cnt;
             }
+            full = full && cnt == 15;
             for (; cnt < w; ++cnt) { tv[cnt * kSellChunk + rl] = 0.0; tc[cnt * kSellChunk + rl] = padcol; }
         }
         __syncwarp();
-        if (C8) {
+        if (C8 && __all_sync(0xffffffffu, full && !ghost)) {
+            // interior slice (all but ~3 % of a cube): all 64 rows store the 15 stencil slots in slot order and every
+            // column is owned, so entry k of every row has offset (column - row) of slot k — the table IS the 15
+            // offsets of lane 0's first row and every index is k; no look-up at all
+            if (lane < 15) tab[lane] = tc[lane * kSellChunk] - (int32_t)(s * kSellChunk);
+            for (int e = lane; e < 15 * kSellChunk / 4; e += 32)                       // idx[k][0..63] = k, 4 bytes per store
+                reinterpret_cast<uint32_t *>(ti)[e] = 0x01010101u * (uint32_t)(e / (kSellChunk / 4));
+            __syncwarp();
+            for (int t = lane; t < a.tpad; t += 32) a.tab[s * a.tpad + t] = t < 15 ? tab[t] : 0;
+        } else if (C8) {
             const int row0 = (int)(s * kSellChunk) + 2 * lane;
             int T = 0;
             bool ok = true;
