@@ -581,8 +581,9 @@ def run_ours(args):
                          "peak": peak, "unit": "GB/s", "frac": asm_bytes / (fill_ms * 1e-3) / 1e9 / peak if fill_ms else None,
                          "bytes_written_actual": mi.sell_padded_nnz * (8 + mi.col_index_bytes) + 25 * n_loc,
                          "matrix_bytes_resident": mi.matrix_bytes, "csr_resident": bool(mi.csr_resident),
-                         "note": "FP64-issue bound, not HBM bound: every row recomputes its 24 incident tets (~1500 DP instructions) so that "
-                                 "the values stay bit-identical to the oracle's"}
+                         "note": "write-only stream; the kernel is issue/latency bound at 16 warps per SM (124 registers, 102 KB of staging per CTA), "
+                                 "ncu: DRAM 38 % busy, fp64 pipe 39 %.  Every row evaluates its 24 incident tets (partially evaluated: ~125 fp64 "
+                                 "operations + 15 divisions) so that the values stay bit-identical to the oracle's"}
 
     # ---- (5) weak-scaling point (configs[4]) measured after the strong run on >1 GPU ------------------------
     weak = None
