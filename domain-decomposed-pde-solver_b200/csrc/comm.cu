@@ -12,6 +12,7 @@
 #include "comm.cuh"
 #include "kernels.cuh"
 #include "peer.cuh"
+#include "solve.cuh"
 
 namespace heat {
 
@@ -264,9 +265,14 @@ int peer_matrix_setup(heat_ctx *ctx, heat_matrix *A, bool need_z) {
         delete st;
         return 0;
     }
+    // Blocks that deliver the halo at the start of the producing kernel.  They finish later than the others by the time
+    // their share of the push takes (a gather + a remote store per entry), which is pure tail: with 64 blocks for the
+    // 522 240 entries of an interior slab the 8-GPU timeline showed update_p at 107 us against 84 us of streaming.  Up to
+    // one resident wave (4 CTAs per SM) now takes part, ~1 K entries each.
     const long long total = h.n_neighbors ? h.send_ptr[h.n_neighbors] : 0;
     int nb = (int)((total + 4 * 256 - 1) / (4 * 256));
-    nb = nb < 1 ? 1 : nb > 64 ? 64 : nb;
+    const int nb_cap = 4 * sm_count(ctx->device);
+    nb = nb < 1 ? 1 : nb > nb_cap ? nb_cap : nb;
     for (int b = 0; b < 4; ++b) st->push[b].n_blocks = nb;
     st->halo.n_nbr = h.n_neighbors;
     st->halo.flags = ctx->peer_arena + kPeerInboxWords;
