@@ -79,6 +79,7 @@ __global__ void __launch_bounds__(kBlock) cg_update_xr_kernel(int64_t n, double 
                                                               CgRec *H, double *S, int *I,
                                                               double *partials, int *counter) {
     pdl_wait();
+    pdl_launch_dependents();                 // every CTA of this grid has started: the next kernel's CTAs may move in as SMs free up
     if (cg_done(g)) return;
     const double pap = S[S_PAP0];
     if (!(pap > 0.0)) {                                   // Belos: "p.Ap <= 0" is a breakdown
@@ -107,7 +108,6 @@ __global__ void __launch_bounds__(kBlock) cg_update_xr_kernel(int64_t n, double 
         x[i] = xv; r[i] = rv;
         acc[0] += (dinv[i] * rv) * rv; acc[1] += rv * rv;
     }
-    pdl_launch_dependents();
     double *const out[2] = {&H[g.it + 1].rz, &H[g.it + 1].rr};
     if (grid_sum<2>(acc, partials, 0, gridDim.x, counter, out)) {
         H[g.it].alpha = alpha;
@@ -128,6 +128,7 @@ __global__ void __launch_bounds__(kBlock) cg_update_p_kernel(int64_t n, double *
                                                              const double *__restrict__ r,
                                                              const double *__restrict__ dinv, CgGate g) {
     pdl_wait();
+    pdl_launch_dependents();                 // every CTA of this grid has started: the next kernel's CTAs may move in as SMs free up
     if (cg_done(g)) return;
     CgGate nxt = g; nxt.it = g.it + 1;
     if (cg_done(nxt)) return;                              // converged: p is never used again
@@ -169,6 +170,7 @@ __global__ void __launch_bounds__(kBlock) cg_update_xr_peer_kernel(int64_t n, do
                                                                    unsigned long long seq_in,
                                                                    unsigned long long seq_out) {
     pdl_wait();
+    pdl_launch_dependents();                 // every CTA of this grid has started: the next kernel's CTAs may move in as SMs free up
     if (cg_done(g)) return;
     if (threadIdx.x == 0) HEAT_TRACE_MIN(g.it, 1, 0);
     __shared__ double sh[2];
@@ -207,7 +209,6 @@ __global__ void __launch_bounds__(kBlock) cg_update_xr_peer_kernel(int64_t n, do
         x[i] = xv; r[i] = rv;
         acc[0] += (dinv[i] * rv) * rv; acc[1] += rv * rv;
     }
-    pdl_launch_dependents();
     double *const out[2] = {S + S_TMP0, S + S_TMP1};
     if (grid_sum_block<2>(acc, partials, 0, gridDim.x, counter, out)) {
         if (threadIdx.x == 0) H[g.it].alpha = alpha;
@@ -258,6 +259,7 @@ __global__ void __launch_bounds__(kBlock) cg_update_p_peer_kernel(int64_t n, dou
                                                                   CgRec *H, int *I, PeerRed pr,
                                                                   unsigned long long seq_in, PeerPush push) {
     pdl_wait();
+    pdl_launch_dependents();                 // every CTA of this grid has started: the next kernel's CTAs may move in as SMs free up
     if (cg_done(g)) return;
     if (threadIdx.x == 0) HEAT_TRACE_MIN(g.it, 2, 0);
     __shared__ double sh[3];

@@ -221,6 +221,7 @@ sell_spmv_tma_kernel(const SliceMeta *__restrict__ meta, const int32_t *__restri
         if (ti < n_list) { issue(s); ++n_issued; }
 
     pdl_wait();                                                      // the producer of x (and of the gate's records) is complete
+    pdl_launch_dependents();                                         // all CTAs of this grid are resident: the next kernel's may move in as SMs free up
     if (gate_done(gate)) {                                           // frozen solve: drain the loads in flight, then leave
         for (int s = 0; s < n_issued; ++s) mbar_wait(bars + s, 0);
         return;
@@ -312,7 +313,6 @@ sell_spmv_tma_kernel(const SliceMeta *__restrict__ meta, const int32_t *__restri
         }
         if (++stage == NSTAGE) { stage = 0; parity ^= 1u; }
     }
-    pdl_launch_dependents();                                         // the next kernel's CTAs may move in as this grid drains
     if (DOT == 2) {
         double acc[2] = {dsum, ysum};
         double *const out[2] = {dot.out, dot.out + 1};
