@@ -6,7 +6,11 @@ EXTRA=-DHEAT_PEER_TRACE`).  Under torchrun, one rank per GPU:
 
 Every rank writes <prefix><rank>.txt: one line per iteration with, for SpMV / update_xr / update_p,
 {first block in, last block through its peer wait, last block out} in %globaltimer ns.
-`python tools/peer_trace.py --analyse gpurun_out/trace_ N` prints where an iteration's time goes."""
+`python tools/peer_trace.py --analyse gpurun_out/trace_ N` prints where an iteration's time goes.
+("last block past its wait" is the LATEST block to get past its peer wait: the vector kernels run their 1184 blocks
+in two resident waves, so for them that time is essentially the start of the second wave, not a wait for a peer.)
+The NVLink data counters of `nvidia-smi nvlink -gt d` are sampled around the timed solve where the driver exposes them
+(on the pods used here every link reads "N/A")."""
 import os
 import sys
 
