@@ -270,12 +270,15 @@ sell_spmv_tma_kernel(const SliceMeta *__restrict__ meta, const int32_t *__restri
                 __syncwarp();
                 halo_ready = true;
             }
+            // only the GHOST columns were written by other GPUs (through L2): owned entries keep the L1 path
 #pragma unroll 4
             for (int k = 0; k < kc; ++k) {
                 const double2 v = *reinterpret_cast<const double2 *>(vs + k * kSellChunk);
                 const int2 c = cols_at(k);
-                acc0 = fma(v.x, __ldcg(x + c.x), acc0);
-                acc1 = fma(v.y, __ldcg(x + c.y), acc1);
+                const double x0 = c.x < n_rows ? __ldg(x + c.x) : __ldcg(x + c.x);
+                const double x1 = c.y < n_rows ? __ldg(x + c.y) : __ldcg(x + c.y);
+                acc0 = fma(v.x, x0, acc0);
+                acc1 = fma(v.y, x1, acc1);
             }
         } else if (kc == KC) {
 #pragma unroll

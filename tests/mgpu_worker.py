@@ -76,7 +76,15 @@ def check_rows(io, A, ref, part, rank, world, tag):
     xg = hash_vector(np.arange(ref.n), 4242)
     np.testing.assert_array_equal(xv.numpy(), xg[owned], err_msg=f"{tag}: hash vector")
     io.spmv(A, xv, yv)
-    np.testing.assert_array_equal(yv.numpy(), O.spmv(ref, xg)[owned], err_msg=f"{tag}: spmv")
+    y_ref = O.spmv(ref, xg)
+    np.testing.assert_array_equal(yv.numpy(), y_ref[owned], err_msg=f"{tag}: spmv")
+    if os.environ.get("HEAT_COMM", "peer") != "nccl":
+        # the same product through the peer-memory halo path (the SpMV launch of the CG loop): same bits, and the fused
+        # global dot x.y to rounding
+        yv.fill(0.0)
+        xy, _ = io.spmv_peer(A, xv, yv, 2)
+        np.testing.assert_array_equal(yv.numpy(), y_ref[owned], err_msg=f"{tag}: peer-path spmv")
+        assert abs(xy - float(xg @ y_ref)) <= 1e-10 * max(1.0, float(np.abs(xg) @ np.abs(y_ref))), (tag, xy)
     return owned, ghost, nbr
 
 

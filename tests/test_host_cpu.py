@@ -319,3 +319,46 @@ def test_first_write_at_a_later_timestep_keeps_the_boundary_frame(hb, host_io, t
     np.testing.assert_array_equal(vals[2], f)
     np.testing.assert_array_equal(tw, [0, 0, 2])
     nc.close()
+
+
+def _write_nc(path, build):
+    from scipy.io import netcdf_file
+    nc = netcdf_file(path, "w", version=2)
+    build(nc)
+    nc.close()
+
+
+def test_malformed_exodus_files_fail_cleanly(hb, host_io, tmp_path):
+    """File-controlled sizes are validated before they are used as indices (advisor finding, round 1): a 1-D connect
+    table, a short `coord` array and a short ns_prop1 give an error, not an out-of-bounds read."""
+    def base(nc, n_nodes=4):
+        nc.createDimension("num_dim", 3); nc.createDimension("num_nodes", n_nodes); nc.createDimension("num_elem", 1)
+        nc.createDimension("num_el_blk", 1); nc.createDimension("num_el_in_blk1", 1); nc.createDimension("num_nod_per_el1", 4)
+
+    def flat_connect(nc):
+        base(nc)
+        for ax in "xyz":
+            v = nc.createVariable("coord" + ax, "d", ("num_nodes",)); v[:] = [0.0, 1.0, 0.0, 0.0]
+        nc.createDimension("four", 4)
+        c = nc.createVariable("connect1", "i", ("four",)); c[:] = [1, 2, 3, 4]            # not [elements][nodes]
+
+    def short_coord(nc):
+        base(nc)
+        nc.createDimension("short", 7)
+        v = nc.createVariable("coord", "d", ("short",)); v[:] = np.arange(7.0)             # 3 x 4 values expected
+        c = nc.createVariable("connect1", "i", ("num_el_in_blk1", "num_nod_per_el1")); c[:] = [[1, 2, 3, 4]]
+
+    def short_ns_prop(nc):
+        base(nc)
+        for ax in "xyz":
+            v = nc.createVariable("coord" + ax, "d", ("num_nodes",)); v[:] = [0.0, 1.0, 0.0, 0.0]
+        c = nc.createVariable("connect1", "i", ("num_el_in_blk1", "num_nod_per_el1")); c[:] = [[1, 2, 3, 4]]
+        nc.createDimension("num_node_sets", 3); nc.createDimension("one", 1); nc.createDimension("num_nod_ns1", 1)
+        p = nc.createVariable("ns_prop1", "i", ("one",)); p[:] = [7]                       # 3 nodesets, 1 id
+        ns = nc.createVariable("node_ns1", "i", ("num_nod_ns1",)); ns[:] = [1]
+
+    for name, build in (("flat", flat_connect), ("coord", short_coord), ("nsprop", short_ns_prop)):
+        path = str(tmp_path / f"bad_{name}.exo")
+        _write_nc(path, build)
+        with pytest.raises(hb.HeatError):
+            host_io.open(path, True)
