@@ -32,6 +32,28 @@ int vec_grid(int64_t n, int sm_count) {
     return grid_for(blocks, sm_count, 8);
 }
 
+// The streaming kernels loop grid-stride, so the grid should be exactly ONE resident wave: vec_grid assumes 8 blocks per
+// SM, but update_xr holds 4 (64 registers) and update_p 6 — a 1184-block grid then ran as 592 + 592 or 888 + 296, and
+// the partial second wave streamed with a third of the machine (visible at 1/8 of the problem: 150 us for 143 us of
+// traffic).  Occupancy is asked once per kernel and device.
+template <typename Kern>
+static int one_wave(Kern kern, int grid) {
+    struct Entry { const void *k; int dev; int cap; };
+    static std::vector<Entry> cache;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return grid;
+    for (const Entry &e : cache)
+        if (e.k == (const void *)kern && e.dev == dev) return grid < e.cap ? grid : e.cap;
+    int per_sm = 0, sms = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBlock, 0) != cudaSuccess || per_sm < 1 ||
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1) {
+        cudaGetLastError();
+        return grid;
+    }
+    cache.push_back(Entry{(const void *)kern, dev, per_sm * sms});
+    return grid < per_sm * sms ? grid : per_sm * sms;
+}
+
 // -------------------------------------------------------------------------------------------------
 // r = b - Ax ; z = D^-1 r ; q = z (p, or u of the single-reduce variant) ; H[0] = {r.z, 0, r.r}
 // -------------------------------------------------------------------------------------------------
@@ -118,6 +140,7 @@ __global__ void __launch_bounds__(kBlock) cg_update_xr_kernel(int64_t n, double 
 int launch_cg_update_xr(int64_t n, double *x, double *r, const double *p, const double *ap,
                         const double *dinv, CgGate gate, CgRec *H, double *S, int *I,
                         double *partials, int *counter, int grid, cudaStream_t st) {
+    grid = one_wave(cg_update_xr_kernel, grid);
     HEAT_CUDA(launch_kernel(cg_update_xr_kernel, grid, kBlock, 0, st, gate.pdl != 0, n, x, r, p, ap, dinv, gate, H, S, I, partials, counter));
     HEAT_LAUNCHED();
     return 0;
@@ -150,6 +173,7 @@ __global__ void __launch_bounds__(kBlock) cg_update_p_kernel(int64_t n, double *
 
 int launch_cg_update_p(int64_t n, double *p, const double *r, const double *dinv, CgGate gate,
                        int grid, cudaStream_t st) {
+    grid = one_wave(cg_update_p_kernel, grid);
     HEAT_CUDA(launch_kernel(cg_update_p_kernel, grid, kBlock, 0, st, gate.pdl != 0, n, p, (const double *)r, dinv, gate));
     HEAT_LAUNCHED();
     return 0;
@@ -220,6 +244,7 @@ __global__ void __launch_bounds__(kBlock) cg_update_xr_peer_kernel(int64_t n, do
 int launch_cg_update_xr_peer(int64_t n, double *x, double *r, const double *p, const double *ap, const double *dinv,
                              CgGate gate, CgRec *H, double *S, int *I, double *partials, int *counter, PeerRed pr,
                              unsigned long long seq_in, unsigned long long seq_out, int grid, cudaStream_t st) {
+    grid = one_wave(cg_update_xr_peer_kernel, grid);
     HEAT_CUDA(launch_kernel(cg_update_xr_peer_kernel, grid, kBlock, 0, st, gate.pdl != 0, n, x, r, p, ap, dinv, gate, H, S, I, partials, counter,
                             pr, seq_in, seq_out));
     HEAT_LAUNCHED();
@@ -415,6 +440,7 @@ int launch_cheb_xr_first_peer(bool last, int64_t n, double *x, const double *r_i
                               const double *dinv, double inv_theta, double *w, double *z_out, CgGate gate, CgRec *H, double *S, int *I,
                               double *partials, int *counter, PeerRed pr, unsigned long long seq_in, unsigned long long seq_out,
                               PeerPush push, int grid, cudaStream_t st) {
+    grid = one_wave(last ? cheb_xr_first_peer_kernel<true> : cheb_xr_first_peer_kernel<false>, grid);
     if (push.n_blocks > grid) push.n_blocks = grid;
     if (last) cheb_xr_first_peer_kernel<true><<<grid, kBlock, 0, st>>>(n, x, r_in, r_out, p, ap, dinv, inv_theta, w, z_out, gate, H, S, I, partials, counter, pr, seq_in, seq_out, push);
     else cheb_xr_first_peer_kernel<false><<<grid, kBlock, 0, st>>>(n, x, r_in, r_out, p, ap, dinv, inv_theta, w, z_out, gate, H, S, I, partials, counter, pr, seq_in, seq_out, push);
@@ -424,6 +450,7 @@ int launch_cheb_xr_first_peer(bool last, int64_t n, double *x, const double *r_i
 int launch_cheb_step_peer(bool last, int64_t n, const double *dinv, const double *r, const double *az, double c1, double c2,
                           const double *w_in, double *w_out, const double *z_in, double *z_out, CgGate gate, double *S, double *partials,
                           int *counter, PeerRed pr, unsigned long long seq_out, PeerPush push, int grid, cudaStream_t st) {
+    grid = one_wave(last ? cheb_step_peer_kernel<true> : cheb_step_peer_kernel<false>, grid);
     if (push.n_blocks > grid) push.n_blocks = grid;
     if (last) cheb_step_peer_kernel<true><<<grid, kBlock, 0, st>>>(n, dinv, r, az, c1, c2, w_in, w_out, z_in, z_out, gate, S, partials, counter, pr, seq_out, push);
     else cheb_step_peer_kernel<false><<<grid, kBlock, 0, st>>>(n, dinv, r, az, c1, c2, w_in, w_out, z_in, z_out, gate, S, partials, counter, pr, seq_out, push);
@@ -441,6 +468,7 @@ int trace_set_cg(TraceBuf *buf) {
 int launch_cg_update_p_peer(int64_t n, double *p_out, const double *p_in, const double *r, const double *dinv, const double *z,
                             CgGate gate, CgRec *H, int *I, PeerRed pr, unsigned long long seq_in, PeerPush push,
                             int grid, cudaStream_t st) {
+    grid = one_wave(cg_update_p_peer_kernel, grid);
     if (push.n_blocks > grid) push.n_blocks = grid;
     HEAT_CUDA(launch_kernel(cg_update_p_peer_kernel, grid, kBlock, 0, st, gate.pdl != 0, n, p_out, p_in, r, dinv, z, gate, H, I, pr, seq_in, push));
     HEAT_LAUNCHED();
