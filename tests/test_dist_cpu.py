@@ -18,6 +18,7 @@ from conftest import ROOT, mesh_path
 
 
 GETMATRIX = 2
+CHEBYSHEV = 3      # METIS partition, the fused Chebyshev(3)-PCG recurrence of cg.cu (numpy twin)
 
 
 def _worker(rank, world, port, name, partitioner, q):
@@ -35,7 +36,7 @@ def _worker(rank, world, port, name, partitioner, q):
             part = hb.node_owners(mesh.conn, mesh.num_nodes, epart, world)
         else:
             ref = O.assemble(mesh, O.GRAPH_LAPLACIAN)
-            part = hb.partition_rows(ref.row_ptr, ref.col, partitioner, world)
+            part = hb.partition_rows(ref.row_ptr, ref.col, hb.PART_METIS_KWAY if partitioner == CHEBYSHEV else partitioner, world)
         pl = hb.plan_build(ref.row_ptr, ref.col, part, world, rank)
         owned, ghost = pl["owned"], pl["ghost"]
         g2l = {int(g): i for i, g in enumerate(np.concatenate([owned, ghost]))}
@@ -91,6 +92,50 @@ def _worker(rank, world, port, name, partitioner, q):
             q.put((rank, 30, it_ref, abs(lam - lam_ref) / abs(lam_ref), None))
             dist.destroy_process_group()
             return
+        if partitioner == CHEBYSHEV:
+            # The iteration the CUDA path runs for Chebyshev(k)-PCG (cg.cu: cheb_xr_first / cheb_step / update_p(z)), kernel
+            # by kernel, with the halo of every SpMV input delivered before the SpMV and TWO reductions per iteration:
+            #   SpMV(p) + p.Ap | xr_first: x += a p, r' = r - a Ap, W = D^-1 r'/theta, Z0 = W | (SpMV(Z_{j-1}); step: W' = c1 W +
+            #   c2 D^-1 (r' - A Z_{j-1}), Z_j = Z_{j-1} + W') x (k-1), the last one with r'.Z, r'.r' | p' = Z + beta p
+            k, lmax, ratio = 3, 2.2, 30.0
+            ca, cb = lmax / ratio, 1.1 * lmax
+            delta, theta = 2.0 / (cb - ca), 0.5 * (cb + ca)
+            s1 = theta * delta
+            dinv = 1.0 / ref.csr().diagonal()[owned]
+            b = ref.b[owned]
+
+            def cheb(rv):
+                w = dinv * rv / theta
+                z = np.zeros(n_own + len(ghost)); z[:n_own] = w
+                rho = 1.0 / s1
+                for _ in range(1, k):
+                    rho_new = 1.0 / (2.0 * s1 - rho)
+                    az = spmv(z)                                   # halo of Z, then A Z
+                    w = rho_new * rho * w + 2.0 * rho_new * delta * (dinv * (rv - az))
+                    z = np.concatenate([z[:n_own] + w, z[n_own:]])  # out of place, like the ping-ponged buffers
+                    rho = rho_new
+                return z[:n_own]
+
+            X = np.zeros(n_own); r = b.copy()
+            z = cheb(r)
+            p = np.zeros(n_own + len(ghost)); p[:n_own] = z
+            rz, rr = allsum(r @ z, r @ r)
+            rr0, it = rr, 0
+            while rr > (1e-10 ** 2) * rr0 and it < 2000:
+                ap = spmv(p)
+                pap = allsum(p[:n_own] @ ap)[0]
+                alpha = rz / pap
+                X += alpha * p[:n_own]; r = r - alpha * ap          # r out of place
+                z = cheb(r)
+                rz_new, rr = allsum(r @ z, r @ r)
+                p = np.concatenate([z + (rz_new / rz) * p[:n_own], p[n_own:]])
+                rz = rz_new
+                it += 1
+            x_ref, it_ref, _, _ = O.pcg(ref, tol=1e-10, prec=O.PREC_CHEBYSHEV, cheb_degree=k, cheb_lambda_max=lmax, max_iters=2000)
+            err = np.abs(X - x_ref[owned]).max() / np.abs(x_ref).max()
+            q.put((rank, it, it_ref, float(err), None))
+            dist.destroy_process_group()
+            return
         # Chronopoulos-Gear PCG, one all-reduce per iteration
         dinv = 1.0 / ref.csr().diagonal()[owned]
         b = ref.b[owned]
@@ -121,7 +166,7 @@ def _worker(rank, world, port, name, partitioner, q):
 
 
 @pytest.mark.parametrize("name,partitioner", [("bolted_bracket", 1), ("bolted_bracket", 0), ("mitchell_tri", 1),
-                                              ("bolted_bracket", GETMATRIX)])
+                                              ("bolted_bracket", GETMATRIX), ("bolted_bracket", CHEBYSHEV)])
 def test_plan_drives_distributed_pcg_gloo(name, partitioner):
     world = 2
     ctx = mp.get_context("spawn")
