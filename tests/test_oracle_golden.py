@@ -4,6 +4,8 @@ The reference ships no golden vectors and cannot be built here ("parity unpinned
 binary), so the pins are: the hand-checkable 3x3 system, golden numbers produced by the
 independent numpy/scipy restatement + a sparse direct solve (tests/golden/make_golden.py),
 the analytic P1 solution, structural properties, and METIS known answers."""
+import os
+
 import numpy as np
 import pytest
 import scipy.sparse.linalg as spl
@@ -268,3 +270,41 @@ def test_cube_analytic_equals_explicit(oracle, dims, mode):
     c = oracle.cube_assemble(*dims, mode, copy=False)        # the zero-copy wrapper bench.py uses
     assert np.array_equal(c.val, a.val)
     c.free()
+
+
+@pytest.mark.parametrize("dims", [(3, 2, 2), (7, 5, 6), (12, 9, 11), (5, 4, 3)])
+def test_generated_kuhn_row_arithmetic_is_the_oracles(oracle, dims):
+    """The partially evaluated element arithmetic of the cube assembly kernel (tools/gen_kuhn_rows.py ->
+    csrc/kuhn_rows_generated.cuh: exact-zero operands eliminated, common subexpressions shared) evaluated in IEEE
+    doubles on the CPU gives every row of the oracle's system bit for bit — zero signs included — and the header in
+    the tree is what the generator emits today."""
+    import io
+    import struct
+    import sys as _sys
+    from contextlib import redirect_stderr, redirect_stdout
+    from conftest import ROOT
+    _sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import gen_kuhn_rows as G
+    nx, ny, nz = dims
+    ref = oracle.cube_assemble(nx, ny, nz, oracle.P1_FEM)
+    w = nx - 2
+    for r in range(ref.n):
+        i, j, k = r % w + 1, (r // w) % ny, r // (w * ny)
+        X = [-5.0 + 10.0 * (i - 1 + t) / (nx - 1) for t in range(3)]
+        Y = [-5.0 + 10.0 * (j - 1 + t) / (ny - 1) for t in range(3)]
+        Z = [-5.0 + 10.0 * (k - 1 + t) / (nz - 1) for t in range(3)]
+        v, b = G.evaluate(X, Y, Z, j >= 1, j <= ny - 2, k >= 1, k <= nz - 2, i == 1, i == nx - 2)
+        row = []
+        for s in range(15):
+            code, sg = (s - 7, 1) if s > 7 else (7 - s, -1)
+            ii, jj, kk = i + sg * (code & 1), j + sg * ((code >> 1) & 1), k + sg * ((code >> 2) & 1)
+            if 1 <= ii <= nx - 2 and 0 <= jj < ny and 0 <= kk < nz:
+                row.append(v[s])
+        assert np.array(row).tobytes() == ref.val[ref.row_ptr[r]:ref.row_ptr[r + 1]].tobytes(), (dims, r)
+        assert struct.pack("d", b) == struct.pack("d", ref.b[r]), (dims, r)
+    if dims == (7, 5, 6):
+        out = io.StringIO()
+        with redirect_stdout(out), redirect_stderr(io.StringIO()):
+            G.main()
+        with open(os.path.join(ROOT, "domain-decomposed-pde-solver_b200", "csrc", "kuhn_rows_generated.cuh")) as f:
+            assert f.read() == out.getvalue(), "kuhn_rows_generated.cuh is stale: re-run tools/gen_kuhn_rows.py"

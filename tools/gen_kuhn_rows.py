@@ -85,7 +85,9 @@ def tet(p):
     return G, rcp6(det)
 
 
-def main():
+def build():
+    """-> blocks: [(guard text, [(slot, di, kab)])] in ascending element id; expression nodes live in `defs`"""
+    nodes.clear(); defs.clear()                      # node numbering (hence the emitted names) starts afresh
     X = [sym(f"X[{t}]") for t in range(3)]
     Y = [sym(f"Y[{t}]") for t in range(3)]
     Z = [sym(f"Z[{t}]") for t in range(3)]
@@ -114,6 +116,53 @@ def main():
                         slot = 7 + code if di + dj + dk > 0 else 7 - code
                         stmts.append((slot, di, kab))
             blocks.append((f"{kguard} && {jguard}", stmts))
+    return blocks
+
+
+def evaluate(X, Y, Z, jlo, jhi, klo, khi, at_lo, at_hi):
+    """The generated row in Python floats (IEEE doubles, the same operations in the same order as the emitted CUDA):
+    -> (v[15], bsum).  tests/test_host_cpu.py holds it to the oracle's rows bit for bit, so the symbolic transformation is
+    checked on the CPU, independently of any GPU run."""
+    blocks = build()
+    env = {"klo": klo, "khi": khi, "jlo": jlo, "jhi": jhi}
+    vals = {}
+
+    def val(i):
+        if i in vals:
+            return vals[i]
+        k = defs[i]
+        if k[0] == "sym":
+            r = {"X": X, "Y": Y, "Z": Z}[k[1][0]][int(k[1][2])]
+        elif k[0] == "mul":
+            r = val(k[1]) * val(k[2])
+        elif k[0] == "add":
+            r = val(k[1]) + val(k[3]) if k[2] > 0 else val(k[1]) - val(k[3])
+        elif k[0] == "rcp6":
+            r = 1.0 / (6.0 * abs(val(k[1])))
+        elif k[0] == "mulc":
+            r = val(k[1]) * k[2]
+        vals[i] = r
+        return r
+    v, bsum = [0.0] * 15, 0.0
+    for guard, stmts in blocks:
+        a, b = guard.split(" && ")
+        if not (env[a] and env[b]):
+            continue
+        for slot, di, kab in stmts:
+            x = kab[0] * val(kab[1])
+            if di < 0 and at_lo:
+                sc = scale(kab, 1000.0)
+                bsum = bsum - (sc[0] * val(sc[1]))
+            elif di > 0 and at_hi:
+                sc = scale(kab, 100.0)
+                bsum = bsum - (sc[0] * val(sc[1]))
+            else:
+                v[slot] += x
+    return v, bsum
+
+
+def main():
+    blocks = build()
 
     # ---- emission ---------------------------------------------------------------------------------------------------
     uses = {}                                        # node id -> set of blocks using it (transitively)
