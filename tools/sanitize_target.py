@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Small pass over every kernel family for `compute-sanitizer --tool memcheck` (one GPU, seconds; no torch import)."""
+"""Small pass over every kernel family for `compute-sanitizer --tool memcheck` (one GPU, seconds; no torch import).
+(On the pool this round ran on, compute-sanitizer is closed; the script also serves as a plain 10-second tour of the API.)"""
 import os
 import sys
 
