@@ -850,8 +850,12 @@ int cube_assemble_sell(const CubeGeom &c, int mode, bool byte_index, heat_matrix
     const int64_t n = c.n_owned;
     const int64_t ns = (n + kSellChunk - 1) / kSellChunk;
     if (ns == 0) return 0;
-    cudaEvent_t e0, e1;
-    HEAT_CUDA(cudaEventCreate(&e0)); HEAT_CUDA(cudaEventCreate(&e1));
+    struct EventPair {                                   // destroyed on every exit path
+        cudaEvent_t a = nullptr, b = nullptr;
+        ~EventPair() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+    } ev;
+    HEAT_CUDA(cudaEventCreate(&ev.a)); HEAT_CUDA(cudaEventCreate(&ev.b));
+    cudaEvent_t e0 = ev.a, e1 = ev.b;
     A->n_slices = ns;
     HEAT_TRY(A->slice_ptr.alloc((size_t)ns + 1));
     HEAT_TRY(A->diag.alloc((size_t)n)); HEAT_TRY(A->dinv.alloc((size_t)n)); HEAT_TRY(A->sell_rowlen.alloc((size_t)n));
@@ -920,7 +924,6 @@ int cube_assemble_sell(const CubeGeom &c, int mode, bool byte_index, heat_matrix
     HEAT_CUDA(cudaStreamSynchronize(st));
     float fill_ms = 0.f;
     HEAT_CUDA(cudaEventElapsedTime(&fill_ms, e0, e1));
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
     A->assemble_fill_ms = fill_ms;
     if (h_maxtab > tpad) {          // guard: a slice saw more distinct offsets than the analytic bound
         A->sell_val.release(); A->sell_idx8.release(); A->sell_tab.release(); A->sell_col.release(); A->sell_rowlen.release();

@@ -14,6 +14,8 @@
 //   fused_update: beta, alpha from H[k], H[k-1] ; p = u + beta p ; s = w + beta s ;
 //                 x += alpha p ; r -= alpha s ; u = D^-1 r ; H[k+1].{rz,rr}
 //   spmv+dot    : w = A u ; H[k+1].delta = w.u     -> ONE all-reduce of {rz, delta, rr}
+#include <mutex>
+
 #include "device_utils.cuh"
 #include "kernels.cuh"
 #include "peer.cuh"
@@ -40,8 +42,10 @@ template <typename Kern>
 static int one_wave(Kern kern, int grid) {
     struct Entry { const void *k; int dev; int cap; };
     static std::vector<Entry> cache;
+    static std::mutex mu;                                // contexts on different GPUs may be driven by different threads
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return grid;
+    std::lock_guard<std::mutex> lock(mu);
     for (const Entry &e : cache)
         if (e.k == (const void *)kern && e.dev == dev) return grid < e.cap ? grid : e.cap;
     int per_sm = 0, sms = 0;
